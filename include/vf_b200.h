@@ -1,0 +1,140 @@
+/*
+ * vf_b200.h — C ABI of libvf_b200.so: the sm_100a CUDA kernels behind VariantFormer's
+ * batched-inference hot path.
+ *
+ * The reference has no FFI of its own: its boundary is a set of Python call sites that
+ * reach third-party native code (flash_attn, cuBLASLt via nn.Linear, ATen, HuggingFace
+ * tokenizers, samtools/bcftools subprocesses).  Each entry point below names the reference
+ * call site (file:line under the reference checkout) it replaces; INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative value on error;
+ *     vf_last_error() then returns a thread-local message.  Nothing throws, nothing
+ *     allocates device memory (callers own every buffer), nothing synchronises the device.
+ *   - all pointers are DEVICE pointers unless noted; `stream` is a cudaStream_t passed as void*.
+ *   - bf16 buffers are plain uint16 storage (__nv_bfloat16); "ld*" are row strides in ELEMENTS.
+ *   - re-entrant per stream; the only global state is read-only after first use.
+ */
+#ifndef VF_B200_H
+#define VF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VF_B200_ABI_VERSION 1
+
+const char* vf_last_error(void);
+int vf_abi_version(void);
+/* Device sanity: returns 0 iff the current device is compute capability 10.x; fills sm_count. */
+int vf_device_check(int* sm_count);
+
+/* ---- GEMM epilogues ------------------------------------------------------------------- */
+enum {
+    VF_EPI_BIAS_BF16 = 0,       /* out bf16 [M,N]   = A·W^T + bias                                     */
+    VF_EPI_BIAS_GEGLU_BF16 = 1, /* out bf16 [M,N/2] = (u+bu) * gelu_erf(g+bg); W/bias rows tile-interleaved:
+                                   rows [256j,256j+128) = u columns [128j,128j+128), next 128 rows = their gates */
+    VF_EPI_BIAS_RESID_F32 = 2,  /* out fp32 [M,N]   = A·W^T + bias + resid (out may alias resid); optional bf16 mirror */
+    VF_EPI_BIAS_F32 = 3,        /* out fp32 [M,N]   = A·W^T + bias; optional bf16 mirror                 */
+    VF_EPI_BIAS_GELU_BF16 = 4,  /* out bf16 [M,N]   = gelu_erf(A·W^T + bias)                             */
+    VF_EPI_COUNT = 5
+};
+
+/*
+ * D = A[M,K] (bf16, row stride lda) x W[N,K]^T (bf16 nn.Linear weight layout, row stride ldw), fp32
+ * accumulation on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
+ * Replaces nn.Linear under bf16 autocast (cuBLASLt): seq2reg/modules.py:140-147;
+ * seq2gene/modules/layers.py:63-80 + flash_attn MHA Wqkv/Wq/Wkv/out_proj;
+ * seq2gene/model_combined_modulator.py:502-507,610-612; seq2gene/modules/layers.py:1078-1087.
+ * N % 8 == 0, K % 8 == 0, 16-byte aligned operands.  bias/resid/out2 may be NULL.
+ */
+int vf_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int epilogue,
+                 const float* bias, const float* resid, int ldr, void* out, int ldo, void* out2_bf16, int ldo2,
+                 void* stream);
+
+/*
+ * Variable-length non-causal attention, one launch for all sequences and heads.
+ * q/k/v/o: bf16, head h at columns [h*head_dim, (h+1)*head_dim) of each row; packed QKV/KV buffers are
+ * addressed by passing offset base pointers.  cu_q/cu_k: int32 [n_seq+1] row prefix sums.
+ * tile_seq/tile_q0: int32 [n_tiles] query-tile map (sequence id, first query row) for block_m rows per tile.
+ * slopes: fp32 [heads] ALiBi slopes (bias -slope*|i + Sk - Sq - j|) or NULL.  head_dim in {32,48,64}.
+ * Replaces flash_attn_varlen_qkvpacked_func / flash_attn_varlen_kvpacked_func as called through
+ * flash_attn.modules.mha.MHA at seq2reg/modules.py:159-171 and seq2gene/modules/layers.py:372-467.
+ */
+int vf_attention_varlen(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
+                        const int32_t* cu_q, const int32_t* cu_k, const int32_t* tile_seq, const int32_t* tile_q0,
+                        int n_tiles, int block_m, int heads, int head_dim, const float* slopes, void* stream);
+
+/*
+ * CRE x reference-label cross-attention collapsed to the 9 cCRE classes (exact identity):
+ * q bf16 [n_rows, H*HD]; kv9 fp32 [9, 2*H*HD] = Wkv·Emb9 + b ((two,h,d) order); logc fp32 [n_seq,9] =
+ * log(#CREs of the class in the row's gene) (-inf when absent); row_seq int32 [n_rows].
+ * Replaces the crossMHA call of the CRE stream: seq2gene/modules/layers.py:142-150 with
+ * context = second_level_context_embedding(ref_labels) (model_combined_modulator.py:168,261-267).
+ */
+int vf_label_attention(const void* q, int ldq, const float* kv9, const float* logc, const int32_t* row_seq,
+                       int n_rows, int heads, int head_dim, void* out, int ldo, void* stream);
+
+/* nn.LayerNorm(eps) + optional exact GELU, fp32 [M,d] -> bf16 (seq2reg/modules.py:143-144;
+ * seq2gene/modules/layers.py:74-76; head LayerNorm+GELU :1080-1081). */
+int vf_layernorm(const float* x, int ldx, const float* gamma, const float* beta, int M, int d, float eps,
+                 void* out_bf16, int ldo, int act_gelu, void* stream);
+
+/* Valid-token counts per window from a pad mask (uint8, 1 = padding) [n_win, L]
+ * (flash_attn.bert_padding.unpad_input at seq2reg/modules.py:156-161). */
+int vf_window_lengths(const uint8_t* pad_mask, int n_win, int L, int32_t* lens, void* stream);
+/* Ordered compaction of valid tokens: cu int32 [n_win+1] -> ids/pos int32 [n_tok]. */
+int vf_compact_tokens(const int32_t* tokens, const uint8_t* pad_mask, const int32_t* cu, int n_win, int L,
+                      int32_t* out_ids, int32_t* out_pos, void* stream);
+/* x[t] = E[ids[t]] + PE[pos[t]] (pe may be NULL): seq2reg/model.py:214-220. */
+int vf_embed_tokens(const int32_t* ids, const int32_t* pos, const float* emb, const float* pe, int n_tok, int d,
+                    float* out, void* stream);
+/* Mean over each window's tokens (seq2reg/model.py:263-267); empty window -> NaN as upstream. */
+int vf_masked_meanpool(const float* x, int ldx, const int32_t* cu, int n_win, int d, void* out_bf16, float* out_f32,
+                       int ldo, void* stream);
+/* out[r] = idx[r] >= 0 ? table_a[idx[r]] : table_b[-idx[r]-1]  (registry-token prepend / tissue replication:
+ * seq2gene/modules/layers.py:508-521, model_combined_modulator.py:622-649; pool_outputs :391-392). */
+int vf_gather_rows(const float* table_a, int lda, const float* table_b, int ldb, const int32_t* idx, int n_rows, int d,
+                   float* out_f32, void* out_bf16, int ldo, void* stream);
+/* y = softplus(h·w + b) per row (h bf16): last Linear(emb,1)+Softplus of the head, layers.py:1084-1087. */
+int vf_head_out(const void* h_bf16, int ldh, const float* w, const float* b, int n_rows, int d, int softplus,
+                float* out, void* stream);
+int vf_cast_f32_to_bf16(const float* x, void* y_bf16, size_t n, void* stream);
+
+/* ---- stage 1: genotype -> IUPAC sequence -> BPE-500 tokens (integer work, bit-exact) -------------- */
+/*
+ * Per window w: slice [w0,w1) of the chromosome starting at genome + win_base[w], apply the sample's
+ * variants var_lo[w]..var_hi[w] (sorted by position; gt 0 skip / 1 het / 2 hom-alt): het SNP -> IUPAC code,
+ * hom SNP -> ALT, indel/MNP -> REF span replaced by ALT, overlapping or window-straddling records skipped;
+ * flags bit0 = reverse-complement the result, bit1 = SNP-only filter.
+ * out: uint8 [n_win, pitch]; out_len int32 [n_win]; err: device int32 flag (1 pitch overflow, 2 >2048 records).
+ * Replaces the `samtools faidx | bcftools consensus -H I -e 'ALT~"<.*>"'` subprocess pair per window
+ * (utils/data_process.py:17-101, :367-467) and utils/functions.py:129-172 (reverse_complement).
+ */
+int vf_encode_windows(const uint8_t* genome, const int64_t* win_base, const int32_t* w0, const int32_t* w1,
+                      const int32_t* var_lo, const int32_t* var_hi, const uint8_t* flags, const int32_t* v_pos,
+                      const int32_t* v_ref_len, const int32_t* v_alt_off, const int32_t* v_alt_len, const uint8_t* v_gt,
+                      const uint8_t* alt_pool, int n_win, int max_window, uint8_t* out, int64_t pitch, int32_t* out_len,
+                      int32_t* err, void* stream);
+/*
+ * BPE tokenisation of n_win byte sequences (upper-cased; non-IUPAC characters split words).
+ * merge_a/merge_b/merge_new: uint16 [n_merges] rank-ordered merge table.  out_tokens int32 [n_win, out_pitch]:
+ * the first min(count, out_cap) ids, remainder of the row zero (<pad>); out_count int32 [n_win] = untruncated
+ * token count; out_start (optional) int32 [n_win, start_pitch] = first base index of every token.
+ * scratch: uint16 [n_win, scratch_pitch], required when max_len > 8192.
+ * Replaces utils/seq.py:32-62 (BPEEncoder.normalize/encode -> HF tokenizers), :68-174 (token offsets) and the
+ * pad/truncate/chunk steps datasets/vcfdataset.py:198-217, :338-394.
+ */
+int vf_bpe_tokenize(const uint8_t* seq, int64_t pitch, const int32_t* len, int n_win, int max_len,
+                    const uint16_t* merge_a, const uint16_t* merge_b, const uint16_t* merge_new, int n_merges,
+                    uint16_t* scratch, int64_t scratch_pitch, int32_t* out_tokens, int out_pitch, int out_cap,
+                    int32_t* out_count, int32_t* out_start, int64_t start_pitch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VF_B200_H */

@@ -1,0 +1,337 @@
+// vf_elementwise.cu — the memory-bound glue of stages 2-4 (everything the reference
+// runs as separate ATen eager kernels): LayerNorm, token embedding + positional
+// encoding, window unpadding, masked mean-pool, stream assembly / row gathers, the
+// 9-class CRE x label cross-attention collapse and the final head dot + Softplus.
+// All kernels are warp-per-row with 16-byte accesses where the shape allows.
+#include "vf_common.cuh"
+#include "vf_internal.h"
+
+namespace vf {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------
+// LayerNorm (eps 1e-5, affine), fp32 in -> bf16 out, optional exact-erf GELU.
+// nn.LayerNorm sites: seq2reg/modules.py:143-144, seq2gene/modules/layers.py:74-76, :1080.
+// Exact two-pass statistics in fp32 (mean, then centred variance).
+// ---------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, int M, int d, float eps, __nv_bfloat16* __restrict__ out, int ldo,
+                 int act_gelu) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    const float* xr = x + (size_t)row * ldx;
+    __nv_bfloat16* orow = out + (size_t)row * ldo;
+    if constexpr (VEC) {
+        // d % 128 == 0 and d <= 2048: the whole row lives in registers (<= 16 float4 per lane)
+        float4 v[16];
+        const int nv = d >> 7;
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (i < nv) {
+                v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+                s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            }
+        const float mean = warp_sum(s) / (float)d;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (i < nv) {
+                const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+                q += (a * a + b * b) + (c * c + e * e);
+            }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)d + eps);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (i < nv) {
+                const int c0 = (i * 32 + lane) * 4;
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c0));
+                float y0 = (v[i].x - mean) * rstd * g.x + b.x, y1 = (v[i].y - mean) * rstd * g.y + b.y;
+                float y2 = (v[i].z - mean) * rstd * g.z + b.z, y3 = (v[i].w - mean) * rstd * g.w + b.w;
+                if (act_gelu) { y0 = gelu_erf(y0); y1 = gelu_erf(y1); y2 = gelu_erf(y2); y3 = gelu_erf(y3); }
+                uint2 pk; pk.x = pack_bf16x2(y0, y1); pk.y = pack_bf16x2(y2, y3);
+                *reinterpret_cast<uint2*>(orow + c0) = pk;
+            }
+    } else {
+        float s = 0.f;
+        for (int c = lane; c < d; c += 32) s += xr[c];
+        const float mean = warp_sum(s) / (float)d;
+        float q = 0.f;
+        for (int c = lane; c < d; c += 32) { const float a = xr[c] - mean; q += a * a; }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)d + eps);
+        for (int c = lane; c < d; c += 32) {
+            float y = (xr[c] - mean) * rstd * gamma[c] + beta[c];
+            if (act_gelu) y = gelu_erf(y);
+            orow[c] = __float2bfloat16_rn(y);
+        }
+    }
+}
+
+int layernorm(const float* x, int ldx, const float* gamma, const float* beta, int M, int d, float eps, void* out,
+              int ldo, int act_gelu, cudaStream_t s) {
+    if (M == 0) return 0;
+    const int rows_per_block = 8;
+    const int grid = (M + rows_per_block - 1) / rows_per_block;
+    const bool vec = (d % 128 == 0) && d <= 2048 && (ldx % 4 == 0) && (ldo % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
+    if (vec)
+        layernorm_kernel<true><<<grid, 256, 0, s>>>(x, ldx, gamma, beta, M, d, eps, (__nv_bfloat16*)out, ldo, act_gelu);
+    else
+        layernorm_kernel<false><<<grid, 256, 0, s>>>(x, ldx, gamma, beta, M, d, eps, (__nv_bfloat16*)out, ldo, act_gelu);
+    VF_LAUNCH_OK("layernorm_kernel launch");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// Window unpadding (flash_attn.bert_padding.unpad_input at seq2reg/modules.py:156-161):
+// valid tokens of each [L]-token window are compacted in order; `pos` keeps the
+// original in-window position for the positional encoding.  One warp per window.
+// ---------------------------------------------------------------------------------
+__global__ void window_lengths_kernel(const uint8_t* __restrict__ pad_mask, int n_win, int L, int* __restrict__ lens) {
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= n_win) return;
+    const int lane = threadIdx.x & 31;
+    int c = 0;
+    for (int i = lane; i < L; i += 32) c += pad_mask[(size_t)w * L + i] ? 0 : 1;
+    c = (int)warp_sum((float)c);
+    if (lane == 0) lens[w] = c;
+}
+
+__global__ void compact_tokens_kernel(const int* __restrict__ tokens, const uint8_t* __restrict__ pad_mask,
+                                      const int* __restrict__ cu, int n_win, int L, int* __restrict__ out_ids,
+                                      int* __restrict__ out_pos) {
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= n_win) return;
+    const int lane = threadIdx.x & 31;
+    int base = cu[w];
+    for (int i0 = 0; i0 < L; i0 += 32) {
+        const int i = i0 + lane;
+        const bool keep = i < L && pad_mask[(size_t)w * L + i] == 0;
+        const unsigned b = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int o = base + __popc(b & ((1u << lane) - 1));
+            out_ids[o] = tokens[(size_t)w * L + i];
+            out_pos[o] = i;
+        }
+        base += __popc(b);
+    }
+}
+
+int window_lengths(const uint8_t* pad_mask, int n_win, int L, int* lens, cudaStream_t s) {
+    if (n_win == 0) return 0;
+    window_lengths_kernel<<<(n_win + 7) / 8, 256, 0, s>>>(pad_mask, n_win, L, lens);
+    VF_LAUNCH_OK("window_lengths_kernel launch");
+    return 0;
+}
+int compact_tokens(const int* tokens, const uint8_t* pad_mask, const int* cu, int n_win, int L, int* out_ids,
+                   int* out_pos, cudaStream_t s) {
+    if (n_win == 0) return 0;
+    compact_tokens_kernel<<<(n_win + 7) / 8, 256, 0, s>>>(tokens, pad_mask, cu, n_win, L, out_ids, out_pos);
+    VF_LAUNCH_OK("compact_tokens_kernel launch");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// Token embedding + sinusoidal positional encoding (seq2reg/model.py:214-220):
+//   x[t] = E[id[t]] + PE[pos[t]]           (PE table precomputed exactly like :15-37)
+// ---------------------------------------------------------------------------------
+__global__ void embed_tokens_kernel(const int* __restrict__ ids, const int* __restrict__ pos,
+                                    const float* __restrict__ emb, const float* __restrict__ pe, int n_tok, int d,
+                                    float* __restrict__ out) {
+    const int dv = d >> 2;
+    const size_t total = (size_t)n_tok * dv;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i / dv), c = (int)(i % dv) * 4;
+        float4 e = __ldg(reinterpret_cast<const float4*>(emb + (size_t)ids[t] * d + c));
+        if (pe) {
+            const float4 p = __ldg(reinterpret_cast<const float4*>(pe + (size_t)pos[t] * d + c));
+            e.x += p.x; e.y += p.y; e.z += p.z; e.w += p.w;
+        }
+        *reinterpret_cast<float4*>(out + (size_t)t * d + c) = e;
+    }
+}
+
+int embed_tokens(const int* ids, const int* pos, const float* emb, const float* pe, int n_tok, int d, float* out,
+                 cudaStream_t s) {
+    VF_REQUIRE(d % 4 == 0, "embed_tokens: d must be a multiple of 4");
+    if (n_tok == 0) return 0;
+    const size_t total = (size_t)n_tok * (d / 4);
+    const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    embed_tokens_kernel<<<grid, 256, 0, s>>>(ids, pos, emb, pe, n_tok, d, out);
+    VF_LAUNCH_OK("embed_tokens_kernel launch");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// Masked mean over each window's valid tokens (seq2reg/model.py:263-267).
+// One CTA per window; 0/0 -> NaN for an empty window, as upstream.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+meanpool_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ cu, int d,
+                __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32, int ldo) {
+    const int w = blockIdx.x;
+    const int b = cu[w], e = cu[w + 1];
+    const float inv = 1.0f / (float)(e - b);        // inf for an empty window -> 0*inf = NaN
+    for (int c = threadIdx.x * 4; c < d; c += blockDim.x * 4) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = b; t < e; ++t) {
+            const float4 v = *reinterpret_cast<const float4*>(x + (size_t)t * ldx + c);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+        if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)w * ldo + c) = a;
+        if (out_bf16) {
+            uint2 pk; pk.x = pack_bf16x2(a.x, a.y); pk.y = pack_bf16x2(a.z, a.w);
+            *reinterpret_cast<uint2*>(out_bf16 + (size_t)w * ldo + c) = pk;
+        }
+    }
+}
+
+int masked_meanpool(const float* x, int ldx, const int* cu, int n_win, int d, void* out_bf16, float* out_f32, int ldo,
+                    cudaStream_t s) {
+    VF_REQUIRE(d % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0, "meanpool: d/ld must be multiples of 4");
+    if (n_win == 0) return 0;
+    meanpool_kernel<<<n_win, 128, 0, s>>>(x, ldx, cu, d, (__nv_bfloat16*)out_bf16, out_f32, ldo);
+    VF_LAUNCH_OK("meanpool_kernel launch");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// Row gather with two source tables: idx >= 0 -> table_a[idx], idx < 0 -> table_b[-idx-1].
+// Builds the gene stream (registry token of the tissue + gene-chunk embeddings shared by all
+// tissue copies: layers.py:508-521 + model_combined_modulator.py:622-649) and extracts the
+// registry rows at the end (pool_outputs :391-392).
+// ---------------------------------------------------------------------------------
+__global__ void gather_rows_kernel(const float* __restrict__ ta, int lda, const float* __restrict__ tb, int ldb,
+                                   const int* __restrict__ idx, int n_rows, int d, float* __restrict__ out_f32,
+                                   __nv_bfloat16* __restrict__ out_bf16, int ldo) {
+    const int dv = d >> 2;
+    const size_t total = (size_t)n_rows * dv;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / dv), c = (int)(i % dv) * 4;
+        const int j = idx[r];
+        const float4 v = (j >= 0) ? *reinterpret_cast<const float4*>(ta + (size_t)j * lda + c)
+                                  : *reinterpret_cast<const float4*>(tb + (size_t)(-j - 1) * ldb + c);
+        if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)r * ldo + c) = v;
+        if (out_bf16) {
+            uint2 pk; pk.x = pack_bf16x2(v.x, v.y); pk.y = pack_bf16x2(v.z, v.w);
+            *reinterpret_cast<uint2*>(out_bf16 + (size_t)r * ldo + c) = pk;
+        }
+    }
+}
+
+int gather_rows(const float* ta, int lda, const float* tb, int ldb, const int* idx, int n_rows, int d, float* out_f32,
+                void* out_bf16, int ldo, cudaStream_t s) {
+    VF_REQUIRE(d % 4 == 0 && lda % 4 == 0 && ldo % 4 == 0 && (tb == nullptr || ldb % 4 == 0),
+               "gather_rows: d/ld must be multiples of 4");
+    if (n_rows == 0) return 0;
+    const size_t total = (size_t)n_rows * (d / 4);
+    const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    gather_rows_kernel<<<grid, 256, 0, s>>>(ta, lda, tb, ldb, idx, n_rows, d, out_f32, (__nv_bfloat16*)out_bf16, ldo);
+    VF_LAUNCH_OK("gather_rows_kernel launch");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// CRE x label cross-attention, collapsed over the 9 reference-cCRE classes.
+// The reference attends every CRE query over K/V = Wkv·Emb9[label_j] for all C keys of
+// its gene (layers.py:142-150, model_combined_modulator.py:168,261-267); keys of one class
+// are identical, so softmax over C keys == softmax over the 9 class logits + log(count_c).
+// Exact identity (SURVEY App. D.12, fp32 check 4.8e-7).  fp32 CUDA-core math.
+//   q     bf16 [n_rows, H*HD]
+//   kv9   fp32 [9, 2*H*HD]   ((two, h, d) order like flash_attn's Wkv)
+//   logc  fp32 [n_seq, 9]    log(count of class c among the sequence's CREs), -inf if absent
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+label_attention_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const float* __restrict__ kv9,
+                       const float* __restrict__ logc, const int* __restrict__ row_seq, int n_rows, int H, int HD,
+                       float scale, __nv_bfloat16* __restrict__ out, int ldo) {
+    const int row = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int D = H * HD;
+    const float* lc = logc + (size_t)row_seq[row] * 9;
+    for (int h = warp; h < H; h += nw) {
+        const int c0 = h * HD;
+        const float q0 = lane < HD ? __bfloat162float(q[(size_t)row * ldq + c0 + lane]) : 0.f;
+        const float q1 = lane + 32 < HD ? __bfloat162float(q[(size_t)row * ldq + c0 + lane + 32]) : 0.f;
+        float logit[9];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+            const float* kr = kv9 + (size_t)c * 2 * D + c0;
+            float pdot = (lane < HD ? q0 * __ldg(kr + lane) : 0.f) + (lane + 32 < HD ? q1 * __ldg(kr + lane + 32) : 0.f);
+            pdot = warp_sum(pdot);
+            logit[c] = pdot * scale + lc[c];
+            mx = fmaxf(mx, logit[c]);
+        }
+        float den = 0.f, o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+            const float pc = __expf(logit[c] - mx);      // -inf logit -> 0
+            den += pc;
+            const float* vr = kv9 + (size_t)c * 2 * D + D + c0;
+            if (lane < HD) o0 += pc * __ldg(vr + lane);
+            if (lane + 32 < HD) o1 += pc * __ldg(vr + lane + 32);
+        }
+        const float inv = 1.0f / den;
+        if (lane < HD) out[(size_t)row * ldo + c0 + lane] = __float2bfloat16_rn(o0 * inv);
+        if (lane + 32 < HD) out[(size_t)row * ldo + c0 + lane + 32] = __float2bfloat16_rn(o1 * inv);
+    }
+}
+
+int label_attention(const void* q, int ldq, const float* kv9, const float* logc, const int* row_seq, int n_rows, int H,
+                    int HD, void* out, int ldo, cudaStream_t s) {
+    VF_REQUIRE(HD <= 64, "label_attention: head_dim must be <= 64");
+    if (n_rows == 0) return 0;
+    label_attention_kernel<<<n_rows, 256, 0, s>>>((const __nv_bfloat16*)q, ldq, kv9, logc, row_seq, n_rows, H, HD,
+                                                   1.0f / sqrtf((float)HD), (__nv_bfloat16*)out, ldo);
+    VF_LAUNCH_OK("label_attention_kernel launch");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// Last head layer: y = softplus(w·h + b)  (layers.py:1084-1087; Softplus beta=1, threshold=20).
+// ---------------------------------------------------------------------------------
+__global__ void head_out_kernel(const __nv_bfloat16* __restrict__ h, int ldh, const float* __restrict__ w,
+                                const float* __restrict__ b, int n_rows, int d, int softplus,
+                                float* __restrict__ out) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    float acc = 0.f;
+    for (int c = lane; c < d; c += 32) acc += __bfloat162float(h[(size_t)row * ldh + c]) * __ldg(w + c);
+    acc = warp_sum(acc) + b[0];
+    if (lane == 0) out[row] = softplus ? (acc > 20.f ? acc : log1pf(expf(acc))) : acc;
+}
+
+int head_out(const void* h, int ldh, const float* w, const float* b, int n_rows, int d, int softplus, float* out,
+             cudaStream_t s) {
+    if (n_rows == 0) return 0;
+    head_out_kernel<<<(n_rows + 7) / 8, 256, 0, s>>>((const __nv_bfloat16*)h, ldh, w, b, n_rows, d, softplus, out);
+    VF_LAUNCH_OK("head_out_kernel launch");
+    return 0;
+}
+
+// fp32 -> bf16 cast (weights at load time, contexts)
+__global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        y[i] = __float2bfloat16_rn(x[i]);
+}
+int cast_f32_to_bf16(const float* x, void* y, size_t n, cudaStream_t s) {
+    if (n == 0) return 0;
+    const int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    cast_bf16_kernel<<<grid, 256, 0, s>>>(x, (__nv_bfloat16*)y, n);
+    VF_LAUNCH_OK("cast_bf16_kernel launch");
+    return 0;
+}
+
+}  // namespace vf

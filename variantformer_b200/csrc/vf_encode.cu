@@ -1,0 +1,309 @@
+// vf_encode.cu — stage 1 on the GPU: genotype application (IUPAC diploid encoding)
+// and BPE-500 tokenisation of every cis-regulatory / gene window.  Integer, byte
+// and index work only: HBM/L2-bound, no tensor cores.  Bit-exact against
+// oracle/vf_oracle.c (which is pinned to the reference's utils/seq.py + tokenizers).
+//
+// Replaces, per window:
+//   `samtools faidx | bcftools consensus -H I` subprocess pairs  (utils/data_process.py:17-101, :367-467)
+//   reverse_complement                                          (utils/functions.py:129-172)
+//   BPEEncoder.normalize / encode (HF tokenizers BPE)            (utils/seq.py:32-62)
+//   __adjust_length / chunkify_data                              (datasets/vcfdataset.py:198-217, :338-394)
+#include "vf_common.cuh"
+#include "vf_internal.h"
+
+namespace vf {
+
+// ---------------------------------------------------------------------------------
+// encode_windows: reference slice + sample genotypes -> (optionally reverse-complemented) sequence
+// ---------------------------------------------------------------------------------
+constexpr int kMaxApplied = 2048;     // applied variants per window kept in shared memory
+constexpr int kEncSlice = 16384;      // reference bytes per CTA
+
+__device__ __forceinline__ uint8_t comp_base(uint8_t c) {
+    switch (c) {
+        case 'A': return 'T'; case 'a': return 't'; case 'C': return 'G'; case 'c': return 'g';
+        case 'G': return 'C'; case 'g': return 'c'; case 'T': return 'A'; case 't': return 'a';
+        case 'R': return 'Y'; case 'r': return 'y'; case 'Y': return 'R'; case 'y': return 'r';
+        case 'K': return 'M'; case 'k': return 'm'; case 'M': return 'K'; case 'm': return 'k';
+        case 'B': return 'V'; case 'b': return 'v'; case 'V': return 'B'; case 'v': return 'b';
+        case 'D': return 'H'; case 'd': return 'h'; case 'H': return 'D'; case 'h': return 'd';
+        default: return c;
+    }
+}
+__device__ __forceinline__ uint8_t iupac_het(uint8_t ref, uint8_t alt) {   // vepdataset.py:75-104
+    const int r = ref == 'A' ? 0 : ref == 'C' ? 1 : ref == 'G' ? 2 : ref == 'T' ? 3 : -1;
+    const int a = alt == 'A' ? 0 : alt == 'C' ? 1 : alt == 'G' ? 2 : alt == 'T' ? 3 : -1;
+    if (r < 0 || a < 0) return 'N';
+    const char tbl[17] = "AMRWMCSYRSGKWYKT";
+    return (uint8_t)tbl[r * 4 + a];
+}
+
+struct EncodeParams {
+    const uint8_t* genome;            // concatenated chromosomes, 1 byte/base as in the FASTA (case kept)
+    const int64_t* win_base;          // [n_win] offset of the window's chromosome in `genome`
+    const int32_t* w0; const int32_t* w1;         // [n_win] window [w0, w1) inside the chromosome
+    const int32_t* var_lo; const int32_t* var_hi; // [n_win] range of candidate variants (pos in [w0, w1))
+    const uint8_t* flags;             // [n_win] bit0 = reverse-complement, bit1 = SNP-only filter
+    const int32_t* v_pos; const int32_t* v_ref_len; const int32_t* v_alt_off; const int32_t* v_alt_len;
+    const uint8_t* v_gt;              // 0 skip, 1 het, 2 hom-alt
+    const uint8_t* alt_pool;
+    uint8_t* out; int64_t pitch;      // [n_win, pitch]
+    int32_t* out_len;                 // [n_win]
+    int32_t* err;                     // device error flag (1 = pitch overflow, 2 = too many variants)
+};
+
+__global__ void __launch_bounds__(256)
+encode_windows_kernel(const EncodeParams p) {
+    __shared__ int32_t s_vidx[kMaxApplied];     // applied variant index
+    __shared__ int32_t s_shift[kMaxApplied];    // cumulative (alt_len - ref_len) BEFORE this variant
+    __shared__ int s_n, s_total;
+    const int w = blockIdx.y;
+    const int w0 = p.w0[w], w1 = p.w1[w];
+    const int slice0 = w0 + blockIdx.x * kEncSlice;
+    if (slice0 >= w1 && !(blockIdx.x == 0)) return;
+    const uint8_t fl = p.flags[w];
+    const bool rc = fl & 1, snp_only = fl & 2;
+    if (threadIdx.x == 0) {
+        // sequential scan: which records are applied (overlap rule needs order) and where they land
+        int n = 0, cur = w0, shift = 0, bad = 0;
+        for (int i = p.var_lo[w]; i < p.var_hi[w]; ++i) {
+            if (p.v_gt[i] == 0) continue;
+            const int pos = p.v_pos[i], rl = p.v_ref_len[i], al = p.v_alt_len[i];
+            if (pos < cur || pos + rl > w1) continue;
+            if (snp_only && !(rl == 1 && al == 1)) continue;
+            if (n == kMaxApplied) { bad = 2; break; }
+            s_vidx[n] = i; s_shift[n] = shift; ++n;
+            shift += al - rl;
+            cur = pos + rl;
+        }
+        s_n = n; s_total = (w1 - w0) + shift;
+        if (bad) atomicMax(p.err, bad);
+        if (s_total > p.pitch) atomicMax(p.err, 1);
+        if (blockIdx.x == 0) p.out_len[w] = s_total;
+    }
+    __syncthreads();
+    const int n = s_n, total = s_total;
+    if (total > p.pitch) return;
+    const uint8_t* ref = p.genome + p.win_base[w];
+    uint8_t* out = p.out + (size_t)w * p.pitch;
+    const int slice1 = min(w1, slice0 + kEncSlice);
+    // (1) reference bytes of this slice that survive (not inside an applied record's REF span)
+    for (int x = slice0 + threadIdx.x; x < slice1; x += blockDim.x) {
+        // last applied variant with pos <= x
+        int lo = 0, hi = n;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (p.v_pos[s_vidx[mid]] <= x) lo = mid + 1; else hi = mid; }
+        int shift = 0;
+        if (lo > 0) {
+            const int v = s_vidx[lo - 1];
+            if (x < p.v_pos[v] + p.v_ref_len[v]) continue;              // replaced by the record's ALT
+            shift = s_shift[lo - 1] + p.v_alt_len[v] - p.v_ref_len[v];
+        }
+        const int o = x - w0 + shift;
+        const uint8_t b = ref[x];
+        if (rc) out[total - 1 - o] = comp_base(b); else out[o] = b;
+    }
+    // (2) ALT bytes of the applied records that start inside this slice
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const int v = s_vidx[k];
+        const int pos = p.v_pos[v];
+        if (pos < slice0 || pos >= slice1) continue;
+        const int al = p.v_alt_len[v], rl = p.v_ref_len[v];
+        const int o0 = pos - w0 + s_shift[k];
+        if (al == 1 && rl == 1) {
+            uint8_t a = p.alt_pool[p.v_alt_off[v]];
+            if (p.v_gt[v] == 1) {
+                uint8_t r = ref[pos];
+                if (r >= 'a' && r <= 'z') r -= 32;
+                a = iupac_het(r, a);
+            }
+            if (rc) out[total - 1 - o0] = comp_base(a); else out[o0] = a;
+        } else {
+            for (int j = 0; j < al; ++j) {
+                const uint8_t a = p.alt_pool[p.v_alt_off[v] + j];
+                if (rc) out[total - 1 - (o0 + j)] = comp_base(a); else out[o0 + j] = a;
+            }
+        }
+    }
+}
+
+int encode_windows(const uint8_t* genome, const int64_t* win_base, const int32_t* w0, const int32_t* w1,
+                   const int32_t* var_lo, const int32_t* var_hi, const uint8_t* flags, const int32_t* v_pos,
+                   const int32_t* v_ref_len, const int32_t* v_alt_off, const int32_t* v_alt_len, const uint8_t* v_gt,
+                   const uint8_t* alt_pool, int n_win, int max_window, uint8_t* out, int64_t pitch, int32_t* out_len,
+                   int32_t* err, cudaStream_t s) {
+    if (n_win == 0) return 0;
+    VF_REQUIRE(max_window > 0 && pitch >= max_window, "encode_windows: pitch %lld < max window %d", (long long)pitch,
+               max_window);
+    EncodeParams p{genome, win_base, w0, w1, var_lo, var_hi, flags, v_pos, v_ref_len, v_alt_off, v_alt_len, v_gt,
+                   alt_pool, out, pitch, out_len, err};
+    dim3 grid((max_window + kEncSlice - 1) / kEncSlice, n_win);
+    encode_windows_kernel<<<grid, 256, 0, s>>>(p);
+    VF_LAUNCH_OK("encode_windows_kernel launch");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// BPE-500 tokenisation by ascending-rank sweeps in the base-position domain.
+//
+// HF tokenizers merges the globally lowest-ranked adjacent pair first (leftmost first among
+// equals).  Because the token created by rank r can only be consumed by a merge of rank > r
+// (verified on the 482-entry table at load), processing ranks 0..R-1 in order and, within a
+// rank, all matches left to right (non-overlapping for self pairs) yields the identical
+// segmentation.  State: one uint16 per base position — token id at the
+// token's first base, DEAD on its remaining bases, SEP on non-IUPAC characters (word
+// boundaries, utils/seq.py:36-38).  Tokens are <= 8 bases long, so "next alive symbol" is a
+// scan over <= 7 DEAD slots and no compaction is needed between sweeps.
+// One CTA per window; symbols in shared memory when the window fits, else in a global
+// scratch row (gene windows: ~301 k symbols).  Ranks whose operands are absent from the
+// window (per-CTA occupancy counters) are skipped without touching the symbols.
+// ---------------------------------------------------------------------------------
+constexpr uint16_t kDead = 0xFFFF, kSep = 0xFFFE;
+constexpr int kBpeSmemSyms = 8192;    // windows up to this many symbols stay in shared memory
+constexpr int kMaxVocab = 512;
+
+struct BpeParams {
+    const uint8_t* seq; int64_t pitch; const int32_t* len;   // [n_win, pitch] bytes
+    const uint16_t* merge_a; const uint16_t* merge_b; const uint16_t* merge_new; int n_merges;
+    uint16_t* scratch; int64_t scratch_pitch;                 // [n_win, scratch_pitch] for long windows (may be null)
+    int32_t* out_tokens; int out_pitch; int out_cap;          // [n_win, out_pitch]; first out_cap tokens kept, rest of the row zeroed
+    int32_t* out_count;                                       // [n_win] total token count (before truncation)
+    int32_t* out_start; int64_t start_pitch;                  // optional [n_win, start_pitch]: first base of every token
+};
+
+__device__ __forceinline__ uint16_t base_symbol(uint8_t c) {
+    // upper-case + 14-letter alphabet A,B,C,D,G,H,K,M,R,S,T,V,W,Y -> ids 4..17; everything else separates words
+    if (c >= 'a' && c <= 'z') c -= 32;
+    switch (c) {
+        case 'A': return 4; case 'B': return 5; case 'C': return 6; case 'D': return 7; case 'G': return 8;
+        case 'H': return 9; case 'K': return 10; case 'M': return 11; case 'R': return 12; case 'S': return 13;
+        case 'T': return 14; case 'V': return 15; case 'W': return 16; case 'Y': return 17;
+        default: return kSep;
+    }
+}
+
+__global__ void bpe_tokenize_kernel(const BpeParams p) {
+    extern __shared__ uint16_t s_sym[];                 // kBpeSmemSyms (only used when the window fits)
+    __shared__ int s_cnt[kMaxVocab];                    // alive symbols per token id
+    __shared__ int s_warp_tot[32];
+    __shared__ int s_any;
+    const int w = blockIdx.x;
+    const int n = p.len[w];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const bool in_smem = n <= kBpeSmemSyms;
+    uint16_t* sym = in_smem ? s_sym : p.scratch + (size_t)w * p.scratch_pitch;
+    const uint8_t* src = p.seq + (size_t)w * p.pitch;
+
+    for (int i = tid; i < kMaxVocab; i += nt) s_cnt[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+        const uint16_t b = base_symbol(src[i]);
+        sym[i] = b;
+        if (b != kSep) atomicAdd(&s_cnt[b], 1);
+    }
+    __syncthreads();
+
+    for (int r = 0; r < p.n_merges; ++r) {
+        const uint16_t a = p.merge_a[r], b = p.merge_b[r], c = p.merge_new[r];
+        // uniform skip: all threads read the same counters (stable since the last barrier)
+        if (s_cnt[a] == 0 || s_cnt[b] == 0 || (a == b && s_cnt[a] < 2)) continue;
+        int merged = 0;
+        if (a != b) {
+            // matches of a non-self pair can never share a symbol: apply immediately
+            for (int i = tid; i < n; i += nt) {
+                if (sym[i] != a) continue;
+                int j = i + 1;
+                while (j < n && sym[j] == kDead) ++j;
+                if (j < n && sym[j] == b) { sym[i] = c; sym[j] = kDead; ++merged; }
+            }
+        } else {
+            // self pair: within a run of consecutive a's merge (1st,2nd), (3rd,4th), ... -> decide from the
+            // parity of the number of a's that precede i in its run; detect first, apply after a barrier
+            // (the tentative mark c|0x8000 is treated as `a` by concurrent scans, so marking is race-free)
+            const uint16_t mark = (uint16_t)(c | 0x8000);
+            if (tid == 0) s_any = 0;
+            __syncthreads();
+            for (int i = tid; i < n; i += nt) {
+                if (sym[i] != a) continue;
+                int k = 0, q = i - 1;
+                for (;;) {
+                    while (q >= 0 && sym[q] == kDead) --q;
+                    if (q < 0) break;
+                    const uint16_t sq = sym[q];
+                    if (sq != a && sq != mark) break;
+                    ++k; --q;
+                }
+                if (k & 1) continue;                     // i is the right half of the previous pair
+                int j = i + 1;
+                while (j < n && sym[j] == kDead) ++j;
+                if (j < n && (sym[j] == a || sym[j] == mark)) { sym[i] = mark; s_any = 1; }
+            }
+            __syncthreads();
+            if (s_any) {
+                for (int i = tid; i < n; i += nt) {
+                    if (sym[i] != mark) continue;
+                    int j = i + 1;
+                    while (j < n && sym[j] == kDead) ++j;
+                    sym[j] = kDead; sym[i] = c; ++merged;
+                }
+            }
+        }
+        if (merged) { atomicAdd(&s_cnt[c], merged); atomicSub(&s_cnt[a], merged); atomicSub(&s_cnt[b], merged); }
+        __syncthreads();
+    }
+
+    // ---- ordered compaction: each thread owns a contiguous segment ----
+    const int per = (n + nt - 1) / nt;
+    const int b0 = min(n, tid * per), b1 = min(n, b0 + per);
+    int mine = 0;
+    for (int i = b0; i < b1; ++i) mine += (sym[i] < kSep);
+    int incl = mine;
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int v = lane < (nt >> 5) ? s_warp_tot[lane] : 0;
+        int inc2 = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc2, o); if (lane >= o) inc2 += u; }
+        s_warp_tot[lane] = inc2 - v;                       // exclusive warp offsets
+        if (lane == 31) s_any = inc2;                      // grand total
+    }
+    __syncthreads();
+    int o = s_warp_tot[wid] + incl - mine;
+    const int total = s_any;
+    int32_t* out = p.out_tokens + (size_t)w * p.out_pitch;
+    int32_t* ost = p.out_start ? p.out_start + (size_t)w * p.start_pitch : nullptr;
+    for (int i = b0; i < b1; ++i) {
+        const uint16_t sy = sym[i];
+        if (sy < kSep) {
+            if (o < p.out_cap) out[o] = sy;
+            if (ost) ost[o] = i;
+            ++o;
+        }
+    }
+    for (int i = min(total, p.out_cap) + tid; i < p.out_pitch; i += nt) out[i] = 0;    // <pad> = 0
+    if (tid == 0) p.out_count[w] = total;
+}
+
+int bpe_tokenize(const uint8_t* seq, int64_t pitch, const int32_t* len, int n_win, int max_len,
+                 const uint16_t* merge_a, const uint16_t* merge_b, const uint16_t* merge_new, int n_merges,
+                 uint16_t* scratch, int64_t scratch_pitch, int32_t* out_tokens, int out_pitch, int out_cap,
+                 int32_t* out_count, int32_t* out_start, int64_t start_pitch, cudaStream_t s) {
+    if (n_win == 0) return 0;
+    VF_REQUIRE(out_cap <= out_pitch, "bpe_tokenize: out_cap %d > out_pitch %d", out_cap, out_pitch);
+    const bool needs_scratch = max_len > kBpeSmemSyms;
+    VF_REQUIRE(!needs_scratch || (scratch && scratch_pitch >= max_len),
+               "bpe_tokenize: windows longer than %d symbols need a scratch row of >= max_len uint16", kBpeSmemSyms);
+    VF_REQUIRE(out_start == nullptr || start_pitch >= max_len, "bpe_tokenize: start_pitch too small");
+    BpeParams p{seq, pitch, len, merge_a, merge_b, merge_new, n_merges, scratch, scratch_pitch,
+                out_tokens, out_pitch, out_cap, out_count, out_start, start_pitch};
+    const int threads = max_len <= 1024 ? 128 : 1024;
+    const size_t smem = (size_t)kBpeSmemSyms * sizeof(uint16_t);
+    bpe_tokenize_kernel<<<n_win, threads, smem, s>>>(p);
+    VF_LAUNCH_OK("bpe_tokenize_kernel launch");
+    return 0;
+}
+
+}  // namespace vf

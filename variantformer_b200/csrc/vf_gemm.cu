@@ -1,0 +1,414 @@
+// vf_gemm.cu — bf16 GEMM  D[M,N] = A[M,K] · W[N,K]^T  (+ fused epilogues) on the
+// 5th-gen tensor cores: TMA (128B-swizzled K-major tiles) -> shared memory ->
+// tcgen05.mma with fp32 accumulators in TMEM -> tcgen05.ld epilogue.
+//
+// Replaces every nn.Linear on the reference's hot path (cuBLASLt under autocast):
+//   seq2reg/modules.py:140-147 (Wqkv, out_proj, linear_geglu_1/2),
+//   seq2gene/modules/layers.py:63-80 (mixer/crossMHA projections, GeGLU FFN),
+//   seq2gene/model_combined_modulator.py:502-507 (gene_map, cre_map),
+//   seq2gene/modules/layers.py:1078-1087 (head Linear layers).
+//
+// Kernel shape: persistent, one CTA per SM, 192 threads:
+//   warp 0   : TMA producer (one elected lane)       smem ring of kStages x (A 128x64 + W 256x64) bf16
+//   warp 1   : TMEM allocator + tcgen05.mma issuer   UMMA 128x256x16, 4 per k-block
+//   warps 2-5: epilogue (TMEM lane quadrant = warp%4) bias / GeGLU / +residual, direct 16-byte stores
+// Two 256-column fp32 accumulators (all 512 TMEM columns) double-buffer the
+// epilogue of tile i against the mainloop of tile i+1.
+#include <cuda.h>
+#include <stdio.h>
+
+#include "vf_common.cuh"
+#include "vf_internal.h"
+
+namespace vf {
+
+constexpr int BM = 128, BN = 256, BK = 64, kStages = 4;
+constexpr int kGemmThreads = 192;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
+constexpr size_t kGemmSmem = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 /*barriers*/;
+
+struct GemmParams {
+    int M, N, K;
+    const float* bias;       // [N] (GeGLU: tile-interleaved like W) or nullptr
+    const float* resid;      // fp32 [M, ldr] or nullptr
+    int ldr;
+    void* out;               // bf16 or fp32, row stride ldo (elements)
+    int ldo;
+    __nv_bfloat16* out2;     // optional bf16 mirror of an fp32 output (row stride ldo2)
+    int ldo2;
+};
+
+// One 32-column slab of one accumulator row -> global memory.
+template <int EPI>
+__device__ __forceinline__ void epilogue_store(const GemmParams& p, int row, int col0, const float (&v)[32]) {
+    // col0 = first OUTPUT column of this slab; v already holds bias/activation-applied values
+    if constexpr (EPI == VF_EPI_BIAS_BF16 || EPI == VF_EPI_BIAS_GEGLU_BF16 || EPI == VF_EPI_BIAS_GELU_BF16) {
+        const int n_out = (EPI == VF_EPI_BIAS_GEGLU_BF16) ? p.N / 2 : p.N;
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + col0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (col0 + j * 8 + 8 <= n_out) {
+                uint4 q;
+                q.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]);
+                q.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
+                q.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]);
+                q.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
+                *reinterpret_cast<uint4*>(o + j * 8) = q;
+            }
+        }
+    } else {
+        float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (col0 + j * 4 + 4 <= p.N) {
+                *reinterpret_cast<float4*>(o + j * 4) = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+            }
+        }
+        if (p.out2) {
+            __nv_bfloat16* o2 = p.out2 + (size_t)row * p.ldo2 + col0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (col0 + j * 8 + 8 <= p.N) {
+                    uint4 q;
+                    q.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]);
+                    q.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
+                    q.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]);
+                    q.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
+                    *reinterpret_cast<uint4*>(o2 + j * 8) = q;
+                }
+            }
+        }
+    }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;                                  // kStages x 16 KB
+    uint8_t* smem_b = smem + kStages * kABytes;              // kStages x 32 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* full = bars;                 // [kStages]
+    uint64_t* empty = bars + kStages;      // [kStages]
+    uint64_t* tmem_full = bars + 2 * kStages;       // [2]
+    uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+    const int num_tiles = m_tiles * n_tiles;
+    const int k_blocks = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], kStageBytes);
+                    tma_load_2d(smem_a + stage * kABytes, &tmA, &full[stage], kb * BK, m0);
+                    tma_load_2d(smem_b + stage * kBBytes, &tmB, &full[stage], kb * BK, n0);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            int stage = 0; uint32_t phase = 0; int it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+                const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * kABytes));
+                    const uint64_t db = umma_desc_kmajor_sw128(smem_u32(smem_b + stage * kBBytes));
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // +32 bytes per UMMA_K step inside the 128-byte swizzle row (start address is in 16 B units)
+                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty[stage]);                      // frees the smem slot when these MMAs retire
+                    if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue warps =================
+        const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
+        const int lane = threadIdx.x & 31;
+        int it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
+            const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+            const int row = m0 + quad * 32 + lane;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+            if constexpr (EPI == VF_EPI_BIAS_GEGLU_BF16) {
+                // W rows are tile-interleaved: accumulator columns [0,128) = u, [128,256) = gate of the
+                // same 128 output columns (layers.py:159-160: u, gate = chunk(2); out = u * gelu(gate)).
+                const int out0 = (n0 / BN) * (BN / 2);
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    if (n0 + c * 32 >= p.N) break;
+                    uint32_t ru[32], rg[32];
+                    tmem_ld_32x32(t_row + c * 32, ru);
+                    tmem_ld_32x32(t_row + 128 + c * 32, rg);
+                    tmem_ld_wait();
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float u = __uint_as_float(ru[j]), g = __uint_as_float(rg[j]);
+                        if (p.bias) { u += __ldg(p.bias + n0 + c * 32 + j); g += __ldg(p.bias + n0 + 128 + c * 32 + j); }
+                        v[j] = u * gelu_erf(g);
+                    }
+                    if (row < p.M) epilogue_store<EPI>(p, row, out0 + c * 32, v);
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    const int col0 = n0 + c * 32;
+                    if (col0 >= p.N) break;
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_row + c * 32, r);
+                    tmem_ld_wait();
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (col0 + j + 4 <= p.N) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                            }
+                        }
+                    }
+                    if constexpr (EPI == VF_EPI_BIAS_GELU_BF16) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                    }
+                    if constexpr (EPI == VF_EPI_BIAS_RESID_F32) {
+                        if (row < p.M && p.resid) {
+                            const float* rr = p.resid + (size_t)row * p.ldr + col0;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                if (col0 + j + 4 <= p.N) {
+                                    const float4 b = *reinterpret_cast<const float4*>(rr + j);
+                                    v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                                }
+                            }
+                        }
+                    }
+                    if (row < p.M) epilogue_store<EPI>(p, row, col0, v);
+                }
+            }
+            // all TMEM reads of this accumulator are complete (wait::ld above) -> hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Debug cross-check path (VF_GEMM_DEBUG_SIMT=1): plain CUDA-core tiled GEMM into an
+// fp32 scratch + elementwise epilogue.  Exists only to bisect tcgen05/TMA descriptor
+// bugs on the GPU box; never selected by default and never a fallback.
+// ---------------------------------------------------------------------------------
+__global__ void gemm_simt_raw_kernel(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16* __restrict__ W,
+                                     int ldw, float* __restrict__ C, int M, int N, int K) {
+    __shared__ float sa[32][33], sw[32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int row = blockIdx.y * 32 + ty, col = blockIdx.x * 32 + tx;
+    float acc = 0.f;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        const int ka = k0 + tx;
+        sa[ty][tx] = (row < M && ka < K) ? __bfloat162float(A[(size_t)row * lda + ka]) : 0.f;
+        const int wr = blockIdx.x * 32 + ty;
+        sw[ty][tx] = (wr < N && ka < K) ? __bfloat162float(W[(size_t)wr * ldw + ka]) : 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) acc += sa[ty][k] * sw[tx][k];
+        __syncthreads();
+    }
+    if (row < M && col < N) C[(size_t)row * N + col] = acc;
+}
+
+template <int EPI>
+__global__ void gemm_simt_epilogue_kernel(const float* __restrict__ C, const GemmParams p) {
+    const int n_out = (EPI == VF_EPI_BIAS_GEGLU_BF16) ? p.N / 2 : p.N;
+    const size_t total = (size_t)p.M * n_out;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int row = (int)(i / n_out), col = (int)(i % n_out);
+        float v;
+        if constexpr (EPI == VF_EPI_BIAS_GEGLU_BF16) {
+            const int cu = (col / 128) * 256 + (col % 128), cg = cu + 128;   // tile-interleaved columns
+            float u = C[(size_t)row * p.N + cu], g = C[(size_t)row * p.N + cg];
+            if (p.bias) { u += p.bias[cu]; g += p.bias[cg]; }
+            v = u * gelu_erf(g);
+        } else {
+            v = C[(size_t)row * p.N + col];
+            if (p.bias) v += p.bias[col];
+            if (EPI == VF_EPI_BIAS_RESID_F32 && p.resid) v += p.resid[(size_t)row * p.ldr + col];
+            if (EPI == VF_EPI_BIAS_GELU_BF16) v = gelu_erf(v);
+        }
+        if constexpr (EPI == VF_EPI_BIAS_BF16 || EPI == VF_EPI_BIAS_GEGLU_BF16 || EPI == VF_EPI_BIAS_GELU_BF16) {
+            reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)row * p.ldo + col] = __float2bfloat16_rn(v);
+        } else {
+            reinterpret_cast<float*>(p.out)[(size_t)row * p.ldo + col] = v;
+            if (p.out2) p.out2[(size_t)row * p.ldo2 + col] = __float2bfloat16_rn(v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+// K-major bf16 matrix [rows, cols] with row stride ld (elements) -> TMA map with box {64, box_rows}, 128B swizzle.
+static int make_tmap_kmajor(CUtensorMap* tm, const void* base, int rows, int cols, int ld, int box_rows) {
+    PFN_encodeTiled enc = get_encode_fn();
+    VF_REQUIRE(enc, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
+    VF_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld % 8) == 0,
+               "GEMM operand must be 16-byte aligned with a row stride that is a multiple of 8 elements");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VF_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%d cols=%d ld=%d)", (int)r,
+               rows, cols, ld);
+    return 0;
+}
+
+static int g_num_sms = 0;
+static bool g_debug_simt = false;
+static bool g_inited = false;
+
+template <int EPI>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        VF_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)kGemmSmem));
+        attr_set = true;
+    }
+    const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    gemm_tcgen05_kernel<EPI><<<grid, kGemmThreads, kGemmSmem, s>>>(ta, tb, p);
+    VF_LAUNCH_OK("gemm_tcgen05_kernel launch");
+    return 0;
+}
+
+template <int EPI>
+static int launch_simt(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, const GemmParams& p,
+                       cudaStream_t s) {
+    float* scratch = nullptr;
+    VF_CUDA_OK(cudaMallocAsync(&scratch, (size_t)p.M * p.N * sizeof(float), s));
+    dim3 grid((p.N + 31) / 32, (p.M + 31) / 32), block(32, 32);
+    gemm_simt_raw_kernel<<<grid, block, 0, s>>>(A, lda, W, ldw, scratch, p.M, p.N, p.K);
+    VF_LAUNCH_OK("gemm_simt_raw_kernel launch");
+    gemm_simt_epilogue_kernel<EPI><<<1184, 256, 0, s>>>(scratch, p);
+    VF_LAUNCH_OK("gemm_simt_epilogue_kernel launch");
+    VF_CUDA_OK(cudaFreeAsync(scratch, s));
+    return 0;
+}
+
+int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int epi, const float* bias,
+              const float* resid, int ldr, void* out, int ldo, void* out2, int ldo2, cudaStream_t stream) {
+    if (!g_inited) {
+        int dev = 0;
+        VF_CUDA_OK(cudaGetDevice(&dev));
+        VF_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+        const char* e = getenv("VF_GEMM_DEBUG_SIMT");
+        g_debug_simt = e && e[0] == '1';
+        g_inited = true;
+    }
+    VF_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+    if (M == 0) return 0;
+    VF_REQUIRE(N % 8 == 0 && K % 8 == 0, "gemm: N and K must be multiples of 8 (N=%d K=%d)", N, K);
+    VF_REQUIRE(epi >= 0 && epi < VF_EPI_COUNT, "gemm: unknown epilogue %d", epi);
+    if (epi == VF_EPI_BIAS_GEGLU_BF16) VF_REQUIRE(N % 256 == 0, "gemm: GeGLU epilogue needs N %% 256 == 0 (N=%d)", N);
+    const int n_out = epi == VF_EPI_BIAS_GEGLU_BF16 ? N / 2 : N;
+    VF_REQUIRE(ldo >= n_out && (ldo % 8) == 0, "gemm: bad output stride %d", ldo);
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K; p.bias = bias; p.resid = resid; p.ldr = ldr; p.out = out; p.ldo = ldo;
+    p.out2 = reinterpret_cast<__nv_bfloat16*>(out2); p.ldo2 = ldo2;
+    if (g_debug_simt) {
+        const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(A);
+        const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(W);
+        switch (epi) {
+            case VF_EPI_BIAS_BF16: return launch_simt<VF_EPI_BIAS_BF16>(a, lda, w, ldw, p, stream);
+            case VF_EPI_BIAS_GEGLU_BF16: return launch_simt<VF_EPI_BIAS_GEGLU_BF16>(a, lda, w, ldw, p, stream);
+            case VF_EPI_BIAS_RESID_F32: return launch_simt<VF_EPI_BIAS_RESID_F32>(a, lda, w, ldw, p, stream);
+            case VF_EPI_BIAS_GELU_BF16: return launch_simt<VF_EPI_BIAS_GELU_BF16>(a, lda, w, ldw, p, stream);
+            default: return launch_simt<VF_EPI_BIAS_F32>(a, lda, w, ldw, p, stream);
+        }
+    }
+    CUtensorMap ta, tb;
+    if (make_tmap_kmajor(&ta, A, M, K, lda, BM)) return -1;
+    if (make_tmap_kmajor(&tb, W, N, K, ldw, BN)) return -1;
+    switch (epi) {
+        case VF_EPI_BIAS_BF16: return launch_tc<VF_EPI_BIAS_BF16>(ta, tb, p, stream);
+        case VF_EPI_BIAS_GEGLU_BF16: return launch_tc<VF_EPI_BIAS_GEGLU_BF16>(ta, tb, p, stream);
+        case VF_EPI_BIAS_RESID_F32: return launch_tc<VF_EPI_BIAS_RESID_F32>(ta, tb, p, stream);
+        case VF_EPI_BIAS_GELU_BF16: return launch_tc<VF_EPI_BIAS_GELU_BF16>(ta, tb, p, stream);
+        default: return launch_tc<VF_EPI_BIAS_F32>(ta, tb, p, stream);
+    }
+}
+
+}  // namespace vf
