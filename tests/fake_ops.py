@@ -1,0 +1,131 @@
+"""CPU stand-in for variantformer_b200.ops used ONLY by tests/test_engine_host_logic.py.
+
+It mimics each C-ABI kernel's contract (layouts, strides, in-place outputs, tile-interleaved GeGLU) with plain
+torch on the CPU so that the engine's *host-side bookkeeping* (unpadding, tile maps, gather indices, tissue
+stacking, label counts) can be checked against the oracle without a GPU.  It is not a fallback: nothing in
+variantformer_b200/ imports it, and the product raises without libvf_b200.so + a B200.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from variantformer_b200._lib import (EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GEGLU_BF16, EPI_BIAS_GELU_BF16,
+                                     EPI_BIAS_RESID_F32)
+
+LAUNCHES = 0
+
+
+def _store(out, val):
+    out.copy_(val.to(out.dtype))
+    return out
+
+
+def gemm(a, w, epilogue, bias=None, resid=None, out=None, out2=None):
+    y = a.float() @ w.float().t()
+    if bias is not None:
+        y = y + bias
+    if epilogue == EPI_BIAS_GEGLU_BF16:
+        N = w.shape[0]
+        t = y.view(y.shape[0], N // 256, 2, 128)
+        y = (t[:, :, 0] * F.gelu(t[:, :, 1])).reshape(y.shape[0], N // 2)
+        dt = torch.bfloat16
+    elif epilogue == EPI_BIAS_GELU_BF16:
+        y = F.gelu(y); dt = torch.bfloat16
+    elif epilogue == EPI_BIAS_BF16:
+        dt = torch.bfloat16
+    else:
+        if epilogue == EPI_BIAS_RESID_F32 and resid is not None:
+            y = y + resid
+        dt = torch.float32
+    if out2 is not None:
+        out2.copy_(y.to(torch.bfloat16))
+    if out is None:
+        return y.to(dt)
+    assert out.dtype == dt
+    return _store(out, y)
+
+
+class TileMap:
+    def __init__(self, q_lens, block_m, device):
+        self.block_m = block_m
+        self.lens = np.asarray(q_lens)
+
+
+def cu_seqlens(lens, device):
+    cu = np.zeros(len(lens) + 1, np.int32)
+    np.cumsum(np.asarray(lens, np.int64), out=cu[1:])
+    return torch.from_numpy(cu)
+
+
+def attention(q, k, v, cu_q, cu_k, tiles, heads, head_dim, slopes=None, out=None):
+    assert (np.diff(cu_q.numpy()) == tiles.lens).all(), "tile map does not describe the query sequences"
+    res = torch.empty(q.shape[0], heads * head_dim)
+    cq, ck = cu_q.tolist(), cu_k.tolist()
+    for b in range(len(cq) - 1):
+        qq = q[cq[b]:cq[b + 1]].float().reshape(-1, heads, head_dim)
+        kk = k[ck[b]:ck[b + 1]].float().reshape(-1, heads, head_dim)
+        vv = v[ck[b]:ck[b + 1]].float().reshape(-1, heads, head_dim)
+        s = torch.einsum("thd,shd->hts", qq, kk) / math.sqrt(head_dim)
+        if slopes is not None:
+            sq, sk = qq.shape[0], kk.shape[0]
+            i = torch.arange(sq)[:, None]; j = torch.arange(sk)[None, :]
+            s = s - slopes[:, None, None] * (i + sk - sq - j).abs()[None]
+        res[cq[b]:cq[b + 1]] = torch.einsum("hts,shd->thd", s.softmax(-1), vv).reshape(-1, heads * head_dim)
+    return _store(out, res) if out is not None else res.bfloat16()
+
+
+def label_attention(q, kv9, logc, row_seq, heads, head_dim, out=None):
+    D = heads * head_dim
+    qq = q.float().reshape(-1, heads, head_dim)
+    k9 = kv9[:, :D].reshape(9, heads, head_dim); v9 = kv9[:, D:].reshape(9, heads, head_dim)
+    s = torch.einsum("rhd,chd->rhc", qq, k9) / math.sqrt(head_dim) + logc[row_seq.long()][:, None, :]
+    res = torch.einsum("rhc,chd->rhd", s.softmax(-1), v9).reshape(-1, D)
+    return _store(out, res) if out is not None else res.bfloat16()
+
+
+def layernorm(x, gamma, beta, eps=1e-5, gelu=False, out=None):
+    y = F.layer_norm(x, (x.shape[1],), gamma, beta, eps)
+    if gelu:
+        y = F.gelu(y)
+    return _store(out, y) if out is not None else y.bfloat16()
+
+
+def window_lengths(pad_mask_u8):
+    return (pad_mask_u8 == 0).sum(1).int()
+
+
+def compact_tokens(tokens_i32, pad_mask_u8, cu, n_tok):
+    keep = pad_mask_u8 == 0
+    n, L = tokens_i32.shape
+    ids = tokens_i32[keep]; pos = torch.arange(L, dtype=torch.int32).expand(n, L)[keep]
+    assert ids.numel() == n_tok
+    return ids, pos
+
+
+def embed_tokens(ids, pos, emb, pe):
+    x = emb[ids.long()]
+    return x + pe[pos.long()] if pe is not None else x
+
+
+def masked_meanpool(x, cu, n_win, want_f32=False):
+    lens = torch.from_numpy(np.diff(cu.numpy())).long()
+    seg = torch.repeat_interleave(torch.arange(n_win), lens)
+    p = torch.zeros(n_win, x.shape[1]).index_add_(0, seg, x) / lens[:, None]
+    return (p.bfloat16(), p) if want_f32 else p.bfloat16()
+
+
+def gather_rows(table_a, table_b, idx, want_f32=True, want_bf16=False):
+    rows = [table_a[i] if i >= 0 else table_b[-i - 1] for i in idx.tolist()]
+    y = torch.stack(rows)
+    return (y if want_f32 else None), (y.bfloat16() if want_bf16 else None)
+
+
+def head_out(h_bf16, w, b, softplus=True):
+    y = h_bf16.float() @ w + b
+    return F.softplus(y) if softplus else y
+
+
+def cast_bf16(x):
+    return x.bfloat16()

@@ -1,0 +1,206 @@
+"""Per-kernel parity tests (GPU box).  Each CUDA kernel is called through the C ABI
+(variantformer_b200.ops -> libvf_b200.so) and compared with a plain torch fp32
+reference of the same op on the same bf16-rounded operands."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from variantformer_b200 import ops  # noqa: E402
+from variantformer_b200._lib import (EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GEGLU_BF16, EPI_BIAS_GELU_BF16,  # noqa: E402
+                                     EPI_BIAS_RESID_F32)
+from variantformer_b200.engine import interleave_geglu  # noqa: E402
+
+DEV = "cuda"
+
+
+def _describe_mismatch(got, want, tol):
+    err = (got - want).abs()
+    bad = err > tol
+    rows = bad.any(1).nonzero().flatten().tolist()
+    cols = bad.any(0).nonzero().flatten().tolist()
+    return (f"max err {err.max().item():.4g} (tol {tol:.3g}), {int(bad.sum())} bad of {bad.numel()}; "
+            f"bad rows[:16]={rows[:16]} (n={len(rows)}) bad cols[:16]={cols[:16]} (n={len(cols)}); "
+            f"got[0,:4]={got[0, :4].tolist()} want[0,:4]={want[0, :4].tolist()}")
+
+
+GEMM_SHAPES = [(128, 256, 64), (128, 256, 512), (300, 576, 192), (9, 3072, 1536), (1000, 512, 1024),
+               (4096, 4608, 1536), (12663, 1536, 1536), (777, 1536, 512)]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("epi", [EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_RESID_F32, EPI_BIAS_GELU_BF16])
+def test_gemm(M, N, K, epi):
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K + epi)
+    a = (torch.randn(M, K, generator=g) * 0.5).to(DEV).bfloat16()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV).bfloat16()
+    bias = torch.randn(N, generator=g).to(DEV)
+    resid = torch.randn(M, N, generator=g).to(DEV) if epi == EPI_BIAS_RESID_F32 else None
+    want = a.float() @ w.float().t() + bias
+    if resid is not None:
+        want = want + resid
+    if epi == EPI_BIAS_GELU_BF16:
+        want = F.gelu(want)
+    out2 = torch.empty(M, N, dtype=torch.bfloat16, device=DEV) if epi in (EPI_BIAS_F32, EPI_BIAS_RESID_F32) else None
+    got = ops.gemm(a, w, epi, bias=bias, resid=resid, out2=out2)
+    torch.cuda.synchronize()
+    tol = 2e-2 if got.dtype == torch.bfloat16 else 2e-3
+    assert torch.allclose(got.float(), want, atol=tol, rtol=tol), _describe_mismatch(got.float(), want, tol)
+    if out2 is not None:
+        assert torch.allclose(out2.float(), want, atol=2e-2, rtol=2e-2), _describe_mismatch(out2.float(), want, 2e-2)
+
+
+@pytest.mark.parametrize("M,K", [(128, 512), (1000, 1536), (333, 192)])
+def test_gemm_geglu(M, K):
+    N = 2048
+    g = torch.Generator(device="cpu").manual_seed(M + K)
+    a = (torch.randn(M, K, generator=g) * 0.5).to(DEV).bfloat16()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV).bfloat16()
+    bias = torch.randn(N, generator=g).to(DEV)
+    y = a.float() @ w.float().t() + bias
+    u, gate = y.chunk(2, -1)
+    want = u * F.gelu(gate)
+    got = ops.gemm(a, interleave_geglu(w), EPI_BIAS_GEGLU_BF16, bias=interleave_geglu(bias))
+    torch.cuda.synchronize()
+    assert got.shape == (M, N // 2)
+    assert torch.allclose(got.float(), want, atol=3e-2, rtol=2e-2), _describe_mismatch(got.float(), want, 3e-2)
+
+
+def test_gemm_inplace_residual_and_strided_output():
+    M, N, K = 515, 512, 1024
+    g = torch.Generator(device="cpu").manual_seed(5)
+    a = torch.randn(M, K, generator=g).to(DEV).bfloat16()
+    w = (torch.randn(N, K, generator=g) / 32).to(DEV).bfloat16()
+    x = torch.randn(M, N, generator=g).to(DEV)
+    want = a.float() @ w.float().t() + x
+    ops.gemm(a, w, EPI_BIAS_RESID_F32, resid=x, out=x)
+    torch.cuda.synchronize()
+    assert torch.allclose(x, want, atol=2e-3, rtol=2e-3), _describe_mismatch(x, want, 2e-3)
+    big = torch.zeros(M, 3 * N, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(a, w, EPI_BIAS_BF16, out=big[:, N:2 * N])
+    torch.cuda.synchronize()
+    assert torch.allclose(big[:, N:2 * N].float(), a.float() @ w.float().t(), atol=3e-2, rtol=2e-2)
+    assert big[:, :N].abs().max() == 0 and big[:, 2 * N:].abs().max() == 0
+
+
+def _ref_attention(q, k, v, lens_q, lens_k, H, hd, slopes):
+    out = torch.empty(q.shape[0], H * hd, device=q.device)
+    qs = ks = 0
+    for sq, sk in zip(lens_q, lens_k):
+        qq = q[qs:qs + sq].float().view(sq, H, hd); kk = k[ks:ks + sk].float().view(sk, H, hd)
+        vv = v[ks:ks + sk].float().view(sk, H, hd)
+        s = torch.einsum("thd,shd->hts", qq, kk) / math.sqrt(hd)
+        if slopes is not None:
+            i = torch.arange(sq, device=q.device)[:, None]; j = torch.arange(sk, device=q.device)[None, :]
+            s = s - slopes[:, None, None] * (i + sk - sq - j).abs()[None]
+        out[qs:qs + sq] = torch.einsum("hts,shd->thd", s.softmax(-1), vv).reshape(sq, H * hd)
+        qs += sq; ks += sk
+    return out
+
+
+@pytest.mark.parametrize("H,hd,alibi,block_m", [(8, 64, False, 64), (4, 48, True, 64), (32, 48, True, 128),
+                                                (2, 64, True, 128), (4, 32, False, 64)])
+def test_self_attention_packed_qkv(H, hd, alibi, block_m):
+    lens = [1, 97, 200, 64, 65, 201, 130, 7] if H < 32 else [201, 640, 33]
+    n, d = sum(lens), H * hd
+    g = torch.Generator(device="cpu").manual_seed(H * hd)
+    qkv = torch.randn(n, 3 * d, generator=g).to(DEV).bfloat16()
+    slopes = torch.tensor([2 ** (-8 * (h + 1) / H) for h in range(H)], device=DEV) if alibi else None
+    cu = ops.cu_seqlens(lens, DEV)
+    tiles = ops.TileMap(lens, block_m, DEV)
+    got = ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu, cu, tiles, H, hd, slopes)
+    want = _ref_attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], lens, lens, H, hd, slopes)
+    torch.cuda.synchronize()
+    assert torch.allclose(got.float(), want, atol=2e-2, rtol=2e-2), _describe_mismatch(got.float(), want, 2e-2)
+
+
+@pytest.mark.parametrize("H,hd", [(4, 48), (32, 48)])
+def test_cross_attention_stacked_queries(H, hd):
+    # queries of several tissue copies stacked on one "sequence" against the gene's single K/V
+    lens_q = [3 * 41, 5 * 17, 201 * 2]; lens_k = [300, 64, 1024]
+    d = H * hd
+    g = torch.Generator(device="cpu").manual_seed(11)
+    q = torch.randn(sum(lens_q), d, generator=g).to(DEV).bfloat16()
+    kv = torch.randn(sum(lens_k), 2 * d, generator=g).to(DEV).bfloat16()
+    got = ops.attention(q, kv[:, :d], kv[:, d:], ops.cu_seqlens(lens_q, DEV), ops.cu_seqlens(lens_k, DEV),
+                        ops.TileMap(lens_q, 128, DEV), H, hd, None)
+    want = _ref_attention(q, kv[:, :d], kv[:, d:], lens_q, lens_k, H, hd, None)
+    torch.cuda.synchronize()
+    assert torch.allclose(got.float(), want, atol=2e-2, rtol=2e-2), _describe_mismatch(got.float(), want, 2e-2)
+
+
+def test_label_attention_equals_full_attention_over_labels():
+    H, hd, C = 4, 48, [37, 120]
+    D = H * hd
+    g = torch.Generator(device="cpu").manual_seed(3)
+    q = torch.randn(sum(C), D, generator=g).to(DEV).bfloat16()
+    kv9 = torch.randn(9, 2 * D, generator=g).to(DEV)
+    labels = [torch.randint(0, 9, (c,), generator=g) for c in C]
+    labels[0][labels[0] == 4] = 5                                      # make one class absent in gene 0
+    counts = torch.stack([torch.bincount(l, minlength=9) for l in labels]).float()
+    logc = counts.log().to(DEV)
+    row_seq = torch.repeat_interleave(torch.arange(2), torch.tensor(C)).int().to(DEV)
+    got = ops.label_attention(q, kv9, logc, row_seq, H, hd)
+    kfull = torch.cat([kv9[l.to(DEV)] for l in labels])               # what the reference materialises
+    want = _ref_attention(q, kfull[:, :D], kfull[:, D:], C, C, H, hd, None)
+    torch.cuda.synchronize()
+    assert torch.allclose(got.float(), want, atol=1e-2, rtol=1e-2), _describe_mismatch(got.float(), want, 1e-2)
+
+
+@pytest.mark.parametrize("M,d,gelu", [(1000, 1536, False), (77, 512, False), (50, 192, True), (63, 1536, True)])
+def test_layernorm(M, d, gelu):
+    g = torch.Generator(device="cpu").manual_seed(d)
+    x = (torch.randn(M, d, generator=g) * 3 + 1).to(DEV)
+    gam = torch.randn(d, generator=g).to(DEV); bet = torch.randn(d, generator=g).to(DEV)
+    want = F.layer_norm(x, (d,), gam, bet, 1e-5)
+    if gelu:
+        want = F.gelu(want)
+    got = ops.layernorm(x, gam, bet, gelu=gelu)
+    torch.cuda.synchronize()
+    assert torch.allclose(got.float(), want, atol=2e-2, rtol=1e-2), _describe_mismatch(got.float(), want, 2e-2)
+
+
+def test_unpad_embed_meanpool():
+    n, L, d, V = 50, 200, 512, 500
+    g = torch.Generator(device="cpu").manual_seed(1)
+    tok = torch.randint(4, V, (n, L), generator=g, dtype=torch.int32)
+    mask = torch.rand(n, L, generator=g) < 0.4                      # arbitrary (non-prefix) masks
+    mask[3] = False; mask[4, 1:] = True
+    lens = (~mask).sum(1).numpy()
+    emb = torch.randn(V, d, generator=g).to(DEV); pe = torch.randn(L, d, generator=g).to(DEV)
+    tok_d, mask_d = tok.to(DEV), mask.to(torch.uint8).to(DEV)
+    got_lens = ops.window_lengths(mask_d)
+    assert got_lens.cpu().tolist() == lens.tolist()
+    cu = ops.cu_seqlens(lens, DEV)
+    ids, pos = ops.compact_tokens(tok_d, mask_d, cu, int(lens.sum()))
+    keep = ~mask
+    assert ids.cpu().tolist() == tok[keep].tolist()
+    assert pos.cpu().tolist() == torch.arange(L).expand(n, L)[keep].tolist()
+    x = ops.embed_tokens(ids, pos, emb, pe)
+    want = emb[tok_d[keep.to(DEV)].long()] + pe[pos.long()]
+    assert torch.equal(x, want)
+    pooled_bf, pooled = ops.masked_meanpool(x, cu, n, want_f32=True)
+    seg = torch.repeat_interleave(torch.arange(n), torch.from_numpy(lens)).to(DEV)
+    wantp = torch.zeros(n, d, device=DEV).index_add_(0, seg, want) / torch.from_numpy(lens).to(DEV)[:, None]
+    torch.cuda.synchronize()
+    assert torch.allclose(pooled, wantp, atol=1e-5, rtol=1e-5)
+    assert torch.allclose(pooled_bf.float(), wantp, atol=2e-2, rtol=1e-2)
+
+
+def test_gather_and_head_out():
+    g = torch.Generator(device="cpu").manual_seed(2)
+    ta = torch.randn(40, 192, generator=g).to(DEV); tb = torch.randn(63, 192, generator=g).to(DEV)
+    idx = torch.tensor([-1, 0, 1, 2, -63, 39, 5, -7], dtype=torch.int32)
+    of, ob = ops.gather_rows(ta, tb, idx.to(DEV), want_f32=True, want_bf16=True)
+    want = torch.stack([ta[i] if i >= 0 else tb[-i - 1] for i in idx.tolist()])
+    assert torch.equal(of, want) and torch.equal(ob, want.bfloat16())
+    h = torch.randn(21, 1536, generator=g).to(DEV).bfloat16()
+    w = (torch.randn(1536, generator=g) / 40).to(DEV); b = torch.randn(1, generator=g).to(DEV)
+    got = ops.head_out(h, w, b)
+    want = F.softplus(h.float() @ w + b)
+    torch.cuda.synchronize()
+    assert torch.allclose(got, want, atol=1e-4, rtol=1e-4)

@@ -1,0 +1,310 @@
+"""Forward schedule of the hot path on top of the C-ABI kernels.
+
+What runs here (reference sites in brackets):
+  seq2reg window encoder      [seq2reg/model.py:193-279, seq2reg/modules.py:149-191]
+  cre_map / gene_map          [seq2gene/model_combined_modulator.py:610-612]
+  registry token + tissue axis [layers.py:508-521, model_combined_modulator.py:622-666]
+  CombinedModulator           [model_combined_modulator.py:137-328, layers.py:88-165]
+  head + Softplus             [layers.py:1078-1087, 1113-1144]
+
+Schedule differences from the reference (results identical, oracle/model_fp32.py proves it):
+  * the CRE stream is computed once per gene, not once per (gene, tissue) — tissue only enters
+    through the registry token of the gene stream;
+  * all tissue copies of a gene share one K/V projection of the CRE stream: their queries are
+    stacked on the M axis of a single cross-attention problem;
+  * the CRE x label cross-attention is collapsed to the 9 label classes;
+  * only valid (unpadded) tokens are ever materialised.
+Numerics: bf16 GEMM/attention operands, fp32 accumulation, fp32 residual stream and LayerNorm.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GEGLU_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32
+from .utils.alibi import alibi_slopes
+
+NUM_REF_CRES = 9
+
+
+def sinusoidal_pe(d_model: int, length: int) -> torch.Tensor:
+    """Same arithmetic as seq2reg/model.py:15-37 (computed once on the host in fp32)."""
+    pe = torch.zeros(length, d_model)
+    position = torch.arange(0, length).unsqueeze(1).float()
+    div = torch.exp(torch.arange(0, d_model, 2, dtype=torch.float) * -(math.log(10000.0) / d_model))
+    pe[:, 0::2] = torch.sin(position * div)
+    pe[:, 1::2] = torch.cos(position * div)
+    return pe
+
+
+def interleave_geglu(w: torch.Tensor) -> torch.Tensor:
+    """Reorder linear_geglu_1 rows so each 256-row tile holds 128 `u` rows followed by their 128 `gate`
+    rows (u, gate = chunk(2, -1): layers.py:159-160).  Works for weights [2h, K] and biases [2h]."""
+    h = w.shape[0] // 2
+    assert h % 128 == 0, "GeGLU hidden size must be a multiple of 128"
+    u = w[:h].reshape(h // 128, 128, *w.shape[1:])
+    g = w[h:].reshape(h // 128, 128, *w.shape[1:])
+    return torch.cat([u, g], dim=1).reshape(w.shape).contiguous()
+
+
+class _Linear:
+    __slots__ = ("w", "b")
+
+    def __init__(self, sd, name, device, geglu=False):
+        w, b = sd[name + ".weight"].float(), sd[name + ".bias"].float()
+        if geglu:
+            w, b = interleave_geglu(w), interleave_geglu(b)
+        self.w = w.to(device=device, dtype=torch.bfloat16).contiguous()
+        self.b = b.to(device=device, dtype=torch.float32).contiguous()
+
+
+class _Norm:
+    __slots__ = ("g", "b")
+
+    def __init__(self, sd, name, device):
+        self.g = sd[name + ".weight"].to(device=device, dtype=torch.float32).contiguous()
+        self.b = sd[name + ".bias"].to(device=device, dtype=torch.float32).contiguous()
+
+
+class Workspace:
+    """Grow-only named device buffers, reused across layers and batches."""
+
+    def __init__(self, device):
+        self.device = device
+        self._buf = {}
+
+    def get(self, name, shape, dtype):
+        n = int(np.prod(shape))
+        b = self._buf.get(name)
+        if b is None or b.numel() < n or b.dtype != dtype:
+            b = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self._buf[name] = b
+        return b[:n].view(*shape)
+
+
+class Seq2RegWeights:
+    """Device copy of one Seq2RegPredictor (`use_context=False`, the configuration both tokenizers use)."""
+
+    def __init__(self, sd, prefix, hp, device):
+        if hp.get("use_context", False):
+            raise NotImplementedError("seq2reg use_context=True checkpoints are not supported on the B200 path yet")
+        self.d = hp["embedding_dim"]; self.H = hp["num_heads"]; self.L = hp["num_layers"]
+        self.hd = self.d // self.H
+        self.token_length = hp.get("token_length") or 200
+        self.emb = sd[prefix + "token_embedding.weight"].to(device=device, dtype=torch.float32).contiguous()
+        if hp.get("positional_encoding", "sinusoidal") == "sinusoidal":
+            self.pe = sinusoidal_pe(self.d, self.token_length).to(device)
+            self.slopes = None
+        else:
+            self.pe = None
+            self.slopes = alibi_slopes(self.H).to(device)
+        self.layers = []
+        for l in range(self.L):
+            p = f"{prefix}transformer_encoder.{l}."
+            self.layers.append(dict(
+                qkv=_Linear(sd, p + "MHA.Wqkv", device), out=_Linear(sd, p + "MHA.out_proj", device),
+                n1=_Norm(sd, p + "norm1", device), n2=_Norm(sd, p + "norm2", device),
+                g1=_Linear(sd, p + "linear_geglu_1", device, geglu=True), g2=_Linear(sd, p + "linear_geglu_2", device)))
+
+
+class Seq2GeneWeights:
+    def __init__(self, sd, cfg, device):
+        self.D = cfg["emb_dim"]; self.H = cfg["num_heads"]; self.NL = cfg["num_layers"]
+        self.hd = self.D // self.H
+        assert cfg.get("use_context", False) and not cfg.get("only_cross_attention", True) and \
+            cfg.get("gene_pooling") == "multi_registry" and not cfg.get("add_context_to_cres", False) and \
+            not cfg.get("use_res", False) and not cfg.get("cross_alibi", False) and \
+            cfg.get("use_bigger_head", False) and not cfg.get("multi_head", True), \
+            "only the configs/vf_model.yaml architecture variant is implemented on the B200 path"
+        self.slopes = alibi_slopes(self.H).to(device) if cfg.get("use_alibi", True) else None
+        self.registry = sd["start_tkn.registry_tokens.weight"].to(device=device, dtype=torch.float32).contiguous()
+        self.gene_map = _Linear(sd, "gene_map", device)
+        self.cre_map = _Linear(sd, "cre_map", device) if "cre_map.weight" in sd else None
+        emb9 = sd["combined_modulator.second_level_context_embedding.weight"].to(device=device, dtype=torch.bfloat16)
+
+        def layer(p, with_kv9):
+            L = dict(qkv=_Linear(sd, p + "mixer.MHA.Wqkv", device), out=_Linear(sd, p + "mixer.MHA.out_proj", device),
+                     q=_Linear(sd, p + "crossMHA.MHA.Wq", device), kv=_Linear(sd, p + "crossMHA.MHA.Wkv", device),
+                     out2=_Linear(sd, p + "crossMHA.MHA.out_proj", device),
+                     n1=_Norm(sd, p + "norm1", device), n2=_Norm(sd, p + "norm2", device), n3=_Norm(sd, p + "norm3", device),
+                     g1=_Linear(sd, p + "linear_geglu_1", device, geglu=True), g2=_Linear(sd, p + "linear_geglu_2", device))
+            if with_kv9:
+                # K/V of the 9 label embeddings depend on weights only: computed once here with the same GEMM
+                L["kv9"] = ops.gemm(emb9.contiguous(), L["kv"].w, EPI_BIAS_F32, bias=L["kv"].b)
+                L["kv"] = None
+            return L
+
+        self.cre_layers = [layer(f"combined_modulator.cre_layers.{i}.", True) for i in range(self.NL - 1)]
+        self.gene_layers = [layer(f"combined_modulator.gene_layers.{i}.", False) for i in range(self.NL)]
+        p = "tissue_heads.tissue_expressions."
+        self.h0 = _Linear(sd, p + "0", device); self.hn = _Norm(sd, p + "1", device); self.h4 = _Linear(sd, p + "4", device)
+        self.h6_w = sd[p + "6.weight"].to(device=device, dtype=torch.float32).reshape(-1).contiguous()
+        self.h6_b = sd[p + "6.bias"].to(device=device, dtype=torch.float32).contiguous()
+
+
+class Engine:
+    """Batched inference over a slab of genes: tokens -> expression + embeddings."""
+
+    def __init__(self, state_dict, cfg, seq2reg_hp, device="cuda", gene_seq2reg_hp=None):
+        self.device = torch.device(device)
+        self.cfg = dict(cfg)
+        with torch.cuda.device(self.device):
+            self.cre_tok = Seq2RegWeights(state_dict, "cre_tokenizer.", seq2reg_hp, self.device)
+            self.gene_tok = Seq2RegWeights(state_dict, "gene_tokenizer.", gene_seq2reg_hp or seq2reg_hp, self.device)
+            self.w = Seq2GeneWeights(state_dict, cfg, self.device)
+        self.ws = Workspace(self.device)
+
+    # ---------------------------------------------------------------- seq2reg
+    def seq2reg(self, W: Seq2RegWeights, tokens_i32, mask_u8, lens_host, tag):
+        """tokens/mask: device [n_win, L]; lens_host: numpy valid-token counts.  -> bf16 [n_win, d] mean-pooled."""
+        dev, ws = self.device, self.ws
+        n_win = tokens_i32.shape[0]
+        n_tok = int(lens_host.sum())
+        cu = ops.cu_seqlens(lens_host, dev)
+        ids, pos = ops.compact_tokens(tokens_i32, mask_u8, cu, n_tok)
+        x = ops.embed_tokens(ids, pos, W.emb, W.pe)
+        tiles = ops.TileMap(lens_host, 64, dev)
+        d, H, hd = W.d, W.H, W.hd
+        h = ws.get("r_h", (n_tok, d), torch.bfloat16)
+        qkv = ws.get("r_qkv", (n_tok, 3 * d), torch.bfloat16)
+        a = ws.get("r_a", (n_tok, d), torch.bfloat16)
+        x1 = ws.get("r_x1", (n_tok, d), torch.float32)
+        f = ws.get("r_f", (n_tok, W.layers[0]["g2"].w.shape[1]), torch.bfloat16)
+        for L in W.layers:
+            ops.layernorm(x, L["n1"].g, L["n1"].b, out=h)
+            ops.gemm(h, L["qkv"].w, EPI_BIAS_BF16, bias=L["qkv"].b, out=qkv)
+            ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu, cu, tiles, H, hd, W.slopes, out=a)
+            ops.gemm(a, L["out"].w, EPI_BIAS_RESID_F32, bias=L["out"].b, resid=x, out=x1)
+            ops.layernorm(x1, L["n2"].g, L["n2"].b, out=h)
+            ops.gemm(h, L["g1"].w, EPI_BIAS_GEGLU_BF16, bias=L["g1"].b, out=f)
+            ops.gemm(f, L["g2"].w, EPI_BIAS_RESID_F32, bias=L["g2"].b, resid=x, out=x)      # + layer input, in place
+        return ops.masked_meanpool(x, cu, n_win)
+
+    # ---------------------------------------------------------------- one encoder layer of seq2gene
+    def _layer(self, L, x, M, self_attn, cross_attn, tag, mirror=None):
+        """ContextFlashAttentionEncoderLayer on an unpadded fp32 stream x [M, D] (updated in place)."""
+        ws, D = self.ws, self.w.D
+        h = ws.get(tag + "_h", (M, D), torch.bfloat16)
+        qkv = ws.get(tag + "_qkv", (M, 3 * D), torch.bfloat16)
+        a = ws.get(tag + "_a", (M, D), torch.bfloat16)
+        x1 = ws.get(tag + "_x1", (M, D), torch.float32)
+        f = ws.get(tag + "_f", (M, L["g2"].w.shape[1]), torch.bfloat16)
+        ops.layernorm(x, L["n1"].g, L["n1"].b, out=h)
+        ops.gemm(h, L["qkv"].w, EPI_BIAS_BF16, bias=L["qkv"].b, out=qkv)
+        self_attn(qkv, a)
+        ops.gemm(a, L["out"].w, EPI_BIAS_RESID_F32, bias=L["out"].b, resid=x, out=x1)
+        ops.layernorm(x1, L["n2"].g, L["n2"].b, out=h)
+        q = qkv[:, :D]                                                  # reuse the qkv buffer for the cross query
+        ops.gemm(h, L["q"].w, EPI_BIAS_BF16, bias=L["q"].b, out=q)
+        cross_attn(q, a)
+        ops.gemm(a, L["out2"].w, EPI_BIAS_RESID_F32, bias=L["out2"].b, resid=x1, out=x1)
+        ops.layernorm(x1, L["n3"].g, L["n3"].b, out=h)
+        ops.gemm(h, L["g1"].w, EPI_BIAS_GEGLU_BF16, bias=L["g1"].b, out=f)
+        ops.gemm(f, L["g2"].w, EPI_BIAS_RESID_F32, bias=L["g2"].b, resid=x, out=x, out2=mirror)
+
+    # ---------------------------------------------------------------- full forward on a slab of genes
+    @torch.no_grad()
+    def forward_tokens(self, cre_tokens, cre_masks, gene_tokens, gene_masks, tissues, ref_labels,
+                       cre_token_position=None, gene_token_position=None):
+        """Lists (one entry per gene) of: cre_tokens [C,L] int, cre_masks [C,L] bool (True = pad), gene_tokens
+        [G,L], gene_masks [G,L], tissues [T] int, ref_labels [C] int (CPU or CUDA tensors).
+        -> dict(pred fp32 [sum T], emb fp32 [sum T, D], T list, optional token embeddings)."""
+        dev, w, ws = self.device, self.w, self.ws
+        B = len(cre_tokens)
+        D, H, hd = w.D, w.H, w.hd
+        C = np.array([t.shape[0] for t in cre_tokens]); G = np.array([t.shape[0] for t in gene_tokens])
+        T = np.array([len(t) for t in tissues])
+
+        def stage(tok_list, mask_list):
+            tok = torch.cat([t.reshape(-1, t.shape[-1]) for t in tok_list]).to(torch.int32)
+            msk = torch.cat([m.reshape(-1, m.shape[-1]) for m in mask_list]).to(torch.uint8)
+            if tok.is_cuda:
+                lens = ops.window_lengths(msk).cpu().numpy().astype(np.int64)
+                return tok, msk, lens
+            lens = (msk == 0).sum(1).numpy().astype(np.int64)
+            return (tok.pin_memory().to(dev, non_blocking=True), msk.pin_memory().to(dev, non_blocking=True), lens)
+
+        ctok, cmsk, clens = stage(cre_tokens, cre_masks)
+        gtok, gmsk, glens = stage(gene_tokens, gene_masks)
+
+        # ---- stage 2: window encoders ----
+        cre_pooled = self.seq2reg(self.cre_tok, ctok, cmsk, clens, "cre")           # bf16 [sum C, d_r]
+        gene_pooled = self.seq2reg(self.gene_tok, gtok, gmsk, glens, "gene")        # bf16 [sum G, d_r]
+        nC, nG = int(C.sum()), int(G.sum())
+        cre_bf = ws.get("cre_bf", (nC, D), torch.bfloat16)                           # bf16 mirror = cross-attn context
+        if w.cre_map is not None:
+            cx = ops.gemm(cre_pooled, w.cre_map.w, EPI_BIAS_F32, bias=w.cre_map.b, out2=cre_bf)
+        else:
+            raise NotImplementedError("token_dim == emb_dim (no cre_map) is not wired on the B200 path")
+        gene_emb = ops.gemm(gene_pooled, w.gene_map.w, EPI_BIAS_F32, bias=w.gene_map.b)
+
+        # ---- gene stream: [registry(tissue); gene chunks] per (gene, tissue) ----
+        g_off = np.concatenate([[0], np.cumsum(G)])
+        idx, seq_lens = [], []
+        for g in range(B):
+            tis = tissues[g].detach().cpu().numpy().astype(np.int64).reshape(-1)
+            body = np.arange(g_off[g], g_off[g + 1], dtype=np.int64)
+            for t in tis:
+                idx.append(np.concatenate([[-(t + 1)], body]))
+                seq_lens.append(G[g] + 1)
+        idx = np.concatenate(idx).astype(np.int32)
+        Mg = int(idx.shape[0])
+        gx, _ = ops.gather_rows(gene_emb, w.registry, torch.from_numpy(idx).to(dev, non_blocking=True))
+        seq_lens = np.asarray(seq_lens)
+        cu_gseq = ops.cu_seqlens(seq_lens, dev)                       # one sequence per (gene, tissue): self-attention
+        cu_gq = ops.cu_seqlens(T * (G + 1), dev)                      # one "sequence" per gene: stacked cross queries
+        cu_cre = ops.cu_seqlens(C, dev)
+        tiles_gself = ops.TileMap(seq_lens, 64, dev)
+        tiles_gcross = ops.TileMap(T * (G + 1), 128, dev)
+        tiles_cself = ops.TileMap(C, 128 if C.max() > 256 else 64, dev)
+        row_seq = torch.from_numpy(np.repeat(np.arange(B), C).astype(np.int32)).to(dev, non_blocking=True)
+        lab = torch.cat([l.reshape(-1) for l in ref_labels]).detach().cpu().numpy().astype(np.int64)
+        counts = np.zeros((B, NUM_REF_CRES), np.float64)
+        np.add.at(counts, (np.repeat(np.arange(B), C), lab), 1.0)
+        with np.errstate(divide="ignore"):
+            logc = torch.from_numpy(np.log(counts).astype(np.float32)).to(dev, non_blocking=True)
+        kv = ws.get("g_kv", (nC, 2 * D), torch.bfloat16)
+
+        def gene_self(qkv, out):
+            ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], cu_gseq, cu_gseq, tiles_gself, H, hd, w.slopes, out=out)
+
+        def cre_self(qkv, out):
+            ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], cu_cre, cu_cre, tiles_cself, H, hd, w.slopes, out=out)
+
+        def gene_layer(L):
+            ops.gemm(cre_bf, L["kv"].w, EPI_BIAS_BF16, bias=L["kv"].b, out=kv)      # shared by every tissue copy
+
+            def cross(q, out):
+                ops.attention(q, kv[:, :D], kv[:, D:], cu_gq, cu_cre, tiles_gcross, H, hd, None, out=out)
+            self._layer(L, gx, Mg, gene_self, cross, "g")
+
+        def cre_layer(L):
+            def cross(q, out):
+                ops.label_attention(q, L["kv9"], logc, row_seq, H, hd, out=out)
+            self._layer(L, cx, nC, cre_self, cross, "c", mirror=cre_bf)
+
+        gene_layer(w.gene_layers[0])
+        for i in range(w.NL - 1):
+            cre_layer(w.cre_layers[i])
+            gene_layer(w.gene_layers[i + 1])
+
+        # ---- registry rows -> embeddings -> head ----
+        reg_rows = (np.cumsum(seq_lens) - seq_lens).astype(np.int32)
+        reg_idx = torch.from_numpy(reg_rows).to(dev, non_blocking=True)
+        emb, emb_bf = ops.gather_rows(gx, None, reg_idx, want_f32=True, want_bf16=True)
+        h1 = ops.gemm(emb_bf, w.h0.w, EPI_BIAS_F32, bias=w.h0.b)
+        h1n = ops.layernorm(h1, w.hn.g, w.hn.b, gelu=True)
+        h2 = ops.gemm(h1n, w.h4.w, EPI_BIAS_GELU_BF16, bias=w.h4.b)
+        pred = ops.head_out(h2, w.h6_w, w.h6_b, softplus=True)
+        out = {"pred": pred, "emb": emb, "T": T.tolist()}
+
+        if gene_token_position is not None:
+            gp = np.repeat(np.asarray([int(p) for p in gene_token_position]) + 1, T)   # +1: registry token (:665-666)
+            rows = torch.from_numpy((reg_rows + gp).astype(np.int32)).to(dev)
+            out["gene_token_embedding"], _ = ops.gather_rows(gx, None, rows)
+        if cre_token_position is not None:
+            c_off = np.concatenate([[0], np.cumsum(C)])[:-1]
+            cp = np.repeat(c_off + np.asarray([int(p) for p in cre_token_position]), T)
+            out["cre_token_embedding"], _ = ops.gather_rows(cx, None, torch.from_numpy(cp.astype(np.int32)).to(dev))
+        return out
