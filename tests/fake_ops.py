@@ -48,7 +48,7 @@ def gemm(a, w, epilogue, bias=None, resid=None, out=None, out2=None):
 
 
 class TileMap:
-    def __init__(self, q_lens, block_m, device):
+    def __init__(self, q_lens, block_m, device, k_lens=None):
         self.block_m = block_m
         self.lens = np.asarray(q_lens)
 

@@ -1,0 +1,140 @@
+"""Full four-stage path on the GPU box: window tables -> tokens (bit-exact) -> expression/embeddings (bf16 tolerance),
+through HotPath and through the reference-shaped VCFProcessor / VCFDataset / ModelManager / Trainer surface."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import model_fp32, stage1 as O  # noqa: E402  (checker only)
+from tests.common import pearson, rel_err  # noqa: E402
+from variantformer_b200.engine import Engine  # noqa: E402
+from variantformer_b200.pipeline import GeneSpec, HotPath  # noqa: E402
+from variantformer_b200.stage1 import Genome, SampleVariants, cre_window, gene_window  # noqa: E402
+from variantformer_b200.utils import random_init, synth  # noqa: E402
+from variantformer_b200.utils.constants import REF_CREs  # noqa: E402
+
+CFG = dict(random_init.V4_PCG_MODEL, emb_dim=384, gene_emb_dim=256, num_heads=8, num_layers=3, token_dim=256)
+HP = dict(random_init.SEQ2REG_HP, embedding_dim=256, num_heads=4, num_layers=2)
+
+
+def _world(seed=77, chrom_len=3_000_000, n_genes=3, n_cres=40):
+    rng = np.random.default_rng(seed)
+    chrom = synth.make_chromosome(rng, chrom_len)
+    var = synth.make_variants(rng, chrom)
+    genes = []
+    for g in range(n_genes):
+        lay = synth.make_gene_layout(rng, chrom_len, n_cres, strand="+-"[g % 2], body_len=int(rng.integers(20_000, 60_000)),
+                                     cre_span=200_000)
+        genes.append(GeneSpec("chr1", lay["start"], lay["end"], lay["strand"], lay["cre_start"], lay["cre_end"],
+                              lay["labels"], [62, 3, 14][: 1 + g]))
+    return {"chr1": chrom}, {"chr1": var}, genes
+
+
+def _oracle_batch(chroms, var, genes, use_var=True):
+    bpe = O.OracleBPE()
+    b = {k: [] for k in ("cre_sequences", "cre_attention_masks", "gene_embeddings", "gene_attention_masks",
+                         "tissue_context", "ref_cre_labels")}
+    for g in genes:
+        chrom = chroms[g.chrom]; v = var[g.chrom]
+        lens = np.array([len(a) for a in v["alt"]], np.int32); pool = np.frombuffer(b"".join(v["alt"]), np.uint8)
+        aoff = np.cumsum(lens) - lens
+        minus = g.strand == "-"
+
+        def window(a0, a1):
+            if use_var:
+                lo, hi = np.searchsorted(v["pos"], a0), np.searchsorted(v["pos"], a1)
+                s = O.apply_variants(chrom, a0, a1, v["pos"][lo:hi], v["ref_len"][lo:hi], aoff[lo:hi], lens[lo:hi],
+                                     v["gt"][lo:hi], pool)
+            else:
+                s = chrom[a0:a1].tobytes()
+            return O.reverse_complement(s) if minus else s
+        order = np.argsort(g.cre_start, kind="stable")
+        order = order[::-1] if minus else order
+        toks, masks = zip(*[O.adjust_length(bpe.encode(window(*cre_window(g.cre_start[i], g.cre_end[i], 50))), 200)
+                            for i in order])
+        gt, gm = O.chunkify(bpe.encode(window(*gene_window(g.start, g.end, g.strand, 1000, 300000))), 200, 200)
+        b["cre_sequences"].append(torch.from_numpy(np.stack(toks)).long().unsqueeze(1))
+        b["cre_attention_masks"].append(torch.from_numpy(np.stack(masks)).unsqueeze(1))
+        b["gene_embeddings"].append(torch.from_numpy(gt).long().unsqueeze(1))
+        b["gene_attention_masks"].append(torch.from_numpy(gm).unsqueeze(1))
+        b["tissue_context"].append(torch.tensor(g.tissues)); b["ref_cre_labels"].append(torch.from_numpy(np.asarray(g.cre_labels)[order].copy()))
+    return b
+
+
+def test_hotpath_tokens_bit_exact_and_outputs_within_tolerance():
+    chroms, var, genes = _world()
+    sd = random_init.make_state_dict(CFG, HP, seed=5)
+    hot = HotPath(Engine(sd, CFG, HP), Genome.from_arrays(chroms, "cuda"))
+    sv = SampleVariants(var, "cuda")
+    t = hot.tokenize(genes, sv)
+    want = _oracle_batch(chroms, var, genes)
+    for g in range(len(genes)):
+        assert torch.equal(t["cre_tok"][g].cpu().long(), want["cre_sequences"][g][:, 0]), f"CRE tokens gene {g}"
+        assert torch.equal(t["cre_msk"][g].cpu(), want["cre_attention_masks"][g][:, 0])
+        assert torch.equal(t["gene_tok"][g].cpu().long(), want["gene_embeddings"][g][:, 0]), f"gene tokens gene {g}"
+        assert torch.equal(t["gene_msk"][g].cpu(), want["gene_attention_masks"][g][:, 0])
+    pred, emb = hot.predict(genes, sv)
+    ref = model_fp32.predict_step(sd, CFG, HP, want, schedule="reference")
+    w_emb = np.concatenate(ref["embeddings"]); w_pred = np.concatenate(ref["pred_gene_exp"]).ravel()
+    assert rel_err(emb, w_emb) <= 1e-2 and pearson(emb, w_emb) >= 0.9999 and rel_err(pred, w_pred) <= 1e-2
+
+
+def test_vcfprocessor_surface_end_to_end(tmp_path):
+    from variantformer_b200.processors.vcfprocessor import VCFProcessor
+    chroms, var, genes = _world(seed=78, n_genes=2, n_cres=24)
+    art = tmp_path / "_artifacts"; (art / "gene_cre_manifests").mkdir(parents=True)
+    with open(art / "GRCh38_no_alt_analysis_set_GCA_000001405.15.fasta.gz", "wb") as f:     # plain text is accepted too
+        f.write(b">chr1 synthetic\n")
+        s = chroms["chr1"].tobytes()
+        for i in range(0, len(s), 60):
+            f.write(s[i:i + 60] + b"\n")
+    v = var["chr1"]
+    with open(tmp_path / "sample.vcf", "w") as f:
+        f.write("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS1\n")
+        for p, rl, alt, gt in zip(v["pos"], v["ref_len"], v["alt"], v["gt"]):
+            ref = chroms["chr1"][p:p + rl].tobytes().decode().upper()
+            f.write(f"chr1\t{p + 1}\t.\t{ref}\t{alt.decode()}\t.\tPASS\t.\tGT\t{'0/1' if gt == 1 else '1|1'}\n")
+    rows = []
+    for i, g in enumerate(genes):
+        gid = f"ENSG{i:011d}.1"
+        rows.append(dict(gene_id=gid, gene_name=f"G{i}", chromosome="chr1", start=g.start, end=g.end, strand=g.strand))
+        pd.DataFrame(dict(chromosome="chr1", start_cre=g.cre_start, end_cre=g.cre_end,
+                          cre_name=[REF_CREs[l] for l in g.cre_labels])).to_csv(art / "gene_cre_manifests" / f"{gid}.csv", index=False)
+    pd.DataFrame(rows).to_csv(art / "all_genes_v1_pcg_gencodeV24.csv", index=False)
+    over = dict(CFG, random_init=5, seq2reg_hyper_parameters=HP)
+    vp = VCFProcessor("v4_pcg", base_dir=str(tmp_path), model_overrides=over)
+    assert "whole blood" in vp.get_tissues() and len(vp.get_genes()) == 2
+    query = pd.DataFrame({"gene_id": [r["gene_id"] for r in rows] + ["ENSG_missing"],
+                          "tissues": ["whole blood,K562,not-a-tissue", "thyroid", "whole blood"]})
+    ds, dl = vp.create_data(str(tmp_path / "sample.vcf"), query, batch_size=2)
+    model, ckpt, trainer = vp.load_model()
+    assert model.vep is False and not model.training and trainer.precision == "bf16-mixed"
+    out = vp.predict(model, None, trainer, dl, ds)
+    assert list(out["gene_id"]) == [r["gene_id"] for r in rows]
+    assert out["predicted_expression"].iloc[0].shape == (2, 1) and out["embeddings"].iloc[0].shape == (2, CFG["emb_dim"])
+    # oracle on the same genome / variants / weights
+    tv = vp.tissue_vocab
+    for g, names in zip(genes, (["whole blood", "K562"], ["thyroid"])):
+        g.tissues = [tv[n] for n in names]
+    sd = random_init.make_state_dict({k: v for k, v in CFG.items()}, HP, seed=5)
+    ref = model_fp32.predict_step(sd, CFG, HP, _oracle_batch(chroms, var, genes), schedule="reference")
+    for i in range(2):
+        assert rel_err(out["embeddings"].iloc[i], ref["embeddings"][i]) <= 1e-2
+        assert pearson(out["embeddings"].iloc[i], ref["embeddings"][i]) >= 0.9999
+        assert rel_err(out["predicted_expression"].iloc[i], ref["pred_gene_exp"][i]) <= 1e-2
+    # checkpoint path: tokenizer checkpoints load ({"hyper_parameters","state_dict"}), missing model checkpoint raises
+    tok_sd = {k[len("cre_tokenizer."):]: v for k, v in sd.items() if k.startswith("cre_tokenizer.")}
+    torch.save({"hyper_parameters": HP, "state_dict": tok_sd}, art / "pretrained_tokenizers_checkpoint.pth")
+    with pytest.raises(ValueError, match="Checkpoint not found"):
+        VCFProcessor("v4_pcg", base_dir=str(tmp_path), model_overrides=dict(CFG)).load_model()
+    torch.save({"state_dict": sd}, art / "v4_pcg_epoch11_checkpoint.pth")
+    vp2 = VCFProcessor("v4_pcg", base_dir=str(tmp_path), model_overrides=dict(CFG))
+    model2, ckpt2, trainer2 = vp2.load_model()
+    ds2, dl2 = vp2.create_data(str(tmp_path / "sample.vcf"), query, batch_size=1)
+    out2 = vp2.predict(model2, ckpt2, trainer2, dl2, ds2)
+    for i in range(2):           # same weights through the checkpoint path, different batching -> identical
+        assert np.array_equal(out2["embeddings"].iloc[i], out["embeddings"].iloc[i])

@@ -108,6 +108,7 @@ def test_empty_and_all_n_windows():
     buf, lens, mx = _pack(["NNNNNNNN", "A", "nnnnACGTnnnn"])
     lens[1] = 0                                              # empty window
     tok, mask, cnt = tk.tokenize_fixed(buf, lens, mx)
-    assert cnt.cpu().tolist() == [0, 0, 1] and mask[0].all() and mask[1].all()
-    assert tok[2, 0].item() == int(O.OracleBPE().encode("ACGT")[0])
+    want = O.OracleBPE().encode("nnnnACGTnnnn").tolist()            # [ACG, T]
+    assert cnt.cpu().tolist() == [0, 0, len(want)] and mask[0].all() and mask[1].all()
+    assert tok[2, :len(want)].cpu().tolist() == want
     assert (tok[:2] == 0).all()

@@ -208,6 +208,8 @@ __global__ void bpe_tokenize_kernel(const BpeParams p) {
         if (s_cnt[a] == 0 || s_cnt[b] == 0 || (a == b && s_cnt[a] < 2)) continue;
         int merged = 0;
         if (a != b) {
+            // every thread must have taken the skip decision above before any occupancy counter moves
+            __syncthreads();
             // matches of a non-self pair can never share a symbol: apply immediately
             for (int i = tid; i < n; i += nt) {
                 if (sym[i] != a) continue;

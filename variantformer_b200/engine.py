@@ -156,15 +156,14 @@ class Engine:
         self.ws = Workspace(self.device)
 
     # ---------------------------------------------------------------- seq2reg
-    def seq2reg(self, W: Seq2RegWeights, tokens_i32, mask_u8, lens_host, tag):
-        """tokens/mask: device [n_win, L]; lens_host: numpy valid-token counts.  -> bf16 [n_win, d] mean-pooled."""
-        dev, ws = self.device, self.ws
+    def seq2reg(self, W: Seq2RegWeights, tokens_i32, mask_u8, lens_host, cu, tiles):
+        """tokens/mask: device [n_win, L]; lens_host: numpy valid-token counts; cu/tiles: their prefix sums and
+        attention tile map on the device.  -> bf16 [n_win, d] masked mean of the last layer."""
+        ws = self.ws
         n_win = tokens_i32.shape[0]
         n_tok = int(lens_host.sum())
-        cu = ops.cu_seqlens(lens_host, dev)
         ids, pos = ops.compact_tokens(tokens_i32, mask_u8, cu, n_tok)
         x = ops.embed_tokens(ids, pos, W.emb, W.pe)
-        tiles = ops.TileMap(lens_host, 64, dev)
         d, H, hd = W.d, W.H, W.hd
         h = ws.get("r_h", (n_tok, d), torch.bfloat16)
         qkv = ws.get("r_qkv", (n_tok, 3 * d), torch.bfloat16)
@@ -203,43 +202,35 @@ class Engine:
         ops.gemm(h, L["g1"].w, EPI_BIAS_GEGLU_BF16, bias=L["g1"].b, out=f)
         ops.gemm(f, L["g2"].w, EPI_BIAS_RESID_F32, bias=L["g2"].b, resid=x, out=x, out2=mirror)
 
-    # ---------------------------------------------------------------- full forward on a slab of genes
-    @torch.no_grad()
-    def forward_tokens(self, cre_tokens, cre_masks, gene_tokens, gene_masks, tissues, ref_labels,
-                       cre_token_position=None, gene_token_position=None):
+    # ---------------------------------------------------------------- slab preparation (host bookkeeping + H2D)
+    def prepare(self, cre_tokens, cre_masks, gene_tokens, gene_masks, tissues, ref_labels,
+                cre_token_position=None, gene_token_position=None, lens=None):
         """Lists (one entry per gene) of: cre_tokens [C,L] int, cre_masks [C,L] bool (True = pad), gene_tokens
-        [G,L], gene_masks [G,L], tissues [T] int, ref_labels [C] int (CPU or CUDA tensors).
-        -> dict(pred fp32 [sum T], emb fp32 [sum T, D], T list, optional token embeddings)."""
-        dev, w, ws = self.device, self.w, self.ws
+        [G,L], gene_masks [G,L], tissues [T] int, ref_labels [C] int (CPU or CUDA tensors).  Builds every index
+        structure the kernels need and moves the token windows to the device (pinned staging for CPU inputs).
+        `lens` = optional (cre_lens, gene_lens) host arrays to skip the valid-token count."""
+        dev = self.device
         B = len(cre_tokens)
-        D, H, hd = w.D, w.H, w.hd
         C = np.array([t.shape[0] for t in cre_tokens]); G = np.array([t.shape[0] for t in gene_tokens])
         T = np.array([len(t) for t in tissues])
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dt)).to(dev, non_blocking=True)
 
-        def stage(tok_list, mask_list):
+        def stage(tok_list, mask_list, known):
             tok = torch.cat([t.reshape(-1, t.shape[-1]) for t in tok_list]).to(torch.int32)
             msk = torch.cat([m.reshape(-1, m.shape[-1]) for m in mask_list]).to(torch.uint8)
             if tok.is_cuda:
-                lens = ops.window_lengths(msk).cpu().numpy().astype(np.int64)
-                return tok, msk, lens
-            lens = (msk == 0).sum(1).numpy().astype(np.int64)
-            return (tok.pin_memory().to(dev, non_blocking=True), msk.pin_memory().to(dev, non_blocking=True), lens)
+                ln = known if known is not None else ops.window_lengths(msk).cpu().numpy().astype(np.int64)
+                return tok, msk, ln
+            ln = known if known is not None else (msk == 0).sum(1).numpy().astype(np.int64)
+            return tok.pin_memory().to(dev, non_blocking=True), msk.pin_memory().to(dev, non_blocking=True), ln
 
-        ctok, cmsk, clens = stage(cre_tokens, cre_masks)
-        gtok, gmsk, glens = stage(gene_tokens, gene_masks)
-
-        # ---- stage 2: window encoders ----
-        cre_pooled = self.seq2reg(self.cre_tok, ctok, cmsk, clens, "cre")           # bf16 [sum C, d_r]
-        gene_pooled = self.seq2reg(self.gene_tok, gtok, gmsk, glens, "gene")        # bf16 [sum G, d_r]
-        nC, nG = int(C.sum()), int(G.sum())
-        cre_bf = ws.get("cre_bf", (nC, D), torch.bfloat16)                           # bf16 mirror = cross-attn context
-        if w.cre_map is not None:
-            cx = ops.gemm(cre_pooled, w.cre_map.w, EPI_BIAS_F32, bias=w.cre_map.b, out2=cre_bf)
-        else:
-            raise NotImplementedError("token_dim == emb_dim (no cre_map) is not wired on the B200 path")
-        gene_emb = ops.gemm(gene_pooled, w.gene_map.w, EPI_BIAS_F32, bias=w.gene_map.b)
-
-        # ---- gene stream: [registry(tissue); gene chunks] per (gene, tissue) ----
+        s = {"B": B, "C": C, "G": G, "T": T}
+        s["ctok"], s["cmsk"], s["clens"] = stage(cre_tokens, cre_masks, None if lens is None else lens[0])
+        s["gtok"], s["gmsk"], s["glens"] = stage(gene_tokens, gene_masks, None if lens is None else lens[1])
+        for tag, ln in (("c", s["clens"]), ("g", s["glens"])):
+            s[tag + "_cu_tok"] = ops.cu_seqlens(ln, dev)
+            s[tag + "_tiles_tok"] = ops.TileMap(ln, 64, dev)
+        # gene stream layout: per (gene, tissue): [registry(tissue); the gene's chunk embeddings]
         g_off = np.concatenate([[0], np.cumsum(G)])
         idx, seq_lens = [], []
         for g in range(B):
@@ -248,40 +239,71 @@ class Engine:
             for t in tis:
                 idx.append(np.concatenate([[-(t + 1)], body]))
                 seq_lens.append(G[g] + 1)
-        idx = np.concatenate(idx).astype(np.int32)
-        Mg = int(idx.shape[0])
-        gx, _ = ops.gather_rows(gene_emb, w.registry, torch.from_numpy(idx).to(dev, non_blocking=True))
+        idx = np.concatenate(idx)
         seq_lens = np.asarray(seq_lens)
-        cu_gseq = ops.cu_seqlens(seq_lens, dev)                       # one sequence per (gene, tissue): self-attention
-        cu_gq = ops.cu_seqlens(T * (G + 1), dev)                      # one "sequence" per gene: stacked cross queries
-        cu_cre = ops.cu_seqlens(C, dev)
-        tiles_gself = ops.TileMap(seq_lens, 64, dev)
-        tiles_gcross = ops.TileMap(T * (G + 1), 128, dev)
-        tiles_cself = ops.TileMap(C, 128 if C.max() > 256 else 64, dev)
-        row_seq = torch.from_numpy(np.repeat(np.arange(B), C).astype(np.int32)).to(dev, non_blocking=True)
+        s["Mg"] = int(idx.shape[0])
+        s["gene_idx"] = up(idx, np.int32)
+        s["cu_gseq"] = ops.cu_seqlens(seq_lens, dev)                  # one sequence per (gene, tissue): self-attention
+        s["cu_gq"] = ops.cu_seqlens(T * (G + 1), dev)                 # one "sequence" per gene: stacked cross queries
+        s["cu_cre"] = ops.cu_seqlens(C, dev)
+        s["tiles_gself"] = ops.TileMap(seq_lens, 64, dev)
+        s["tiles_gcross"] = ops.TileMap(T * (G + 1), 128, dev, k_lens=C)
+        s["tiles_cself"] = ops.TileMap(C, 128 if C.max() > 256 else 64, dev)
+        s["row_seq"] = up(np.repeat(np.arange(B), C), np.int32)
         lab = torch.cat([l.reshape(-1) for l in ref_labels]).detach().cpu().numpy().astype(np.int64)
         counts = np.zeros((B, NUM_REF_CRES), np.float64)
         np.add.at(counts, (np.repeat(np.arange(B), C), lab), 1.0)
         with np.errstate(divide="ignore"):
-            logc = torch.from_numpy(np.log(counts).astype(np.float32)).to(dev, non_blocking=True)
+            s["logc"] = up(np.log(counts), np.float32)
+        reg_rows = np.cumsum(seq_lens) - seq_lens
+        s["reg_idx"] = up(reg_rows, np.int32)
+        if gene_token_position is not None:
+            gp = np.repeat(np.asarray([int(p) for p in gene_token_position]) + 1, T)   # +1: registry token (:665-666)
+            s["gene_pos_idx"] = up(reg_rows + gp, np.int32)
+        if cre_token_position is not None:
+            c_off = np.concatenate([[0], np.cumsum(C)])[:-1]
+            s["cre_pos_idx"] = up(np.repeat(c_off + np.asarray([int(p) for p in cre_token_position]), T), np.int32)
+        return s
+
+    # ---------------------------------------------------------------- device work for one prepared slab
+    @torch.no_grad()
+    def run(self, s):
+        """-> dict(pred fp32 [sum T], emb fp32 [sum T, D], T list, optional token embeddings); device tensors."""
+        w, ws = self.w, self.ws
+        D, H, hd = w.D, w.H, w.hd
+        nC, Mg = int(s["C"].sum()), s["Mg"]
+
+        # ---- stage 2: window encoders ----
+        cre_pooled = self.seq2reg(self.cre_tok, s["ctok"], s["cmsk"], s["clens"], s["c_cu_tok"], s["c_tiles_tok"])
+        gene_pooled = self.seq2reg(self.gene_tok, s["gtok"], s["gmsk"], s["glens"], s["g_cu_tok"], s["g_tiles_tok"])
+        cre_bf = ws.get("cre_bf", (nC, D), torch.bfloat16)                           # bf16 mirror = cross-attn context
+        if w.cre_map is None:
+            raise NotImplementedError("token_dim == emb_dim (no cre_map) is not wired on the B200 path")
+        cx = ops.gemm(cre_pooled, w.cre_map.w, EPI_BIAS_F32, bias=w.cre_map.b, out=ws.get("cx", (nC, D), torch.float32),
+                      out2=cre_bf)
+        gene_emb = ops.gemm(gene_pooled, w.gene_map.w, EPI_BIAS_F32, bias=w.gene_map.b)
+        gx, _ = ops.gather_rows(gene_emb, w.registry, s["gene_idx"])
         kv = ws.get("g_kv", (nC, 2 * D), torch.bfloat16)
+        cu_gseq, cu_gq, cu_cre = s["cu_gseq"], s["cu_gq"], s["cu_cre"]
 
         def gene_self(qkv, out):
-            ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], cu_gseq, cu_gseq, tiles_gself, H, hd, w.slopes, out=out)
+            ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], cu_gseq, cu_gseq, s["tiles_gself"], H, hd,
+                          w.slopes, out=out)
 
         def cre_self(qkv, out):
-            ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], cu_cre, cu_cre, tiles_cself, H, hd, w.slopes, out=out)
+            ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], cu_cre, cu_cre, s["tiles_cself"], H, hd,
+                          w.slopes, out=out)
 
         def gene_layer(L):
             ops.gemm(cre_bf, L["kv"].w, EPI_BIAS_BF16, bias=L["kv"].b, out=kv)      # shared by every tissue copy
 
             def cross(q, out):
-                ops.attention(q, kv[:, :D], kv[:, D:], cu_gq, cu_cre, tiles_gcross, H, hd, None, out=out)
+                ops.attention(q, kv[:, :D], kv[:, D:], cu_gq, cu_cre, s["tiles_gcross"], H, hd, None, out=out)
             self._layer(L, gx, Mg, gene_self, cross, "g")
 
         def cre_layer(L):
             def cross(q, out):
-                ops.label_attention(q, L["kv9"], logc, row_seq, H, hd, out=out)
+                ops.label_attention(q, L["kv9"], s["logc"], s["row_seq"], H, hd, out=out)
             self._layer(L, cx, nC, cre_self, cross, "c", mirror=cre_bf)
 
         gene_layer(w.gene_layers[0])
@@ -290,21 +312,17 @@ class Engine:
             gene_layer(w.gene_layers[i + 1])
 
         # ---- registry rows -> embeddings -> head ----
-        reg_rows = (np.cumsum(seq_lens) - seq_lens).astype(np.int32)
-        reg_idx = torch.from_numpy(reg_rows).to(dev, non_blocking=True)
-        emb, emb_bf = ops.gather_rows(gx, None, reg_idx, want_f32=True, want_bf16=True)
+        emb, emb_bf = ops.gather_rows(gx, None, s["reg_idx"], want_f32=True, want_bf16=True)
         h1 = ops.gemm(emb_bf, w.h0.w, EPI_BIAS_F32, bias=w.h0.b)
         h1n = ops.layernorm(h1, w.hn.g, w.hn.b, gelu=True)
         h2 = ops.gemm(h1n, w.h4.w, EPI_BIAS_GELU_BF16, bias=w.h4.b)
         pred = ops.head_out(h2, w.h6_w, w.h6_b, softplus=True)
-        out = {"pred": pred, "emb": emb, "T": T.tolist()}
-
-        if gene_token_position is not None:
-            gp = np.repeat(np.asarray([int(p) for p in gene_token_position]) + 1, T)   # +1: registry token (:665-666)
-            rows = torch.from_numpy((reg_rows + gp).astype(np.int32)).to(dev)
-            out["gene_token_embedding"], _ = ops.gather_rows(gx, None, rows)
-        if cre_token_position is not None:
-            c_off = np.concatenate([[0], np.cumsum(C)])[:-1]
-            cp = np.repeat(c_off + np.asarray([int(p) for p in cre_token_position]), T)
-            out["cre_token_embedding"], _ = ops.gather_rows(cx, None, torch.from_numpy(cp.astype(np.int32)).to(dev))
+        out = {"pred": pred, "emb": emb, "T": s["T"].tolist()}
+        if "gene_pos_idx" in s:
+            out["gene_token_embedding"], _ = ops.gather_rows(gx, None, s["gene_pos_idx"])
+        if "cre_pos_idx" in s:
+            out["cre_token_embedding"], _ = ops.gather_rows(cx, None, s["cre_pos_idx"])
         return out
+
+    def forward_tokens(self, cre_tokens, cre_masks, gene_tokens, gene_masks, tissues, ref_labels, **kw):
+        return self.run(self.prepare(cre_tokens, cre_masks, gene_tokens, gene_masks, tissues, ref_labels, **kw))

@@ -12,13 +12,54 @@ from ._lib import (EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GEGLU_BF16, EPI_BIAS_GE
                    ptr, stream)
 
 LAUNCHES = 0
+PROFILER = None          # set to an EventProfiler to time every launch with CUDA events on the launching stream
+
+
+class EventProfiler:
+    """Per-launch CUDA-event timing grouped by kernel kind (bench.py's roofline numerator/denominator)."""
+
+    def __init__(self):
+        self.items = []
+
+    def begin(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def end(self, e0, kind, flops=0.0):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.items.append((kind, float(flops), e0, e1))
+
+    def summarize(self):
+        torch.cuda.synchronize()
+        out = {}
+        for kind, flops, e0, e1 in self.items:
+            d = out.setdefault(kind, {"ms": 0.0, "flops": 0.0, "n": 0})
+            d["ms"] += e0.elapsed_time(e1); d["flops"] += flops; d["n"] += 1
+        return out
+
+
+class _timed:
+    __slots__ = ("kind", "flops", "e0")
+
+    def __init__(self, kind, flops=0.0):
+        self.kind, self.flops, self.e0 = kind, flops, None
+
+    def __enter__(self):
+        if PROFILER is not None:
+            self.e0 = PROFILER.begin()
+
+    def __exit__(self, *a):
+        global LAUNCHES
+        LAUNCHES += 1
+        if self.e0 is not None and PROFILER is not None:
+            PROFILER.end(self.e0, self.kind, self.flops)
+        return False
+
+
 _OUT_DTYPE = {EPI_BIAS_BF16: torch.bfloat16, EPI_BIAS_GEGLU_BF16: torch.bfloat16, EPI_BIAS_GELU_BF16: torch.bfloat16,
               EPI_BIAS_RESID_F32: torch.float32, EPI_BIAS_F32: torch.float32}
-
-
-def _count(n=1):
-    global LAUNCHES
-    LAUNCHES += n
 
 
 def _chk_bf16(t):
@@ -41,18 +82,19 @@ def gemm(a, w, epilogue, bias=None, resid=None, out=None, out2=None):
         assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
     if out2 is not None:
         assert out2.dtype == torch.bfloat16 and out2.shape == (M, N) and out2.stride(1) == 1
-    check(_lib.lib().vf_gemm_bf16(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, epilogue, ptr(bias), ptr(resid),
-                                  resid.stride(0) if resid is not None else 0, ptr(out), out.stride(0), ptr(out2),
-                                  out2.stride(0) if out2 is not None else 0, stream()))
-    _count()
+    with _timed("gemm", 2.0 * M * N * K):
+        check(_lib.lib().vf_gemm_bf16(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, epilogue, ptr(bias),
+                                      ptr(resid), resid.stride(0) if resid is not None else 0, ptr(out), out.stride(0),
+                                      ptr(out2), out2.stride(0) if out2 is not None else 0, stream()))
     return out
 
 
 class TileMap:
     """Query-tile map of a batch of variable-length sequences (host-built, device-resident)."""
 
-    def __init__(self, q_lens, block_m, device):
+    def __init__(self, q_lens, block_m, device, k_lens=None):
         q_lens = np.asarray(q_lens, np.int64)
+        self.qk_pairs = float((q_lens * (q_lens if k_lens is None else np.asarray(k_lens, np.int64))).sum())
         nt = (q_lens + block_m - 1) // block_m
         seq = np.repeat(np.arange(len(q_lens)), nt)
         first = np.cumsum(nt) - nt
@@ -75,10 +117,11 @@ def attention(q, k, v, cu_q, cu_k, tiles: TileMap, heads, head_dim, slopes=None,
         assert t.is_cuda and t.dtype == torch.bfloat16 and t.stride(1) == 1
     if out is None:
         out = torch.empty((q.shape[0], heads * head_dim), dtype=torch.bfloat16, device=q.device)
-    check(_lib.lib().vf_attention_varlen(ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(out),
-                                         out.stride(0), ptr(cu_q), ptr(cu_k), ptr(tiles.tile_seq), ptr(tiles.tile_q0),
-                                         tiles.n_tiles, tiles.block_m, heads, head_dim, ptr(slopes), stream()))
-    _count()
+    with _timed("attention", 4.0 * tiles.qk_pairs * heads * head_dim):
+        check(_lib.lib().vf_attention_varlen(ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(out),
+                                             out.stride(0), ptr(cu_q), ptr(cu_k), ptr(tiles.tile_seq),
+                                             ptr(tiles.tile_q0), tiles.n_tiles, tiles.block_m, heads, head_dim,
+                                             ptr(slopes), stream()))
     return out
 
 
@@ -87,9 +130,9 @@ def label_attention(q, kv9, logc, row_seq, heads, head_dim, out=None):
     assert row_seq.dtype == torch.int32 and kv9.is_contiguous() and logc.is_contiguous()
     if out is None:
         out = torch.empty((q.shape[0], heads * head_dim), dtype=torch.bfloat16, device=q.device)
-    check(_lib.lib().vf_label_attention(ptr(q), q.stride(0), ptr(kv9), ptr(logc), ptr(row_seq), q.shape[0], heads,
-                                        head_dim, ptr(out), out.stride(0), stream()))
-    _count()
+    with _timed("label_attention"):
+        check(_lib.lib().vf_label_attention(ptr(q), q.stride(0), ptr(kv9), ptr(logc), ptr(row_seq), q.shape[0], heads,
+                                            head_dim, ptr(out), out.stride(0), stream()))
     return out
 
 
@@ -98,17 +141,17 @@ def layernorm(x, gamma, beta, eps=1e-5, gelu=False, out=None):
     M, d = x.shape
     if out is None:
         out = torch.empty((M, d), dtype=torch.bfloat16, device=x.device)
-    check(_lib.lib().vf_layernorm(ptr(x), x.stride(0), ptr(gamma), ptr(beta), M, d, eps, ptr(out), out.stride(0),
-                                  int(gelu), stream()))
-    _count()
+    with _timed("layernorm"):
+        check(_lib.lib().vf_layernorm(ptr(x), x.stride(0), ptr(gamma), ptr(beta), M, d, eps, ptr(out), out.stride(0),
+                                      int(gelu), stream()))
     return out
 
 
 def window_lengths(pad_mask_u8):
     n, L = pad_mask_u8.shape
     lens = torch.empty(n, dtype=torch.int32, device=pad_mask_u8.device)
-    check(_lib.lib().vf_window_lengths(ptr(pad_mask_u8), n, L, ptr(lens), stream()))
-    _count()
+    with _timed("misc"):
+        check(_lib.lib().vf_window_lengths(ptr(pad_mask_u8), n, L, ptr(lens), stream()))
     return lens
 
 
@@ -116,16 +159,16 @@ def compact_tokens(tokens_i32, pad_mask_u8, cu, n_tok):
     n, L = tokens_i32.shape
     ids = torch.empty(n_tok, dtype=torch.int32, device=tokens_i32.device)
     pos = torch.empty(n_tok, dtype=torch.int32, device=tokens_i32.device)
-    check(_lib.lib().vf_compact_tokens(ptr(tokens_i32), ptr(pad_mask_u8), ptr(cu), n, L, ptr(ids), ptr(pos), stream()))
-    _count()
+    with _timed("misc"):
+        check(_lib.lib().vf_compact_tokens(ptr(tokens_i32), ptr(pad_mask_u8), ptr(cu), n, L, ptr(ids), ptr(pos), stream()))
     return ids, pos
 
 
 def embed_tokens(ids, pos, emb, pe):
     n, d = ids.numel(), emb.shape[1]
     out = torch.empty((n, d), dtype=torch.float32, device=ids.device)
-    check(_lib.lib().vf_embed_tokens(ptr(ids), ptr(pos), ptr(emb), ptr(pe), n, d, ptr(out), stream()))
-    _count()
+    with _timed("misc"):
+        check(_lib.lib().vf_embed_tokens(ptr(ids), ptr(pos), ptr(emb), ptr(pe), n, d, ptr(out), stream()))
     return out
 
 
@@ -133,8 +176,8 @@ def masked_meanpool(x, cu, n_win, want_f32=False):
     d = x.shape[1]
     ob = torch.empty((n_win, d), dtype=torch.bfloat16, device=x.device)
     of = torch.empty((n_win, d), dtype=torch.float32, device=x.device) if want_f32 else None
-    check(_lib.lib().vf_masked_meanpool(ptr(x), x.stride(0), ptr(cu), n_win, d, ptr(ob), ptr(of), d, stream()))
-    _count()
+    with _timed("misc"):
+        check(_lib.lib().vf_masked_meanpool(ptr(x), x.stride(0), ptr(cu), n_win, d, ptr(ob), ptr(of), d, stream()))
     return (ob, of) if want_f32 else ob
 
 
@@ -142,26 +185,26 @@ def gather_rows(table_a, table_b, idx, want_f32=True, want_bf16=False):
     n, d = idx.numel(), table_a.shape[1]
     of = torch.empty((n, d), dtype=torch.float32, device=idx.device) if want_f32 else None
     ob = torch.empty((n, d), dtype=torch.bfloat16, device=idx.device) if want_bf16 else None
-    check(_lib.lib().vf_gather_rows(ptr(table_a), table_a.stride(0), ptr(table_b),
-                                    table_b.stride(0) if table_b is not None else 0, ptr(idx), n, d, ptr(of), ptr(ob),
-                                    d, stream()))
-    _count()
+    with _timed("misc"):
+        check(_lib.lib().vf_gather_rows(ptr(table_a), table_a.stride(0), ptr(table_b),
+                                        table_b.stride(0) if table_b is not None else 0, ptr(idx), n, d, ptr(of), ptr(ob),
+                                        d, stream()))
     return of, ob
 
 
 def head_out(h_bf16, w, b, softplus=True):
     n, d = h_bf16.shape
     out = torch.empty(n, dtype=torch.float32, device=h_bf16.device)
-    check(_lib.lib().vf_head_out(ptr(h_bf16), h_bf16.stride(0), ptr(w), ptr(b), n, d, int(softplus), ptr(out), stream()))
-    _count()
+    with _timed("misc"):
+        check(_lib.lib().vf_head_out(ptr(h_bf16), h_bf16.stride(0), ptr(w), ptr(b), n, d, int(softplus), ptr(out), stream()))
     return out
 
 
 def cast_bf16(x):
     assert x.dtype == torch.float32 and x.is_contiguous()
     y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    check(_lib.lib().vf_cast_f32_to_bf16(ptr(x), ptr(y), x.numel(), stream()))
-    _count()
+    with _timed("misc"):
+        check(_lib.lib().vf_cast_f32_to_bf16(ptr(x), ptr(y), x.numel(), stream()))
     return y
 
 
@@ -173,11 +216,11 @@ def encode_windows(genome, win_base, w0, w1, var_lo, var_hi, flags, variants, ma
     out_len = torch.empty(n, dtype=torch.int32, device=genome.device)
     err = torch.zeros(1, dtype=torch.int32, device=genome.device)
     v = variants
-    check(_lib.lib().vf_encode_windows(ptr(genome), ptr(win_base), ptr(w0), ptr(w1), ptr(var_lo), ptr(var_hi),
-                                       ptr(flags), ptr(v["pos"]), ptr(v["ref_len"]), ptr(v["alt_off"]),
-                                       ptr(v["alt_len"]), ptr(v["gt"]), ptr(v["alt_pool"]), n, int(max_window),
-                                       ptr(out), int(pitch), ptr(out_len), ptr(err), stream()))
-    _count()
+    with _timed("stage1_encode"):
+        check(_lib.lib().vf_encode_windows(ptr(genome), ptr(win_base), ptr(w0), ptr(w1), ptr(var_lo), ptr(var_hi),
+                                           ptr(flags), ptr(v["pos"]), ptr(v["ref_len"]), ptr(v["alt_off"]),
+                                           ptr(v["alt_len"]), ptr(v["gt"]), ptr(v["alt_pool"]), n, int(max_window),
+                                           ptr(out), int(pitch), ptr(out_len), ptr(err), stream()))
     return out, out_len, err
 
 
@@ -190,8 +233,8 @@ def bpe_tokenize(seq, lens, max_len, merges, out_pitch, out_cap, want_starts=Fal
     scratch = torch.empty((n, max_len), dtype=torch.int16, device=dev) if max_len > 8192 else None
     starts = torch.empty((n, max_len), dtype=torch.int32, device=dev) if want_starts else None
     a, b, c = merges
-    check(_lib.lib().vf_bpe_tokenize(ptr(seq), pitch, ptr(lens), n, int(max_len), ptr(a), ptr(b), ptr(c), a.numel(),
-                                     ptr(scratch), int(max_len) if scratch is not None else 0, ptr(out), out_pitch,
-                                     out_cap, ptr(cnt), ptr(starts), int(max_len) if want_starts else 0, stream()))
-    _count()
+    with _timed("stage1_bpe"):
+        check(_lib.lib().vf_bpe_tokenize(ptr(seq), pitch, ptr(lens), n, int(max_len), ptr(a), ptr(b), ptr(c), a.numel(),
+                                         ptr(scratch), int(max_len) if scratch is not None else 0, ptr(out), out_pitch,
+                                         out_cap, ptr(cnt), ptr(starts), int(max_len) if want_starts else 0, stream()))
     return (out, cnt, starts) if want_starts else (out, cnt)

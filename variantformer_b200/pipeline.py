@@ -1,0 +1,85 @@
+"""HotPath — the batched four-stage pipeline as one call: window tables (host) -> genotype encoding + BPE
+(device) -> seq2reg -> seq2gene -> head -> (expression, embeddings).  This is what VCFProcessor / bench.py drive
+for slabs of genes; per-item access with the reference's tuple layout lives in datasets/vcfdataset.py."""
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from .engine import Engine
+from .stage1 import Genome, SampleVariants, WindowTokenizer, cre_window, gene_window
+
+
+@dataclass
+class GeneSpec:
+    """One query row: gene coordinates, its CRE table and the tissues to predict."""
+    chrom: str
+    start: int
+    end: int
+    strand: str
+    cre_start: np.ndarray
+    cre_end: np.ndarray
+    cre_labels: np.ndarray              # ids into utils.constants.REF_CREs
+    tissues: list
+    cre_chrom: list = field(default=None)
+
+
+class HotPath:
+    def __init__(self, engine: Engine, genome: Genome, max_length=200, max_chunks=200, cre_neighbour_hood=50,
+                 gene_upstream=1000, gene_downstream=300000):
+        self.engine, self.genome = engine, genome
+        self.tok = WindowTokenizer(engine.device, max_length=max_length, max_chunks=max_chunks)
+        self.nb, self.up, self.down = cre_neighbour_hood, gene_upstream, gene_downstream
+        self.max_length, self.max_chunks = max_length, max_chunks
+
+    def tokenize(self, genes, variants: SampleVariants = None):
+        """Stage 1 for a slab of genes: two kernel launches for all CRE windows, two for all gene windows.
+        -> per-gene lists of device tensors (tokens int32 [n, L], masks bool [n, L]) + host token counts."""
+        dev = self.engine.device
+        chroms, w0, w1, rc, owner = [], [], [], [], []
+        for gi, g in enumerate(genes):
+            minus = g.strand == "-"
+            order = np.argsort(g.cre_start, kind="stable")
+            if minus:
+                order = order[::-1]                       # vcfdataset.py:243-246
+            for i in order:
+                a0, a1 = cre_window(g.cre_start[i], g.cre_end[i], self.nb)
+                chroms.append(g.chrom if g.cre_chrom is None else g.cre_chrom[i])
+                w0.append(a0); w1.append(a1); rc.append(int(minus)); owner.append(gi)
+        seq, lens, err1 = self.tok.sequences(self.genome, chroms, w0, w1, rc, variants)
+        ctok, cmask, ccnt = self.tok.tokenize_fixed(seq, lens, seq.shape[1])
+        gw = [gene_window(g.start, g.end, g.strand, self.up, self.down) for g in genes]
+        gseq, glens, err2 = self.tok.sequences(self.genome, [g.chrom for g in genes], [x[0] for x in gw],
+                                               [x[1] for x in gw], [int(g.strand == "-") for g in genes], variants)
+        chunks, gcnt = self.tok.tokenize_chunked(gseq, glens, gseq.shape[1])      # (one small D2H of the counts)
+        errs = torch.maximum(err1, err2)
+        C = np.bincount(np.asarray(owner), minlength=len(genes))
+        off = np.concatenate([[0], np.cumsum(C)])
+        ccnt_h = np.minimum(ccnt.cpu().numpy(), self.max_length).astype(np.int64)
+        cre_tok = [ctok[off[i]:off[i + 1]] for i in range(len(genes))]
+        cre_msk = [cmask[off[i]:off[i + 1]] for i in range(len(genes))]
+        gene_tok = [c[0] for c in chunks]; gene_msk = [c[1] for c in chunks]
+        glen_h = np.concatenate([np.minimum(self.max_length, np.maximum(
+            0, min(int(n), self.max_length * self.max_chunks) - self.max_length * np.arange(t.shape[0])))
+            for n, t in zip(gcnt, gene_tok)]).astype(np.int64)
+        labels = []
+        for g in genes:
+            order = np.argsort(g.cre_start, kind="stable")
+            labels.append(torch.from_numpy(np.asarray(g.cre_labels)[order[::-1] if g.strand == "-" else order].copy()))
+        return dict(cre_tok=cre_tok, cre_msk=cre_msk, gene_tok=gene_tok, gene_msk=gene_msk, labels=labels,
+                    lens=(ccnt_h, glen_h), err=errs)
+
+    def predict(self, genes, variants: SampleVariants = None, to_host=True):
+        """-> (pred [sum T], emb [sum T, D]) as numpy (to_host) or device tensors."""
+        t = self.tokenize(genes, variants)
+        tissues = [torch.as_tensor(g.tissues, dtype=torch.long) for g in genes]
+        slab = self.engine.prepare(t["cre_tok"], t["cre_msk"], t["gene_tok"], t["gene_msk"], tissues, t["labels"],
+                                   lens=t["lens"])
+        out = self.engine.run(slab)
+        if not to_host:
+            return out["pred"], out["emb"], t["err"]
+        pred = out["pred"].cpu().numpy(); emb = out["emb"].cpu().numpy()
+        code = int(t["err"].item())
+        if code:
+            raise RuntimeError(f"stage-1 kernel reported error {code} (1: pitch overflow, 2: >2048 variants/window)")
+        return pred, emb

@@ -1,0 +1,184 @@
+"""Seq2GenePredictorCombinedModulator — the configured `model_class` (configs/vf_model.yaml:10) behind the
+reference's signatures (seq2gene/model_combined_modulator.py:411-435 ctor, :540-552 forward, :857 predict_step,
+:909 variant_prediction).  All tensor math runs in libvf_b200.so through variantformer_b200.engine.Engine.
+"""
+import logging
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+
+from .._params import Affine, Table
+from ..utils.functions import precision2dtype
+from .modules.layers import ContextFlashAttentionEncoderLayer, MultiRegistry, TissueExpressionHeads
+
+logger = logging.getLogger(__name__)
+NUM_REF_CRES = 9
+
+
+class _HParams(dict):
+    __getattr__ = dict.get
+
+
+class CombinedModulator(nn.Module):
+    """Interleaved CRE / gene encoder stacks: gene_0(g, cre_in); for i: cre_i(cre, label ctx); gene_{i+1}(g, cre)."""
+
+    def __init__(self, emb_dim, num_heads, num_layers, use_alibi, mlp_dout, use_context, num_ref_cres=None,
+                 only_cross_attention=True, use_res=False, cross_alibi=False, flash_attn_3=False):
+        super().__init__()
+        if not use_context or only_cross_attention or use_res or cross_alibi or flash_attn_3:
+            raise NotImplementedError("only the vf_model.yaml variant (use_context, full gene layers, no use_res / "
+                                      "cross_alibi / flash_attn_3) is implemented on the B200 path")
+        assert num_ref_cres is not None, "num_ref_cres must be provided when use_context is True"
+        self.emb_dim, self.num_heads, self.num_layers = emb_dim, num_heads, num_layers
+        self.use_context, self.only_cross_attention, self.use_res, self.cross_alibi = True, False, False, False
+        self.second_level_context_embedding = Table(num_ref_cres, emb_dim)
+        mk = lambda: ContextFlashAttentionEncoderLayer(d_model=emb_dim, nhead=num_heads, batch_first=True,
+                                                       use_alibi=use_alibi, mlp_dout=mlp_dout)
+        self.cre_layers = nn.ModuleList([mk() for _ in range(num_layers - 1)])
+        self.gene_layers = nn.ModuleList([mk() for _ in range(num_layers)])
+
+
+class Seq2GenePredictorCombinedModulator(nn.Module):
+    def __init__(self, num_tissues: int, emb_dim: int, gene_emb_dim: int, num_heads: int, num_layers: int,
+                 use_alibi: bool = True, mlp_dout: float = 0.1, weight_decay: float = 0.0, learning_rate: float = 1e-4,
+                 lr_scale: float = 1, use_context: bool = False, token_dim: int = 128, cre_tokenizer=None,
+                 gene_tokenizer=None, cre_tokenizer_train_mode="val", cre_tokenizer_val_mode="val",
+                 gene_tokenizer_train_mode="val", gene_tokenizer_val_mode="val", tissues: list = None,
+                 optimizer="adam", gene_pooling="mean", flash_attn_3=False, **kwargs):
+        super().__init__()
+        assert gene_pooling in ["mean", "max", "start_token", "multi_registry"], \
+            "gene_pooling must be one of mean, max, start_token, or multi_registry"
+        if gene_pooling != "multi_registry":
+            raise NotImplementedError("only gene_pooling='multi_registry' (vf_model.yaml) is implemented")
+        if kwargs.get("add_context_to_cres", False):
+            raise NotImplementedError("add_context_to_cres=True is not implemented")
+        self.hparams = _HParams(dict(num_tissues=num_tissues, emb_dim=emb_dim, gene_emb_dim=gene_emb_dim,
+                                     num_heads=num_heads, num_layers=num_layers, use_alibi=use_alibi, mlp_dout=mlp_dout,
+                                     use_context=use_context, token_dim=token_dim, gene_pooling=gene_pooling, **kwargs))
+        self.precision = None
+        self.gene_pooling = gene_pooling
+        self.start_tkn = MultiRegistry(num_tissues, emb_dim)
+        self.cre_tokenizer, self.gene_tokenizer = cre_tokenizer, gene_tokenizer
+        self.emb_dim, self.use_context, self.tissues = emb_dim, use_context, tissues
+        self.use_res = kwargs.get("use_res", False)
+        self.loss_fn = kwargs.get("loss_fn", "poisson")
+        self.use_bigger_head = kwargs.get("use_bigger_head", False)
+        self.multi_head = kwargs.get("multi_head", True)
+        self.only_cross_attention = kwargs.get("only_cross_attention", True)
+        self.cross_alibi = kwargs.get("cross_alibi", False) and use_alibi
+        self.gene_map = Affine(emb_dim, gene_emb_dim)
+        if token_dim != emb_dim:
+            self.cre_map = Affine(emb_dim, token_dim)
+        self.combined_modulator = CombinedModulator(
+            emb_dim=emb_dim, num_heads=num_heads, num_layers=num_layers, use_alibi=use_alibi, mlp_dout=mlp_dout,
+            use_context=use_context, num_ref_cres=NUM_REF_CRES if use_context else None,
+            only_cross_attention=self.only_cross_attention, use_res=self.use_res, cross_alibi=self.cross_alibi,
+            flash_attn_3=flash_attn_3)
+        self.tissue_heads = TissueExpressionHeads(emb_dim, num_tissues, use_bigger_head=self.use_bigger_head,
+                                                  multi_head=self.multi_head, mlp_dout=mlp_dout, loss_fn=self.loss_fn,
+                                                  head_type=kwargs.get("head_type", "mlp"))
+        self.vep = False
+        self.trainer = None
+        self._engine = None
+
+    # -- engine plumbing ---------------------------------------------------------------------------
+    def engine(self):
+        from ..engine import Engine
+        dev = self.gene_map.weight.device
+        if self._engine is None or self._engine.device != dev:
+            if dev.type != "cuda":
+                raise RuntimeError("this model runs on a B200 only: call .to('cuda') first (there is no CPU path)")
+            cfg = dict(self.hparams)
+            self._engine = Engine(self.state_dict(), cfg, dict(self.cre_tokenizer.hparams), device=dev,
+                                  gene_seq2reg_hp=dict(self.gene_tokenizer.hparams))
+        return self._engine
+
+    def load_state_dict(self, *a, **k):
+        self._engine = None
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def _check_precision(self):
+        """model_combined_modulator.py:736-744: bf16/fp16 trainers run the mixed path; anything else asked the
+        reference for its fp16-cast attention path, which this implementation does not reproduce."""
+        try:
+            p = precision2dtype(self.trainer.precision)
+        except Exception:
+            p = torch.bfloat16 if self.trainer is None else torch.float32
+        if p not in (torch.float16, torch.bfloat16):
+            raise NotImplementedError("the B200 path computes in bf16 (fp32 accumulate); use precision='bf16-mixed'")
+
+    # -- reference forward signature ----------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, inp, attention_mask, tissue_vector, cre_context, strand, gene_embedding, gene_att_mask,
+                return_embedding=False, get_all=False, **kwargs):
+        """inp / gene_embedding: lists of int64 [n,1,L]; masks bool (True = pad); tissue_vector: list of [T_i];
+        cre_context: list of ref-cCRE label ids [C_i].  -> (pred [sum T,1], donors[, emb [sum T, D], gene_token_emb,
+        cre_token_emb]) exactly like the reference (:705-720)."""
+        self._check_precision()
+        sq = lambda xs: [x[:, 0, :] if x.dim() == 3 else x for x in xs]
+        cpos, gpos = kwargs.get("cre_token_position"), kwargs.get("gene_token_position")
+        out = self.engine().forward_tokens(
+            sq(inp), sq(attention_mask), sq(gene_embedding), sq(gene_att_mask), list(tissue_vector), list(cre_context),
+            cre_token_position=None if cpos is None else [int(p) for p in cpos],
+            gene_token_position=None if gpos is None else [int(p) for p in gpos])
+        donors = list(range(len(inp)))
+        emb = out["emb"]
+        if kwargs.get("only_embedding", False):
+            return {"embedding": emb, "donors": donors}
+        pred = out["pred"].unsqueeze(1)
+        if not return_embedding:
+            return pred, donors
+        zeros = lambda: torch.zeros(emb.shape[0], emb.shape[1], device=emb.device)
+        return (pred, donors, emb, out.get("gene_token_embedding", zeros()), out.get("cre_token_embedding", zeros()))
+
+    def predict_step(self, batch, batch_idx, dataloader_idx=None):
+        """:857-907 — one batch of genes -> per-gene numpy predictions and registry-token embeddings."""
+        if self.vep:
+            return self.variant_prediction(batch)
+        pred, donors, embd, _, _ = self(batch["cre_sequences"], batch["cre_attention_masks"], batch["tissue_context"],
+                                        batch["ref_cre_labels"], batch["strand_val"], batch["gene_embeddings"],
+                                        batch["gene_attention_masks"], return_embedding=True)
+        assert len(donors) == len(batch["cre_sequences"]), "Number of donors and CREs do not match"
+        pred = pred.cpu().float().numpy(); embd = embd.cpu().float().numpy()
+        preds, embs, s = [], [], 0
+        for i in donors:
+            e = s + len(batch["tissue_context"][i])
+            preds.append(pred[s:e]); embs.append(embd[s:e]); s = e
+        return {"pred_gene_exp": preds, "embeddings": embs, "batch_idx": batch_idx, "dataloader_idx": dataloader_idx}
+
+    def variant_prediction(self, batch):
+        """:909-1004 — (ref, het, hom) triplet; the three samples run as ONE batched pass instead of three
+        sequential batch-1 forwards (identical results: items are independent)."""
+        x = batch["cre_sequences"]
+        n = len(x)
+        if n == 0:
+            return {"pred_gene_exp": [], "embd": [], "variant_type": batch["variant_type"],
+                    "gene_token_embedding": [], "cre_token_embedding": []}
+        cpos, gpos = batch["cre_token_position"], batch["gene_token_position"]
+        assert len(cpos) == 3 and len(gpos) == 3, "there should be 3 samples in the batch for ref, het, hom"
+        cpos = None if torch.isnan(torch.as_tensor(cpos, dtype=torch.float)).any() else cpos
+        gpos = None if torch.isnan(torch.as_tensor(gpos, dtype=torch.float)).any() else gpos
+        pred, _, embd, gtok, ctok = self(x, batch["cre_attention_masks"], batch["tissue_context"], batch["ref_labels"],
+                                         batch["strand"], batch["gene_embeddings"], batch["gene_attention_masks"],
+                                         return_embedding=True, cre_token_position=cpos, gene_token_position=gpos)
+        arrs = [t.cpu().float().numpy() for t in (pred, embd, gtok, ctok)]
+        outs = [[], [], [], []]
+        s = 0
+        for i in range(n):
+            e = s + len(batch["tissue_context"][i])
+            for o, a in zip(outs, arrs):
+                o.append(a[s:e])
+            s = e
+        return {"pred_gene_exp": outs[0], "embd": outs[1], "variant_type": batch["variant_type"],
+                "gene_token_embedding": outs[2], "cre_token_embedding": outs[3]}
+
+
+def attach_trainer(model, precision="bf16-mixed"):
+    """Mimic Lightning's `model.trainer` attribute (read at model_combined_modulator.py:736)."""
+    model.trainer = SimpleNamespace(precision=precision)
+    return model

@@ -30,20 +30,20 @@ NUM_REF_CRES = 9   # len(utils.constants.REF_CREs)
 
 def _linear(sd, g, name, out_f, in_f, dtype):
     bound = 1.0 / math.sqrt(in_f)
-    sd[name + ".weight"] = ((torch.rand(out_f, in_f, generator=g) * 2 - 1) * bound).to(dtype)
-    sd[name + ".bias"] = ((torch.rand(out_f, generator=g) * 2 - 1) * bound).to(dtype)
+    sd[name + ".weight"] = ((torch.rand(out_f, in_f, generator=g, device=g.device) * 2 - 1) * bound).to(dtype)
+    sd[name + ".bias"] = ((torch.rand(out_f, generator=g, device=g.device) * 2 - 1) * bound).to(dtype)
 
 
 def _norm(sd, g, name, d, dtype):
     # perturbed around (1, 0) so that gamma/beta handling is actually exercised by parity tests
-    sd[name + ".weight"] = (1.0 + 0.1 * torch.randn(d, generator=g)).to(dtype)
-    sd[name + ".bias"] = (0.1 * torch.randn(d, generator=g)).to(dtype)
+    sd[name + ".weight"] = (1.0 + 0.1 * torch.randn(d, generator=g, device=g.device)).to(dtype)
+    sd[name + ".bias"] = (0.1 * torch.randn(d, generator=g, device=g.device)).to(dtype)
 
 
 def seq2reg_state_dict(hp, prefix, g, dtype=torch.float32):
     sd = {}
     d = hp["embedding_dim"]
-    sd[prefix + "token_embedding.weight"] = torch.randn(hp["vocab_size"], d, generator=g).to(dtype)
+    sd[prefix + "token_embedding.weight"] = torch.randn(hp["vocab_size"], d, generator=g, device=g.device).to(dtype)
     for l in range(hp["num_layers"]):
         p = f"{prefix}transformer_encoder.{l}."
         _linear(sd, g, p + "MHA.Wqkv", 3 * d, d, dtype)
@@ -56,25 +56,27 @@ def seq2reg_state_dict(hp, prefix, g, dtype=torch.float32):
     return sd
 
 
-def make_state_dict(cfg=None, seq2reg_hp=None, seed=0, dtype=torch.float32):
+def make_state_dict(cfg=None, seq2reg_hp=None, seed=0, dtype=torch.float32, device="cpu"):
+    """device='cpu' is the bit-reproducible stream the golden fixtures use; device='cuda' draws from the CUDA
+    generator instead (different values, same distributions) for fast full-size benchmark set-up."""
     cfg = dict(V4_PCG_MODEL if cfg is None else cfg)
     hp = dict(SEQ2REG_HP if seq2reg_hp is None else seq2reg_hp)
-    g = torch.Generator().manual_seed(seed)
+    g = torch.Generator(device=device).manual_seed(seed)
     D, H = cfg["emb_dim"], cfg["num_heads"]
     sd = {}
-    sd["start_tkn.registry_tokens.weight"] = torch.randn(cfg["num_tissues"], D, generator=g).to(dtype)
+    sd["start_tkn.registry_tokens.weight"] = torch.randn(cfg["num_tissues"], D, generator=g, device=g.device).to(dtype)
     sd.update(seq2reg_state_dict(hp, "cre_tokenizer.", g, dtype))
     sd.update(seq2reg_state_dict(hp, "gene_tokenizer.", g, dtype))
     _linear(sd, g, "gene_map", D, cfg["gene_emb_dim"], dtype)
     if cfg["token_dim"] != D:
         _linear(sd, g, "cre_map", D, cfg["token_dim"], dtype)
-    sd["combined_modulator.second_level_context_embedding.weight"] = torch.randn(NUM_REF_CRES, D, generator=g).to(dtype)
+    sd["combined_modulator.second_level_context_embedding.weight"] = torch.randn(NUM_REF_CRES, D, generator=g, device=g.device).to(dtype)
     slopes = alibi_slopes(H)
     for stream, n in (("cre_layers", cfg["num_layers"] - 1), ("gene_layers", cfg["num_layers"])):
         for l in range(n):
             p = f"combined_modulator.{stream}.{l}."
             if cfg.get("use_alibi", True):
-                sd[p + "m"] = slopes.clone()
+                sd[p + "m"] = slopes.clone().to(g.device)
             _linear(sd, g, p + "mixer.MHA.Wqkv", 3 * D, D, dtype)
             _linear(sd, g, p + "mixer.MHA.out_proj", D, D, dtype)
             _linear(sd, g, p + "crossMHA.MHA.Wq", D, D, dtype)
