@@ -55,8 +55,12 @@ def sinusoidal_pe(d_model: int, length: int) -> torch.Tensor:
 class _Num:
     """Numerics policy: plain fp32, or bf16-rounded GEMM/attention operands."""
 
-    def __init__(self, emulate_bf16=False):
+    def __init__(self, emulate_bf16=False, stream_bf16=False):
         self.bf16 = emulate_bf16
+        self.stream_bf16 = stream_bf16        # design probe: residual stream rounded to bf16 after every add
+
+    def s(self, x):
+        return x.to(torch.bfloat16).float() if self.stream_bf16 else x
 
     def r(self, x):
         return x.to(torch.bfloat16).float() if self.bf16 else x
@@ -131,8 +135,8 @@ def seq2reg_embed(sd, pre, hp, tokens, pad_mask, num=None):
         p = f"{pre}transformer_encoder.{l}."
         src = x
         a = _mha_self(num, sd, p + "MHA.", _ln(sd, p + "norm1.", src), cu, H, slopes)
-        x = a + src
-        x = _geglu_ffn(num, sd, p, _ln(sd, p + "norm2.", x)) + src          # res_long = layer input
+        x = num.s(a + src)
+        x = num.s(_geglu_ffn(num, sd, p, _ln(sd, p + "norm2.", x)) + src)   # res_long = layer input
     seg = torch.repeat_interleave(torch.arange(n), lens)
     out = torch.zeros(n, x.shape[1]).index_add_(0, seg, x)
     return out / lens[:, None]                                              # 0/0 = NaN for an all-pad window, as upstream
@@ -141,10 +145,10 @@ def seq2reg_embed(sd, pre, hp, tokens, pad_mask, num=None):
 def _context_layer(num, sd, p, src, cu_src, context, cu_ctx, H, slopes):
     """ContextFlashAttentionEncoderLayer.forward on unpadded streams (layers.py:88-165)."""
     a = _mha_self(num, sd, p + "mixer.MHA.", _ln(sd, p + "norm1.", src), cu_src, H, slopes)
-    x = a + src
+    x = num.s(a + src)
     c = _mha_cross(num, sd, p + "crossMHA.MHA.", _ln(sd, p + "norm2.", x), context, cu_src, cu_ctx, H)
-    x = c + x
-    return _geglu_ffn(num, sd, p, _ln(sd, p + "norm3.", x)) + src
+    x = num.s(c + x)
+    return num.s(_geglu_ffn(num, sd, p, _ln(sd, p + "norm3.", x)) + src)
 
 
 def head(num, sd, e):
@@ -158,14 +162,14 @@ def head(num, sd, e):
 
 @torch.no_grad()
 def predict_step(sd, cfg, seq2reg_hp, batch, schedule="reference", emulate_bf16=False,
-                 return_streams=False):
+                 return_streams=False, stream_bf16=False):
     """Restates Seq2GenePredictorCombinedModulator.predict_step for the vf_model.yaml variant
     (use_context, multi_registry, not only_cross_attention, shared bigger head).
 
     batch: dict with the reference's collate keys (vcfdataset.py:53-63).
     -> {"pred_gene_exp": [np (T_i,1)], "embeddings": [np (T_i,emb)]}
     """
-    num = _Num(emulate_bf16)
+    num = _Num(emulate_bf16, stream_bf16)
     H, NL, D = cfg["num_heads"], cfg["num_layers"], cfg["emb_dim"]
     slopes = alibi_slopes(H) if cfg.get("use_alibi", True) else None
     B = len(batch["cre_sequences"])
@@ -196,11 +200,11 @@ def predict_step(sd, cfg, seq2reg_hp, batch, schedule="reference", emulate_bf16=
                 return _context_layer(num, sd, p, gx, cu_gene, cx, cu_cre_for_gene, H, slopes)
             # dedup: every tissue copy attends to the single shared CRE stream
             a = _mha_self(num, sd, p + "mixer.MHA.", _ln(sd, p + "norm1.", gx), cu_gene, H, slopes)
-            x = a + gx
+            x = num.s(a + gx)
             c = _mha_cross(num, sd, p + "crossMHA.MHA.", _ln(sd, p + "norm2.", x), cx,
                            [0, gx.shape[0]], [0, Cn], H)
-            x = c + x
-            return _geglu_ffn(num, sd, p, _ln(sd, p + "norm3.", x)) + gx
+            x = num.s(c + x)
+            return num.s(_geglu_ffn(num, sd, p, _ln(sd, p + "norm3.", x)) + gx)
 
         gx = gene_layer(0, gx, cx)
         for i in range(NL - 1):
