@@ -8,10 +8,11 @@
 //   seq2gene/model_combined_modulator.py:502-507 (gene_map, cre_map),
 //   seq2gene/modules/layers.py:1078-1087 (head Linear layers).
 //
-// Kernel shape: persistent, one CTA per SM, 192 threads:
+// Kernel shape: persistent, one CTA per SM, 320 threads:
 //   warp 0   : TMA producer (one elected lane)       smem ring of kStages x (A 128x64 + W 256x64) bf16
 //   warp 1   : TMEM allocator + tcgen05.mma issuer   UMMA 128x256x16, 4 per k-block
-//   warps 2-5: epilogue (TMEM lane quadrant = warp%4) bias / GeGLU / +residual, direct 16-byte stores
+//   warps 2-9: epilogue (TMEM lane quadrant = warp%4, two warps per quadrant): pipelined tcgen05.ld, bias /
+//              GeGLU / GELU / +residual, transposed through a swizzled smem tile for fully coalesced stores
 // Two 256-column fp32 accumulators (all 512 TMEM columns) double-buffer the
 // epilogue of tile i against the mainloop of tile i+1.
 #include <cuda.h>
@@ -23,10 +24,13 @@
 namespace vf {
 
 constexpr int BM = 128, BN = 256, BK = 64, kStages = 4;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;                          // two warps per TMEM lane quadrant
+constexpr int kGemmThreads = 64 + kEpiWarps * 32;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
-constexpr size_t kGemmSmem = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 /*barriers*/;
+constexpr uint32_t kStageOutBytes = 32 * 32 * 4;      // per-epilogue-warp staging tile: 32 rows x 32 fp32 columns
+constexpr size_t kGemmSmem = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + kEpiWarps * kStageOutBytes +
+                             256 /*barriers*/;
 
 struct GemmParams {
     int M, N, K;
@@ -39,46 +43,76 @@ struct GemmParams {
     int ldo2;
 };
 
-// One 32-column slab of one accumulator row -> global memory.
 template <int EPI>
-__device__ __forceinline__ void epilogue_store(const GemmParams& p, int row, int col0, const float (&v)[32]) {
-    // col0 = first OUTPUT column of this slab; v already holds bias/activation-applied values
-    if constexpr (EPI == VF_EPI_BIAS_BF16 || EPI == VF_EPI_BIAS_GEGLU_BF16 || EPI == VF_EPI_BIAS_GELU_BF16) {
-        const int n_out = (EPI == VF_EPI_BIAS_GEGLU_BF16) ? p.N / 2 : p.N;
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + col0;
+constexpr bool epi_is_bf16() {
+    return EPI == VF_EPI_BIAS_BF16 || EPI == VF_EPI_BIAS_GEGLU_BF16 || EPI == VF_EPI_BIAS_GELU_BF16;
+}
+
+// One 32-row x 32-column slab (thread = row, v = its 32 finished values) -> global memory, transposed through the
+// warp's private shared-memory tile so that every global access is a run of full 32-byte sectors:
+//   bf16 out : rows are 64 B; a warp instruction stores 8 rows x 64 B
+//   fp32 out : rows are 128 B; a warp instruction loads the residual / stores 4 rows x 128 B
+// 16-byte chunks are XOR-swizzled inside the tile so both the row-wise writes and the column-wise reads are
+// bank-conflict free.
+// Residual slab prefetch: the 8 float4 this lane will add in the coalesced phase (4 rows x 128 B per warp request).
+// Issued as one batch well before they are needed so DRAM latency overlaps the TMEM load and the staging writes
+// (loads cannot be hoisted by the compiler itself: `out` may alias `resid`).
+__device__ __forceinline__ void load_resid_slab(const GemmParams& p, int row0, int col0, int lane, float4 (&rr4)[8]) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int grow = row0 + it * 4 + (lane >> 3), gcol = col0 + (lane & 7) * 4;
+        rr4[it] = (p.resid && grow < p.M && gcol + 4 <= p.N)
+                      ? *reinterpret_cast<const float4*>(p.resid + (size_t)grow * p.ldr + gcol)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_store_slab(const GemmParams& p, uint8_t* stage, int row0, int col0, int n_out,
+                                                    const float (&v)[32], int lane, const float4 (&rr4)[8]) {
+    if constexpr (epi_is_bf16<EPI>()) {
+        uint4* st = reinterpret_cast<uint4*>(stage);                    // [32 rows][4 chunks of 16 B]
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (col0 + j * 8 + 8 <= n_out) {
-                uint4 q;
-                q.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]);
-                q.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
-                q.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]);
-                q.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
-                *reinterpret_cast<uint4*>(o + j * 8) = q;
-            }
+            uint4 q;
+            q.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]); q.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
+            q.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]); q.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
+            st[lane * 4 + (j ^ ((lane >> 1) & 3))] = q;
         }
+        __syncwarp();
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + (lane >> 2), jj = lane & 3;
+            const uint4 q = st[rr * 4 + (jj ^ ((rr >> 1) & 3))];
+            const int grow = row0 + rr, gcol = col0 + jj * 8;
+            if (grow < p.M && gcol + 8 <= n_out) *reinterpret_cast<uint4*>(o + (size_t)grow * p.ldo + gcol) = q;
+        }
+        __syncwarp();
     } else {
-        float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
+        float4* st = reinterpret_cast<float4*>(stage);                  // [32 rows][8 chunks of 16 B]
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (col0 + j * 4 + 4 <= p.N) {
-                *reinterpret_cast<float4*>(o + j * 4) = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
-            }
-        }
-        if (p.out2) {
-            __nv_bfloat16* o2 = p.out2 + (size_t)row * p.ldo2 + col0;
+        for (int j = 0; j < 8; ++j)
+            st[lane * 8 + (j ^ (lane & 7))] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+        __syncwarp();
+        float* o = reinterpret_cast<float*>(p.out);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (col0 + j * 8 + 8 <= p.N) {
-                    uint4 q;
-                    q.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]);
-                    q.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
-                    q.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]);
-                    q.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
-                    *reinterpret_cast<uint4*>(o2 + j * 8) = q;
+        for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + (lane >> 3), jj = lane & 7;
+            float4 q = st[rr * 8 + (jj ^ (rr & 7))];
+            const int grow = row0 + rr, gcol = col0 + jj * 4;
+            if (grow < p.M && gcol + 4 <= n_out) {
+                if constexpr (EPI == VF_EPI_BIAS_RESID_F32) {
+                    q.x += rr4[it].x; q.y += rr4[it].y; q.z += rr4[it].z; q.w += rr4[it].w;
+                }
+                *reinterpret_cast<float4*>(o + (size_t)grow * p.ldo + gcol) = q;
+                if (p.out2) {
+                    uint2 h; h.x = pack_bf16x2(q.x, q.y); h.y = pack_bf16x2(q.z, q.w);
+                    *reinterpret_cast<uint2*>(p.out2 + (size_t)grow * p.ldo2 + gcol) = h;
                 }
             }
         }
+        __syncwarp();
     }
 }
 
@@ -90,7 +124,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;                                  // kStages x 16 KB
     uint8_t* smem_b = smem + kStages * kABytes;              // kStages x 32 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint8_t* smem_out = smem + kStages * kStageBytes;        // kEpiWarps x 4 KB staging tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + kEpiWarps * kStageOutBytes);
     uint64_t* full = bars;                 // [kStages]
     uint64_t* empty = bars + kStages;      // [kStages]
     uint64_t* tmem_full = bars + 2 * kStages;       // [2]
@@ -106,7 +141,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -163,76 +198,89 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         __syncwarp();
     } else {
         // ================= epilogue warps =================
-        const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
+        // warp%4 selects the TMEM lane quadrant (hardware rule); the two warps of a quadrant interleave the
+        // 32-column slabs (even / odd).  TMEM loads are software-pipelined: slab i+1 is in flight while slab i is
+        // converted and stored.
+        const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int lane = threadIdx.x & 31;
+        uint8_t* stage_out = smem_out + (warp - 2) * kStageOutBytes;
+        constexpr int kSlabs = (EPI == VF_EPI_BIAS_GEGLU_BF16) ? 2 : 4;      // per warp per tile
+        const int n_out = (EPI == VF_EPI_BIAS_GEGLU_BF16) ? p.N / 2 : p.N;
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
             const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
-            const int row = m0 + quad * 32 + lane;
+            const int row0 = m0 + quad * 32;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
             if constexpr (EPI == VF_EPI_BIAS_GEGLU_BF16) {
-                // W rows are tile-interleaved: accumulator columns [0,128) = u, [128,256) = gate of the
-                // same 128 output columns (layers.py:159-160: u, gate = chunk(2); out = u * gelu(gate)).
+                // W rows are tile-interleaved: accumulator columns [0,128) = u, [128,256) = gate of the same 128
+                // output columns (layers.py:159-160: u, gate = chunk(2); out = u * gelu(gate)).
                 const int out0 = (n0 / BN) * (BN / 2);
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    if (n0 + c * 32 >= p.N) break;
-                    uint32_t ru[32], rg[32];
-                    tmem_ld_32x32(t_row + c * 32, ru);
-                    tmem_ld_32x32(t_row + 128 + c * 32, rg);
+                uint32_t ru[2][32], rg[2][32];
+                tmem_ld_32x32(t_row + half * 32, ru[0]);
+                tmem_ld_32x32(t_row + 128 + half * 32, rg[0]);
+#pragma unroll
+                for (int i = 0; i < kSlabs; ++i) {
+                    const int c = half + 2 * i;                           // 32-column slab of the 128 outputs
                     tmem_ld_wait();
+                    if (i + 1 < kSlabs) {
+                        tmem_ld_32x32(t_row + (c + 2) * 32, ru[(i + 1) & 1]);
+                        tmem_ld_32x32(t_row + 128 + (c + 2) * 32, rg[(i + 1) & 1]);
+                    }
                     float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float u = __uint_as_float(ru[j]), g = __uint_as_float(rg[j]);
-                        if (p.bias) { u += __ldg(p.bias + n0 + c * 32 + j); g += __ldg(p.bias + n0 + 128 + c * 32 + j); }
-                        v[j] = u * gelu_erf(g);
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 bu = make_float4(0.f, 0.f, 0.f, 0.f), bg = bu;
+                        if (p.bias) {
+                            bu = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c * 32 + j));
+                            bg = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 128 + c * 32 + j));
+                        }
+                        v[j + 0] = (__uint_as_float(ru[i & 1][j + 0]) + bu.x) * gelu_erf(__uint_as_float(rg[i & 1][j + 0]) + bg.x);
+                        v[j + 1] = (__uint_as_float(ru[i & 1][j + 1]) + bu.y) * gelu_erf(__uint_as_float(rg[i & 1][j + 1]) + bg.y);
+                        v[j + 2] = (__uint_as_float(ru[i & 1][j + 2]) + bu.z) * gelu_erf(__uint_as_float(rg[i & 1][j + 2]) + bg.z);
+                        v[j + 3] = (__uint_as_float(ru[i & 1][j + 3]) + bu.w) * gelu_erf(__uint_as_float(rg[i & 1][j + 3]) + bg.w);
                     }
-                    if (row < p.M) epilogue_store<EPI>(p, row, out0 + c * 32, v);
+                    float4 none[8];
+                    epilogue_store_slab<EPI>(p, stage_out, row0, out0 + c * 32, n_out, v, lane, none);
                 }
             } else {
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[2][32];
+                float4 rr4[2][8];
+                const bool any = n0 + half * 32 < p.N;
+                if (any) tmem_ld_32x32(t_row + half * 32, r[0]);
+                if constexpr (EPI == VF_EPI_BIAS_RESID_F32) {
+                    if (any) load_resid_slab(p, row0, n0 + half * 32, lane, rr4[0]);
+                }
+#pragma unroll
+                for (int i = 0; i < kSlabs; ++i) {
+                    const int c = half + 2 * i;
                     const int col0 = n0 + c * 32;
-                    if (col0 >= p.N) break;
-                    uint32_t r[32];
-                    tmem_ld_32x32(t_row + c * 32, r);
+                    if (col0 >= p.N) break;                               // warp-uniform
+                    if constexpr (EPI == VF_EPI_BIAS_RESID_F32) {        // next slab's residual: one slab ahead
+                        if (i + 1 < kSlabs && col0 + 64 < p.N) load_resid_slab(p, row0, col0 + 64, lane, rr4[(i + 1) & 1]);
+                    }
                     tmem_ld_wait();
+                    if (i + 1 < kSlabs && col0 + 64 < p.N) tmem_ld_32x32(t_row + (c + 2) * 32, r[(i + 1) & 1]);
                     float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if (p.bias) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            if (col0 + j + 4 <= p.N) {
-                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                            }
-                        }
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.bias && col0 + j + 4 <= p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                        v[j + 0] = __uint_as_float(r[i & 1][j + 0]) + b.x; v[j + 1] = __uint_as_float(r[i & 1][j + 1]) + b.y;
+                        v[j + 2] = __uint_as_float(r[i & 1][j + 2]) + b.z; v[j + 3] = __uint_as_float(r[i & 1][j + 3]) + b.w;
                     }
                     if constexpr (EPI == VF_EPI_BIAS_GELU_BF16) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
                     }
-                    if constexpr (EPI == VF_EPI_BIAS_RESID_F32) {
-                        if (row < p.M && p.resid) {
-                            const float* rr = p.resid + (size_t)row * p.ldr + col0;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                if (col0 + j + 4 <= p.N) {
-                                    const float4 b = *reinterpret_cast<const float4*>(rr + j);
-                                    v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                                }
-                            }
-                        }
-                    }
-                    if (row < p.M) epilogue_store<EPI>(p, row, col0, v);
+                    epilogue_store_slab<EPI>(p, stage_out, row0, col0, n_out, v, lane, rr4[i & 1]);
                 }
             }
             // all TMEM reads of this accumulator are complete (wait::ld above) -> hand it back to the MMA warp
+            tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
