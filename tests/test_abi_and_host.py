@@ -1,0 +1,96 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/vf_b200.h declares; product code has no
+CPU fallback; ingest parsers; config surface."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from variantformer_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "vf_b200.h")).read()
+    declared = set(re.findall(r"\b(vf_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()                                    # dlopen only, no device access
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.vf_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    import torch
+    from variantformer_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip("needs a GPU-less machine")
+    with pytest.raises(_lib.VFError, match="no CPU fallback"):
+        _lib.lib()
+    from variantformer_b200.processors.model_manager import ModelManager
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ModelManager({"model_class": "Seq2GenePredictorCombinedModulator"})
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "variantformer_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+                assert "fake_ops" not in src
+
+
+def test_ingest_fasta_and_vcf(tmp_path):
+    from variantformer_b200 import ingest
+    fa = tmp_path / "g.fa"
+    fa.write_text(">chr1 desc\nACGTacgtNN\nGGCC\n>chr2\nTTTT\n")
+    g = ingest.load_fasta(str(fa))
+    assert g["chr1"].tobytes() == b"ACGTacgtNNGGCC" and g["chr2"].tobytes() == b"TTTT"
+    assert list(ingest.load_fasta(str(fa), chroms={"chr2"})) == ["chr2"]
+    vcf = tmp_path / "s.vcf"
+    vcf.write_text("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS1\tS2\n"
+                   "chr1\t5\t.\tA\tG\t.\t.\t.\tGT\t0/1\t1/1\n"
+                   "chr1\t2\t.\tC\tT,G\t.\t.\t.\tGT:DP\t1|2:9\t0/0\n"
+                   "chr1\t7\t.\tGT\tG\t.\t.\t.\tGT\t1/1\t./.\n"
+                   "chr1\t9\t.\tN\t<DEL>\t.\t.\t.\tGT\t1/1\t1/1\n"
+                   "chr1\t11\t.\tG\tGAA\t.\t.\t.\tGT\t0|1\t0/0\n"
+                   "chr2\t1\t.\tT\tC\t.\t.\t.\tGT\t0/0\t0/1\n")
+    v = ingest.load_vcf_sample(str(vcf), sample="S1")
+    c1 = v["chr1"]
+    assert c1["pos"].tolist() == [1, 4, 6, 10] and c1["ref_len"].tolist() == [1, 1, 2, 1]
+    assert c1["alt"] == [b"K", b"G", b"G", b"GAA"] and c1["gt"].tolist() == [2, 1, 2, 1]     # 1|2 het SNP -> IUPAC K
+    assert "chr2" not in v
+    v2 = ingest.load_vcf_sample(str(vcf), sample="S2")
+    assert v2["chr1"]["pos"].tolist() == [4] and v2["chr1"]["gt"].tolist() == [2] and v2["chr2"]["gt"].tolist() == [1]
+
+
+def test_config_surface():
+    from variantformer_b200.utils.config import CONFIG_DIR, Config, load_yaml
+    cfg = load_yaml(os.path.join(CONFIG_DIR, "vf_model.yaml"))
+    m = cfg.v4_pcg.model
+    assert m.model_class == "Seq2GenePredictorCombinedModulator" and m.emb_dim == 1536 and m["num_layers"] == 25
+    c = m.copy(); del c["cre_tokenizer"]; delattr(c, "gene_tokenizer")
+    assert "cre_tokenizer" in m and "cre_tokenizer" not in c and c.get("nope", 3) == 3
+    assert cfg.v4_pcg.dataset.max_chunks == 200 and cfg.v4_ag.model.checkpoint_path.endswith("v4_ag_epoch9_checkpoint.pth")
+    assert isinstance(Config({"a": {"b": 1}}).a, Config)
+
+
+def test_merge_table_property_and_hf_loader():
+    from variantformer_b200.stage1 import load_merge_table
+    a, b, c, vocab = load_merge_table()
+    assert len(a) == 482 and len(vocab) == 500 and (c == np.arange(18, 500)).all()
+    assert (a < c).all() and (b < c).all()               # operands pre-exist: the rank-sweep kernel's precondition
+    assert int((a == b).sum()) == 27                     # self-pair merges
+
+
+def test_window_arithmetic_matches_oracle():
+    from oracle import stage1 as O
+    from variantformer_b200.stage1 import cre_window, gene_window
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        s = int(rng.integers(0, 2_000_000)); e = s + int(rng.integers(1, 900_000))
+        assert cre_window(s, e, 50) == O.cre_window(s, e, 50)
+        for strand in "+-":
+            assert gene_window(s, e, strand, 1000, 300000) == O.gene_window(s, e, strand == "-")
