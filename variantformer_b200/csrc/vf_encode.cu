@@ -8,6 +8,8 @@
 //   reverse_complement                                          (utils/functions.py:129-172)
 //   BPEEncoder.normalize / encode (HF tokenizers BPE)            (utils/seq.py:32-62)
 //   __adjust_length / chunkify_data                              (datasets/vcfdataset.py:198-217, :338-394)
+#include <cooperative_groups.h>
+
 #include "vf_common.cuh"
 #include "vf_internal.h"
 
@@ -289,18 +291,200 @@ __global__ void bpe_tokenize_kernel(const BpeParams p) {
     if (tid == 0) p.out_count[w] = total;
 }
 
+// ---------------------------------------------------------------------------------
+// Long windows (gene windows, ~301 k symbols): one thread-block CLUSTER per window.  Each CTA keeps a contiguous
+// segment of the symbol array in its own shared memory; neighbours are reached through distributed shared memory
+// (forward "next alive symbol" scans cross a segment boundary by at most 7 slots, self-pair run scans by the run
+// length).  One cluster barrier per applied rank (two for self pairs).  The per-token-id occupancy counters that
+// drive the uniform skip decision are replicated in every CTA; the delta of applied sweep k is added to replica
+// (k+1)&1 before that sweep's barrier and to replica k&1 after it, so the replica read after k applied sweeps is
+// always complete without an extra barrier.
+// ---------------------------------------------------------------------------------
+constexpr int kBpeCluster = 8;
+
+__global__ void __launch_bounds__(1024, 1)
+bpe_tokenize_cluster_kernel(const BpeParams p, const int seg_cap) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ uint16_t s_sym[];                  // seg_cap symbols of this CTA's segment
+    __shared__ int s_cnt[2][kMaxVocab];                  // replicated occupancy counters (double buffered)
+    __shared__ uint16_t* s_peer[kBpeCluster];
+    __shared__ int* s_peer_cnt[kBpeCluster];
+    __shared__ int s_merged[2];
+    __shared__ int s_segcnt[kBpeCluster];
+    __shared__ int s_warp_tot[32];
+    const int rank = (int)cluster.block_rank();
+    const int w = blockIdx.x / kBpeCluster;
+    const int n = p.len[w];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int seg = max(8, (n + kBpeCluster - 1) / kBpeCluster);      // <= seg_cap (host guarantees)
+    const int lo = min(n, rank * seg), hi = min(n, lo + seg);
+    const uint8_t* src = p.seq + (size_t)w * p.pitch;
+
+    if (tid < kBpeCluster) {
+        s_peer[tid] = cluster.map_shared_rank(s_sym, tid);
+        s_peer_cnt[tid] = cluster.map_shared_rank(&s_cnt[0][0], tid);
+    }
+    for (int i = tid; i < 2 * kMaxVocab; i += nt) (&s_cnt[0][0])[i] = 0;
+    if (tid < 2) s_merged[tid] = 0;
+    __syncthreads();
+    // local histogram in replica 0 slots of a scratch copy: count into registers-free smem then publish
+    __shared__ int s_hist[32];                            // base ids 4..17 only
+    if (tid < 32) s_hist[tid] = 0;
+    cluster.sync();                                       // every CTA's counters are zeroed before anyone publishes
+    for (int i = lo + tid; i < hi; i += nt) {
+        const uint16_t b = base_symbol(src[i]);
+        s_sym[i - lo] = b;
+        if (b != kSep) atomicAdd(&s_hist[b], 1);
+    }
+    __syncthreads();
+    if (tid < 32 && s_hist[tid] != 0) {
+        for (int c = 0; c < kBpeCluster; ++c) {
+            atomicAdd(s_peer_cnt[c] + tid, s_hist[tid]);
+            atomicAdd(s_peer_cnt[c] + kMaxVocab + tid, s_hist[tid]);
+        }
+    }
+    cluster.sync();
+
+    auto LD = [&](int pos) -> uint16_t {
+        if (pos >= lo && pos < hi) return s_sym[pos - lo];
+        const int c = pos / seg;
+        return s_peer[c][pos - c * seg];
+    };
+    auto ST = [&](int pos, uint16_t v) {
+        if (pos >= lo && pos < hi) { s_sym[pos - lo] = v; return; }
+        const int c = pos / seg;
+        s_peer[c][pos - c * seg] = v;
+    };
+    auto publish = [&](int buf, uint16_t a, uint16_t b, uint16_t c, int m) {      // thread 0 only
+        for (int r = 0; r < kBpeCluster; ++r) {
+            int* cnt = s_peer_cnt[r] + buf * kMaxVocab;
+            atomicAdd(cnt + c, m); atomicSub(cnt + a, m); atomicSub(cnt + b, m);
+        }
+    };
+
+    int k = 0;                                            // applied sweeps so far (cluster-uniform)
+    for (int r = 0; r < p.n_merges; ++r) {
+        const uint16_t a = p.merge_a[r], b = p.merge_b[r], c = p.merge_new[r];
+        const int* cnt = s_cnt[k & 1];
+        if (cnt[a] == 0 || cnt[b] == 0 || (a == b && cnt[a] < 2)) continue;       // uniform over the whole cluster
+        int merged = 0;
+        if (a != b) {
+            for (int i = lo + tid; i < hi; i += nt) {
+                if (s_sym[i - lo] != a) continue;
+                int j = i + 1;
+                while (j < n && LD(j) == kDead) ++j;
+                if (j < n && LD(j) == b) { s_sym[i - lo] = c; ST(j, kDead); ++merged; }
+            }
+        } else {
+            const uint16_t mark = (uint16_t)(c | 0x8000);
+            for (int i = lo + tid; i < hi; i += nt) {
+                if (s_sym[i - lo] != a) continue;
+                int kk = 0, q = i - 1;
+                for (;;) {
+                    while (q >= 0 && LD(q) == kDead) --q;
+                    if (q < 0) break;
+                    const uint16_t sq = LD(q);
+                    if (sq != a && sq != mark) break;
+                    ++kk; --q;
+                }
+                if (kk & 1) continue;
+                int j = i + 1;
+                while (j < n && LD(j) == kDead) ++j;
+                if (j < n) { const uint16_t sj = LD(j); if (sj == a || sj == mark) s_sym[i - lo] = mark; }
+            }
+            cluster.sync();
+            for (int i = lo + tid; i < hi; i += nt) {
+                if (s_sym[i - lo] != mark) continue;
+                int j = i + 1;
+                while (j < n && LD(j) == kDead) ++j;
+                ST(j, kDead); s_sym[i - lo] = c; ++merged;
+            }
+        }
+        if (merged) atomicAdd(&s_merged[k & 1], merged);
+        __syncthreads();
+        int m = 0;
+        if (tid == 0) {
+            m = s_merged[k & 1];
+            s_merged[(k + 1) & 1] = 0;
+            if (m) publish((k + 1) & 1, a, b, c, m);      // early copy: the replica the NEXT decisions read
+        }
+        cluster.sync();
+        if (tid == 0 && m) publish(k & 1, a, b, c, m);    // late copy: read only after the next applied sweep's barrier
+        ++k;
+    }
+    cluster.sync();                                       // late publishes + all symbol writes have landed
+
+    // ---- ordered compaction of this CTA's segment; token offset = alive symbols of the lower-ranked segments ----
+    const int len_seg = hi - lo;
+    const int per = (len_seg + nt - 1) / nt;
+    const int b0 = min(len_seg, tid * per), b1 = min(len_seg, b0 + per);
+    int mine = 0;
+    for (int i = b0; i < b1; ++i) mine += (s_sym[i] < kSep);
+    int incl = mine;
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        const int v = lane < (nt >> 5) ? s_warp_tot[lane] : 0;
+        int inc2 = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc2, o); if (lane >= o) inc2 += u; }
+        s_warp_tot[lane] = inc2 - v;
+        if (lane == 31) {
+            for (int c2 = 0; c2 < kBpeCluster; ++c2) cluster.map_shared_rank(&s_segcnt[0], c2)[rank] = inc2;
+        }
+    }
+    cluster.sync();
+    int base = 0, total = 0;
+    for (int c2 = 0; c2 < kBpeCluster; ++c2) { if (c2 < rank) base += s_segcnt[c2]; total += s_segcnt[c2]; }
+    int o = base + s_warp_tot[wid] + incl - mine;
+    int32_t* out = p.out_tokens + (size_t)w * p.out_pitch;
+    int32_t* ost = p.out_start ? p.out_start + (size_t)w * p.start_pitch : nullptr;
+    for (int i = b0; i < b1; ++i) {
+        const uint16_t sy = s_sym[i];
+        if (sy < kSep) {
+            if (o < p.out_cap) out[o] = sy;
+            if (ost) ost[o] = lo + i;
+            ++o;
+        }
+    }
+    for (int i = min(total, p.out_cap) + rank * nt + tid; i < p.out_pitch; i += nt * kBpeCluster) out[i] = 0;
+    if (rank == 0 && tid == 0) p.out_count[w] = total;
+    cluster.sync();                                       // keep every CTA's shared memory alive until all peers are done
+}
+
 int bpe_tokenize(const uint8_t* seq, int64_t pitch, const int32_t* len, int n_win, int max_len,
                  const uint16_t* merge_a, const uint16_t* merge_b, const uint16_t* merge_new, int n_merges,
                  uint16_t* scratch, int64_t scratch_pitch, int32_t* out_tokens, int out_pitch, int out_cap,
                  int32_t* out_count, int32_t* out_start, int64_t start_pitch, cudaStream_t s) {
     if (n_win == 0) return 0;
     VF_REQUIRE(out_cap <= out_pitch, "bpe_tokenize: out_cap %d > out_pitch %d", out_cap, out_pitch);
-    const bool needs_scratch = max_len > kBpeSmemSyms;
-    VF_REQUIRE(!needs_scratch || (scratch && scratch_pitch >= max_len),
-               "bpe_tokenize: windows longer than %d symbols need a scratch row of >= max_len uint16", kBpeSmemSyms);
     VF_REQUIRE(out_start == nullptr || start_pitch >= max_len, "bpe_tokenize: start_pitch too small");
     BpeParams p{seq, pitch, len, merge_a, merge_b, merge_new, n_merges, scratch, scratch_pitch,
                 out_tokens, out_pitch, out_cap, out_count, out_start, start_pitch};
+    if (max_len > kBpeSmemSyms) {
+        // cluster path: 8 CTAs per window, segment of the symbol array per CTA in shared memory
+        const int seg_cap = (max_len + kBpeCluster - 1) / kBpeCluster + 8;
+        const size_t smem = (size_t)seg_cap * sizeof(uint16_t);
+        VF_REQUIRE(smem <= 200 * 1024, "bpe_tokenize: window of %d symbols exceeds the cluster kernel's capacity", max_len);
+        static size_t attr_smem = 0;
+        if (smem > attr_smem) {
+            VF_CUDA_OK(cudaFuncSetAttribute(bpe_tokenize_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)smem));
+            attr_smem = smem;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(n_win * kBpeCluster); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = kBpeCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        VF_CUDA_OK(cudaLaunchKernelEx(&cfg, bpe_tokenize_cluster_kernel, p, seg_cap));
+        return 0;
+    }
     const int threads = max_len <= 1024 ? 128 : 1024;
     const size_t smem = (size_t)kBpeSmemSyms * sizeof(uint16_t);
     bpe_tokenize_kernel<<<n_win, threads, smem, s>>>(p);
