@@ -70,6 +70,17 @@ int vf_attention_varlen(const void* q, int ldq, const void* k, int ldk, const vo
                         int n_tiles, int block_m, int heads, int head_dim, const float* slopes, void* stream);
 
 /*
+ * Same operation on the tcgen05 tensor cores (TMA-staged Q/K/V tiles, S and O accumulators in TMEM, one softmax
+ * thread per query row, two-pass exact softmax).  Work items are blocks of up to 4 x 128 query rows of one sequence:
+ * item_seq/item_q0 int32 [n_items] (a tile map built with 512 rows per item).  rows_q / rows_k = total rows of the
+ * q and k/v tensors (TMA bounds).  head_dim in {48, 64}.  Same reference call sites as vf_attention_varlen.
+ */
+int vf_attention_tc_varlen(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
+                           int64_t rows_q, int64_t rows_k, const int32_t* cu_q, const int32_t* cu_k,
+                           const int32_t* item_seq, const int32_t* item_q0, int n_items, int heads, int head_dim,
+                           const float* slopes, void* stream);
+
+/*
  * CRE x reference-label cross-attention collapsed to the 9 cCRE classes (exact identity):
  * q bf16 [n_rows, H*HD]; kv9 fp32 [9, 2*H*HD] = Wkv·Emb9 + b ((two,h,d) order); logc fp32 [n_seq,9] =
  * log(#CREs of the class in the row's gene) (-inf when absent); row_seq int32 [n_rows].

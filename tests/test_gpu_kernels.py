@@ -133,6 +133,40 @@ def test_cross_attention_stacked_queries(H, hd):
     assert torch.allclose(got.float(), want, atol=2e-2, rtol=2e-2), _describe_mismatch(got.float(), want, 2e-2)
 
 
+@pytest.mark.parametrize("H,hd,alibi,lens", [
+    (4, 48, True, [201, 201, 130, 640, 33, 1, 128, 129, 512, 513]),
+    (2, 64, False, [200, 97, 300]),
+    (32, 48, True, [1024, 201]),
+    (8, 64, True, [1300]),
+])
+def test_tc_self_attention(H, hd, alibi, lens):
+    n, d = sum(lens), H * hd
+    g = torch.Generator(device="cpu").manual_seed(H * hd + len(lens))
+    qkv = torch.randn(n, 3 * d, generator=g).to(DEV).bfloat16()
+    slopes = torch.tensor([2 ** (-8 * (h + 1) / H) for h in range(H)], device=DEV) if alibi else None
+    cu = ops.cu_seqlens(lens, DEV)
+    items = ops.TileMap(lens, ops.TC_BLOCK_M, DEV)
+    got = ops.attention_tc(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu, cu, items, H, hd, slopes)
+    want = _ref_attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], lens, lens, H, hd, slopes)
+    torch.cuda.synchronize()
+    assert torch.allclose(got.float(), want, atol=2e-2, rtol=2e-2), _describe_mismatch(got.float(), want, 2e-2)
+
+
+@pytest.mark.parametrize("H,hd", [(4, 48), (32, 48), (4, 64)])
+def test_tc_cross_attention_stacked_queries(H, hd):
+    lens_q = [3 * 41, 5 * 17, 201 * 5, 700]; lens_k = [300, 64, 1024, 129]
+    d = H * hd
+    g = torch.Generator(device="cpu").manual_seed(12)
+    q = torch.randn(sum(lens_q), d, generator=g).to(DEV).bfloat16()
+    kv = torch.randn(sum(lens_k), 2 * d, generator=g).to(DEV).bfloat16()
+    items = ops.TileMap(lens_q, ops.TC_BLOCK_M, DEV, k_lens=lens_k)
+    got = ops.attention_tc(q, kv[:, :d], kv[:, d:], ops.cu_seqlens(lens_q, DEV), ops.cu_seqlens(lens_k, DEV), items,
+                           H, hd, None)
+    want = _ref_attention(q, kv[:, :d], kv[:, d:], lens_q, lens_k, H, hd, None)
+    torch.cuda.synchronize()
+    assert torch.allclose(got.float(), want, atol=2e-2, rtol=2e-2), _describe_mismatch(got.float(), want, 2e-2)
+
+
 def test_label_attention_equals_full_attention_over_labels():
     H, hd, C = 4, 48, [37, 120]
     D = H * hd

@@ -74,6 +74,13 @@ def main():
         fl = sum(4.0 * a * b * d for a, b in zip(lens_q, lk))
         res.append(dict(kernel="attention", name=name, ms=ms, tflops=fl / ms / 1e9))
         print(json.dumps(res[-1])); sys.stdout.flush()
+        try:
+            items = ops.TileMap(lens_q, ops.TC_BLOCK_M, DEV, k_lens=lens_k)
+            ms = timeit(lambda: ops.attention_tc(q, k, v, cq, ck, items, H, hd, slopes, out=o))
+            res.append(dict(kernel="attention_tc", name=name, ms=ms, tflops=fl / ms / 1e9))
+            print(json.dumps(res[-1])); sys.stdout.flush()
+        except Exception as e:
+            print("attention_tc failed:", e)
     # layernorm bandwidth
     x = torch.randn(101304, 1536, device=DEV); g = torch.ones(1536, device=DEV); b = torch.zeros(1536, device=DEV)
     o = torch.empty(101304, 1536, device=DEV, dtype=torch.bfloat16)

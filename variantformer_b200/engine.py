@@ -17,6 +17,7 @@ Schedule differences from the reference (results identical, oracle/model_fp32.py
 Numerics: bf16 GEMM/attention operands, fp32 accumulation, fp32 residual stream and LayerNorm.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -26,6 +27,8 @@ from ._lib import EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GEGLU_BF16, EPI_BIAS_GEL
 from .utils.alibi import alibi_slopes
 
 NUM_REF_CRES = 9
+# "tc" = tcgen05/TMEM attention for the seq2gene streams (default); "legacy" = mma.sync kernel everywhere (debug)
+ATTENTION_IMPL = os.environ.get("VF_ATTENTION", "tc")
 
 
 def sinusoidal_pe(d_model: int, length: int) -> torch.Tensor:
@@ -246,9 +249,14 @@ class Engine:
         s["cu_gseq"] = ops.cu_seqlens(seq_lens, dev)                  # one sequence per (gene, tissue): self-attention
         s["cu_gq"] = ops.cu_seqlens(T * (G + 1), dev)                 # one "sequence" per gene: stacked cross queries
         s["cu_cre"] = ops.cu_seqlens(C, dev)
-        s["tiles_gself"] = ops.TileMap(seq_lens, 64, dev)
-        s["tiles_gcross"] = ops.TileMap(T * (G + 1), 128, dev, k_lens=C)
-        s["tiles_cself"] = ops.TileMap(C, 128 if C.max() > 256 else 64, dev)
+        if ATTENTION_IMPL == "tc" and self.w.hd in (48, 64):
+            s["tiles_gself"] = ops.TileMap(seq_lens, ops.TC_BLOCK_M, dev)
+            s["tiles_gcross"] = ops.TileMap(T * (G + 1), ops.TC_BLOCK_M, dev, k_lens=C)
+            s["tiles_cself"] = ops.TileMap(C, ops.TC_BLOCK_M, dev)
+        else:
+            s["tiles_gself"] = ops.TileMap(seq_lens, 64, dev)
+            s["tiles_gcross"] = ops.TileMap(T * (G + 1), 128, dev, k_lens=C)
+            s["tiles_cself"] = ops.TileMap(C, 128 if C.max() > 256 else 64, dev)
         s["row_seq"] = up(np.repeat(np.arange(B), C), np.int32)
         lab = torch.cat([l.reshape(-1) for l in ref_labels]).detach().cpu().numpy().astype(np.int64)
         counts = np.zeros((B, NUM_REF_CRES), np.float64)
@@ -286,19 +294,21 @@ class Engine:
         kv = ws.get("g_kv", (nC, 2 * D), torch.bfloat16)
         cu_gseq, cu_gq, cu_cre = s["cu_gseq"], s["cu_gq"], s["cu_cre"]
 
+        def attn(q, k, v, cu_q, cu_k, tiles, slopes, out):
+            fn = ops.attention_tc if tiles.block_m == ops.TC_BLOCK_M else ops.attention
+            fn(q, k, v, cu_q, cu_k, tiles, H, hd, slopes, out=out)
+
         def gene_self(qkv, out):
-            ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], cu_gseq, cu_gseq, s["tiles_gself"], H, hd,
-                          w.slopes, out=out)
+            attn(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], cu_gseq, cu_gseq, s["tiles_gself"], w.slopes, out)
 
         def cre_self(qkv, out):
-            ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], cu_cre, cu_cre, s["tiles_cself"], H, hd,
-                          w.slopes, out=out)
+            attn(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], cu_cre, cu_cre, s["tiles_cself"], w.slopes, out)
 
         def gene_layer(L):
             ops.gemm(cre_bf, L["kv"].w, EPI_BIAS_BF16, bias=L["kv"].b, out=kv)      # shared by every tissue copy
 
             def cross(q, out):
-                ops.attention(q, kv[:, :D], kv[:, D:], cu_gq, cu_cre, s["tiles_gcross"], H, hd, None, out=out)
+                attn(q, kv[:, :D], kv[:, D:], cu_gq, cu_cre, s["tiles_gcross"], None, out)
             self._layer(L, gx, Mg, gene_self, cross, "g")
 
         def cre_layer(L):

@@ -125,6 +125,24 @@ def attention(q, k, v, cu_q, cu_k, tiles: TileMap, heads, head_dim, slopes=None,
     return out
 
 
+TC_BLOCK_M = 512          # tcgen05 attention: work items of up to 4 x 128 query rows
+
+
+def attention_tc(q, k, v, cu_q, cu_k, items: TileMap, heads, head_dim, slopes=None, out=None):
+    """Varlen attention on the tcgen05 path (vf_attention_tc_varlen); `items` = TileMap(..., TC_BLOCK_M, ...)."""
+    for t in (q, k, v):
+        assert t.is_cuda and t.dtype == torch.bfloat16 and t.stride(1) == 1
+    assert items.block_m == TC_BLOCK_M
+    if out is None:
+        out = torch.empty((q.shape[0], heads * head_dim), dtype=torch.bfloat16, device=q.device)
+    with _timed("attention", 4.0 * items.qk_pairs * heads * head_dim):
+        check(_lib.lib().vf_attention_tc_varlen(ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0),
+                                                ptr(out), out.stride(0), q.shape[0], k.shape[0], ptr(cu_q), ptr(cu_k),
+                                                ptr(items.tile_seq), ptr(items.tile_q0), items.n_tiles, heads,
+                                                head_dim, ptr(slopes), stream()))
+    return out
+
+
 def label_attention(q, kv9, logc, row_seq, heads, head_dim, out=None):
     assert q.dtype == torch.bfloat16 and kv9.dtype == torch.float32 and logc.dtype == torch.float32
     assert row_seq.dtype == torch.int32 and kv9.is_contiguous() and logc.is_contiguous()
