@@ -46,7 +46,69 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-template <int HD>
+
+// One 32-column slab of a score row.  PASS 0: running max of the biased, scaled scores.  PASS 1: p = exp2(x - m),
+// row sum, bf16 pack and swizzled store into the P tile.  ALIBI / TAIL are compile-time so the common case
+// (no bias, full key block) is FFMA + EX2 + FADD + half a cvt per element.
+template <int PASS, bool ALIBI, bool TAIL>
+__device__ __forceinline__ void softmax_slab(const uint32_t (&r)[32], float scale, float slope, float d0, int nvalid,
+                                             float m_scaled, float& mx, float& sum, uint8_t* dst, int c, int row) {
+    // d0 = (query position + Sk - Sq) - first key of this slab; key e of the slab is at distance |d0 - e|
+    if constexpr (PASS == 0) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            float x = __uint_as_float(r[e]);
+            if constexpr (ALIBI) x = fmaf(x, scale, -slope * fabsf(d0 - (float)e));
+            if constexpr (TAIL) { if (e >= nvalid) x = -INFINITY; }
+            mx = fmaxf(mx, x);
+        }
+    } else {
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+            float x0 = fmaf(__uint_as_float(r[e]), scale, -m_scaled), x1 = fmaf(__uint_as_float(r[e + 1]), scale, -m_scaled);
+            if constexpr (ALIBI) { x0 -= slope * fabsf(d0 - (float)e); x1 -= slope * fabsf(d0 - (float)(e + 1)); }
+            if constexpr (TAIL) { if (e >= nvalid) x0 = -INFINITY; if (e + 1 >= nvalid) x1 = -INFINITY; }
+            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            sum += p0 + p1;
+            pk[e >> 1] = pack_bf16x2(p0, p1);
+        }
+        // P row -> shared memory, K-major SWIZZLE_128B: sub-tile = 64 keys, 16-byte chunk index XOR (row & 7);
+        // this 32-key slab covers chunks (c&1)*4 .. +3 of sub-tile c>>1
+        uint8_t* base = dst + (c >> 1) * kTileBytes + row * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+            const int chunk = ((c & 1) * 4 + q4) ^ (row & 7);
+            *reinterpret_cast<uint4*>(base + chunk * 16) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
+        }
+    }
+}
+
+// A whole 128 x 128 score tile for this thread's row: pipelined TMEM loads, buffer hand-back after the last load.
+template <int PASS, bool ALIBI, bool TAIL>
+__device__ __forceinline__ void softmax_tile(uint32_t t_addr, uint64_t* s_empty_bar, uint64_t* p_empty_bar,
+                                             uint32_t p_empty_parity, float scale, float slope, float qpos, int key0,
+                                             int Sk, float m_scaled, float& mx, float& sum, uint8_t* dst, int row,
+                                             int lane) {
+    uint32_t r[2][32];
+    tmem_ld_32x32(t_addr, r[0]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        tmem_ld_wait();
+        if (c + 1 < 4) {
+            tmem_ld_32x32(t_addr + (c + 1) * 32, r[(c + 1) & 1]);
+        } else {
+            tc_fence_before();                       // whole S tile is in registers: hand the buffer back
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty_bar);
+        }
+        if (PASS == 1 && c == 0) mbar_wait(p_empty_bar, p_empty_parity);     // P buffer free (PV two tiles back done)
+        softmax_slab<PASS, ALIBI, TAIL>(r[c & 1], scale, slope, qpos - (float)(key0 + c * 32), Sk - (key0 + c * 32),
+                                        m_scaled, mx, sum, dst, c, row);
+    }
+}
+
+template <int HD, bool ALIBI>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
@@ -158,36 +220,50 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 // ---- pass 2: scores again, then O_t += P V one (j, t) step behind ----
                 mbar_wait(o_empty, (it & 1) ^ 1);
                 tc_fence_after();
-                int pend_t = -1, pend_j = 0, pend_vs = 0;
-                auto issue_pv = [&]() {
-                    const int b = pend_t & 1;
+                // linearised steps n = j*nq + t.  S(n+2) is issued BEFORE waiting for P(n): the warpgroup that owns
+                // step n finds its next score tile ready the moment it finishes writing P(n).
+                const int N = nk * nq;
+                int kj_issued = 0;                                  // key blocks whose k_full has been awaited
+                int ks_of[2] = {0, 0};                              // smem stage of key block j (parity-indexed, <=2 live)
+                int vs_of[2] = {0, 0};
+                auto ensure_k = [&](int j) {                        // wait for K_j / V_j exactly once, in order
+                    while (kj_issued <= j) {
+                        mbar_wait(&k_full[ks], kph);
+                        mbar_wait(&v_full[vs], vph);
+                        tc_fence_after();
+                        ks_of[kj_issued & 1] = ks; vs_of[kj_issued & 1] = vs;
+                        if (++ks == kKStages) { ks = 0; kph ^= 1; }
+                        if (++vs == kVStages) { vs = 0; vph ^= 1; }
+                        ++kj_issued;
+                    }
+                };
+                auto qk_step = [&](int n) {
+                    const int j = n / nq, t = n - j * nq;
+                    ensure_k(j);
+                    issue_qk(t, ks_of[j & 1]);
+                    if (t == nq - 1) umma_commit(&k_empty[ks_of[j & 1]]);
+                };
+                // look-ahead of 2 steps needs two live key blocks at most (nq >= 2); a single query tile per item
+                // looks ahead one step so that the 2-stage V ring and the parity-indexed stage tables stay valid
+                const int LA = nq >= 2 ? 2 : 1;
+                for (int n = 0; n < LA && n < N; ++n) qk_step(n);
+                for (int n = 0; n < N; ++n) {
+                    if (n + LA < N) qk_step(n + LA);
+                    const int j = n / nq, t = n - j * nq, b = t & 1;
                     mbar_wait(&p_full[b], n_p[b] & 1); ++n_p[b];
                     tc_fence_after();
-                    const uint32_t d = tmem_base + 256 + pend_t * 64;
+                    const uint32_t d = tmem_base + 256 + t * 64;
+                    const int vstage = vs_of[j & 1];
 #pragma unroll
                     for (int kk = 0; kk < kKB / 16; ++kk) {
                         const uint64_t da = umma_desc_kmajor_sw128(
                             smem_u32(sm_p + (b * 2 + (kk >> 2)) * kTileBytes)) + 2 * (kk & 3);
-                        const uint64_t db = umma_desc_kmajor_sw128(smem_u32(sm_v + pend_vs * kTileBytes + kk * 2048));
-                        umma_bf16(d, da, db, idesc_pv, (pend_j | kk) != 0);
+                        const uint64_t db = umma_desc_kmajor_sw128(smem_u32(sm_v + vstage * kTileBytes + kk * 2048));
+                        umma_bf16(d, da, db, idesc_pv, (j | kk) != 0);
                     }
                     umma_commit(&p_empty[b]);
-                    if (pend_t == nq - 1) umma_commit(&v_empty[pend_vs]);
-                };
-                for (int j = 0; j < nk; ++j) {
-                    mbar_wait(&k_full[ks], kph);
-                    mbar_wait(&v_full[vs], vph);
-                    tc_fence_after();
-                    for (int t = 0; t < nq; ++t) {
-                        issue_qk(t, ks);
-                        if (pend_t >= 0) issue_pv();
-                        pend_t = t; pend_j = j; pend_vs = vs;
-                    }
-                    umma_commit(&k_empty[ks]);
-                    if (++ks == kKStages) { ks = 0; kph ^= 1; }
-                    if (++vs == kVStages) { vs = 0; vph ^= 1; }
+                    if (t == nq - 1) umma_commit(&v_empty[vstage]);
                 }
-                issue_pv();
                 umma_commit(o_full);
                 umma_commit(q_empty);
             }
@@ -204,8 +280,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
             int seq, head, q0, qbeg, Sq, kbeg, Sk, nq, nk;
             decode(w, seq, head, q0, qbeg, Sq, kbeg, Sk, nq, nk);
-            const float slope = p.slopes ? p.slopes[head] * 1.4426950408889634f : 0.f;
+            const float slope = ALIBI ? p.slopes[head] * 1.4426950408889634f : 0.f;
             const int shift = Sk - Sq;
+            // pass 0 keeps raw-score maxima when there is no bias (scale > 0 commutes with max)
             float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
             for (int pass = 0; pass < 2; ++pass) {
                 for (int j = 0; j < nk; ++j) {
@@ -216,54 +293,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         const float qpos = (float)(q0 + t * kQT + row + shift);
                         mbar_wait(&s_full[wg], n_s & 1); ++n_s;
                         tc_fence_after();
-                        if (pass == 1) { mbar_wait(&p_empty[wg], (n_p & 1) ^ 1); ++n_p; }
-                        uint32_t r[2][32];
-                        tmem_ld_32x32(t_lane + wg * kKB, r[0]);
+                        const uint32_t t_addr = t_lane + wg * kKB;
                         float mx = m_run[tt], sum = 0.f;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            tmem_ld_wait();
-                            if (c + 1 < 4) tmem_ld_32x32(t_lane + wg * kKB + (c + 1) * 32, r[(c + 1) & 1]);
-                            else {
-                                // the whole S tile is in registers: hand the buffer back to the MMA warp
-                                tc_fence_before();
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive(&s_empty[wg]);
-                            }
-                            float x[32];
-#pragma unroll
-                            for (int e = 0; e < 32; ++e) {
-                                const int key = key0 + c * 32 + e;
-                                float v = __uint_as_float(r[c & 1][e]) * p.scale_log2;
-                                if (p.slopes) v -= slope * fabsf(qpos - (float)key);
-                                if (tail && key >= Sk) v = -INFINITY;
-                                x[e] = v;
-                            }
-                            if (pass == 0) {
-#pragma unroll
-                                for (int e = 0; e < 32; ++e) mx = fmaxf(mx, x[e]);
-                            } else {
-                                uint32_t pk[16];
-#pragma unroll
-                                for (int e = 0; e < 32; e += 2) {
-                                    const float p0 = ex2_approx(x[e] - mx), p1 = ex2_approx(x[e + 1] - mx);
-                                    sum += p0 + p1;
-                                    pk[e >> 1] = pack_bf16x2(p0, p1);
-                                }
-                                // P row -> shared memory, K-major SWIZZLE_128B: sub-tile = 64 keys, 16-byte chunk index
-                                // XOR (row & 7); this 32-key slab covers chunks (c&1)*4 .. +3 of sub-tile c>>1
-                                uint8_t* dst = my_p + (c >> 1) * kTileBytes + row * 128;
-#pragma unroll
-                                for (int q4 = 0; q4 < 4; ++q4) {
-                                    const int chunk = ((c & 1) * 4 + q4) ^ (row & 7);
-                                    *reinterpret_cast<uint4*>(dst + chunk * 16) =
-                                        make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
-                                }
-                            }
-                        }
                         if (pass == 0) {
+                            if (tail) softmax_tile<0, ALIBI, true>(t_addr, &s_empty[wg], nullptr, 0, p.scale_log2, slope, qpos, key0, Sk, 0.f, mx, sum, my_p, row, lane);
+                            else      softmax_tile<0, ALIBI, false>(t_addr, &s_empty[wg], nullptr, 0, p.scale_log2, slope, qpos, key0, Sk, 0.f, mx, sum, my_p, row, lane);
                             m_run[tt] = mx;
                         } else {
+                            const float m_scaled = ALIBI ? mx : mx * p.scale_log2;
+                            const uint32_t par = (n_p & 1) ^ 1; ++n_p;
+                            if (tail) softmax_tile<1, ALIBI, true>(t_addr, &s_empty[wg], &p_empty[wg], par, p.scale_log2, slope, qpos, key0, Sk, m_scaled, mx, sum, my_p, row, lane);
+                            else      softmax_tile<1, ALIBI, false>(t_addr, &s_empty[wg], &p_empty[wg], par, p.scale_log2, slope, qpos, key0, Sk, m_scaled, mx, sum, my_p, row, lane);
                             l_run[tt] += sum;
                             fence_proxy_async_smem();             // generic-proxy writes -> visible to the UMMA (async proxy)
                             __syncwarp();
@@ -338,12 +378,12 @@ static int make_tmap_rows64(CUtensorMap* tm, const void* base, long rows, int co
     return 0;
 }
 
-template <int HD>
+template <int HD, bool ALIBI>
 static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p,
                           cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        VF_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        VF_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<HD, ALIBI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)kAttnSmem));
         attr_set = true;
     }
@@ -352,7 +392,7 @@ static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CU
     VF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const long work = (long)p.n_items * p.heads;
     const int grid = (int)(work < sms ? work : sms);
-    attention_tc_kernel<HD><<<grid, kAttnThreads, kAttnSmem, s>>>(tq, tk, tv, p);
+    attention_tc_kernel<HD, ALIBI><<<grid, kAttnThreads, kAttnSmem, s>>>(tq, tk, tv, p);
     VF_LAUNCH_OK("attention_tc_kernel launch");
     return 0;
 }
@@ -373,8 +413,8 @@ int attention_tc_varlen(const void* q, int ldq, const void* k, int ldk, const vo
     p.cu_q = cu_q; p.cu_k = cu_k; p.item_seq = item_seq; p.item_q0 = item_q0; p.n_items = n_items; p.heads = heads;
     p.o = (__nv_bfloat16*)o; p.ldo = ldo; p.slopes = slopes;
     p.scale_log2 = (1.0f / sqrtf((float)head_dim)) * 1.4426950408889634f;
-    if (head_dim == 48) return launch_attn_tc<48>(tq, tk, tv, p, stream);
-    return launch_attn_tc<64>(tq, tk, tv, p, stream);
+    if (head_dim == 48) return slopes ? launch_attn_tc<48, true>(tq, tk, tv, p, stream) : launch_attn_tc<48, false>(tq, tk, tv, p, stream);
+    return slopes ? launch_attn_tc<64, true>(tq, tk, tv, p, stream) : launch_attn_tc<64, false>(tq, tk, tv, p, stream);
 }
 
 }  // namespace vf

@@ -176,7 +176,8 @@ class Engine:
         for L in W.layers:
             ops.layernorm(x, L["n1"].g, L["n1"].b, out=h)
             ops.gemm(h, L["qkv"].w, EPI_BIAS_BF16, bias=L["qkv"].b, out=qkv)
-            ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu, cu, tiles, H, hd, W.slopes, out=a)
+            attn = ops.attention_tc if tiles.block_m == ops.TC_BLOCK_M else ops.attention
+            attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu, cu, tiles, H, hd, W.slopes, out=a)
             ops.gemm(a, L["out"].w, EPI_BIAS_RESID_F32, bias=L["out"].b, resid=x, out=x1)
             ops.layernorm(x1, L["n2"].g, L["n2"].b, out=h)
             ops.gemm(h, L["g1"].w, EPI_BIAS_GEGLU_BF16, bias=L["g1"].b, out=f)
@@ -230,9 +231,10 @@ class Engine:
         s = {"B": B, "C": C, "G": G, "T": T}
         s["ctok"], s["cmsk"], s["clens"] = stage(cre_tokens, cre_masks, None if lens is None else lens[0])
         s["gtok"], s["gmsk"], s["glens"] = stage(gene_tokens, gene_masks, None if lens is None else lens[1])
-        for tag, ln in (("c", s["clens"]), ("g", s["glens"])):
+        for tag, ln, W in (("c", s["clens"], self.cre_tok), ("g", s["glens"], self.gene_tok)):
             s[tag + "_cu_tok"] = ops.cu_seqlens(ln, dev)
-            s[tag + "_tiles_tok"] = ops.TileMap(ln, 64, dev)
+            use_tc = ATTENTION_IMPL == "tc" and W.hd in (48, 64) and len(ln) and np.mean(ln) > 160
+            s[tag + "_tiles_tok"] = ops.TileMap(ln, ops.TC_BLOCK_M if use_tc else 64, dev)
         # gene stream layout: per (gene, tissue): [registry(tissue); the gene's chunk embeddings]
         g_off = np.concatenate([[0], np.cumsum(G)])
         idx, seq_lens = [], []
@@ -250,9 +252,12 @@ class Engine:
         s["cu_gq"] = ops.cu_seqlens(T * (G + 1), dev)                 # one "sequence" per gene: stacked cross queries
         s["cu_cre"] = ops.cu_seqlens(C, dev)
         if ATTENTION_IMPL == "tc" and self.w.hd in (48, 64):
-            s["tiles_gself"] = ops.TileMap(seq_lens, ops.TC_BLOCK_M, dev)
+            # tcgen05 kernel where a work item has >= 2 query tiles and long key ranges; the 201-token gene
+            # self-attention (2 x 2 tiles per item, 38 % padding) is still faster on the warp-MMA kernel
+            s["tiles_gself"] = (ops.TileMap(seq_lens, ops.TC_BLOCK_M, dev) if seq_lens.max() > 256
+                                else ops.TileMap(seq_lens, 64, dev))
             s["tiles_gcross"] = ops.TileMap(T * (G + 1), ops.TC_BLOCK_M, dev, k_lens=C)
-            s["tiles_cself"] = ops.TileMap(C, ops.TC_BLOCK_M, dev)
+            s["tiles_cself"] = ops.TileMap(C, ops.TC_BLOCK_M if C.max() > 256 else 64, dev)
         else:
             s["tiles_gself"] = ops.TileMap(seq_lens, 64, dev)
             s["tiles_gcross"] = ops.TileMap(T * (G + 1), 128, dev, k_lens=C)
