@@ -136,14 +136,15 @@ int vf_encode_windows(const uint8_t* genome, const int64_t* win_base, const int3
  * merge_a/merge_b/merge_new: uint16 [n_merges] rank-ordered merge table.  out_tokens int32 [n_win, out_pitch]:
  * the first min(count, out_cap) ids, remainder of the row zero (<pad>); out_count int32 [n_win] = untruncated
  * token count; out_start (optional) int32 [n_win, start_pitch] = first base index of every token.
- * scratch: uint16 [n_win, scratch_pitch], required when max_len > 8192.
+ * Windows longer than 8192 symbols run on the cluster/DSMEM kernel (8 CTAs per window); scratch is unused there.
+ * block_threads: 0 = auto, or 128/256/512/1024 (performance hint for the single-CTA kernel).
  * Replaces utils/seq.py:32-62 (BPEEncoder.normalize/encode -> HF tokenizers), :68-174 (token offsets) and the
  * pad/truncate/chunk steps datasets/vcfdataset.py:198-217, :338-394.
  */
 int vf_bpe_tokenize(const uint8_t* seq, int64_t pitch, const int32_t* len, int n_win, int max_len,
                     const uint16_t* merge_a, const uint16_t* merge_b, const uint16_t* merge_new, int n_merges,
                     uint16_t* scratch, int64_t scratch_pitch, int32_t* out_tokens, int out_pitch, int out_cap,
-                    int32_t* out_count, int32_t* out_start, int64_t start_pitch, void* stream);
+                    int32_t* out_count, int32_t* out_start, int64_t start_pitch, int block_threads, void* stream);
 
 #ifdef __cplusplus
 }

@@ -296,9 +296,8 @@ __global__ void bpe_tokenize_kernel(const BpeParams p) {
 // segment of the symbol array in its own shared memory; neighbours are reached through distributed shared memory
 // (forward "next alive symbol" scans cross a segment boundary by at most 7 slots, self-pair run scans by the run
 // length).  One cluster barrier per applied rank (two for self pairs).  The per-token-id occupancy counters that
-// drive the uniform skip decision are replicated in every CTA; the delta of applied sweep k is added to replica
-// (k+1)&1 before that sweep's barrier and to replica k&1 after it, so the replica read after k applied sweeps is
-// always complete without an extra barrier.
+// drive the uniform skip decision are replicated in every CTA and kept identical by gathering the per-CTA merge
+// counts of every applied sweep through DSMEM right after that sweep's cluster barrier.
 // ---------------------------------------------------------------------------------
 constexpr int kBpeCluster = 8;
 
@@ -341,7 +340,6 @@ bpe_tokenize_cluster_kernel(const BpeParams p, const int seg_cap) {
     if (tid < 32 && s_hist[tid] != 0) {
         for (int c = 0; c < kBpeCluster; ++c) {
             atomicAdd(s_peer_cnt[c] + tid, s_hist[tid]);
-            atomicAdd(s_peer_cnt[c] + kMaxVocab + tid, s_hist[tid]);
         }
     }
     cluster.sync();
@@ -356,17 +354,14 @@ bpe_tokenize_cluster_kernel(const BpeParams p, const int seg_cap) {
         const int c = pos / seg;
         s_peer[c][pos - c * seg] = v;
     };
-    auto publish = [&](int buf, uint16_t a, uint16_t b, uint16_t c, int m) {      // thread 0 only
-        for (int r = 0; r < kBpeCluster; ++r) {
-            int* cnt = s_peer_cnt[r] + buf * kMaxVocab;
-            atomicAdd(cnt + c, m); atomicSub(cnt + a, m); atomicSub(cnt + b, m);
-        }
-    };
-
+    // Per applied sweep every CTA posts its merge count in its own shared memory (slot k&1); after the cluster
+    // barrier each CTA gathers the 8 counts through DSMEM and updates its private replica of the counters, so all
+    // replicas stay identical without remote atomics.
+    __shared__ int s_pub[2];
     int k = 0;                                            // applied sweeps so far (cluster-uniform)
     for (int r = 0; r < p.n_merges; ++r) {
         const uint16_t a = p.merge_a[r], b = p.merge_b[r], c = p.merge_new[r];
-        const int* cnt = s_cnt[k & 1];
+        const int* cnt = s_cnt[0];
         if (cnt[a] == 0 || cnt[b] == 0 || (a == b && cnt[a] < 2)) continue;       // uniform over the whole cluster
         int merged = 0;
         if (a != b) {
@@ -403,17 +398,20 @@ bpe_tokenize_cluster_kernel(const BpeParams p, const int seg_cap) {
         }
         if (merged) atomicAdd(&s_merged[k & 1], merged);
         __syncthreads();
-        int m = 0;
-        if (tid == 0) {
-            m = s_merged[k & 1];
-            s_merged[(k + 1) & 1] = 0;
-            if (m) publish((k + 1) & 1, a, b, c, m);      // early copy: the replica the NEXT decisions read
+        if (tid == 0) { s_pub[k & 1] = s_merged[k & 1]; s_merged[(k + 1) & 1] = 0; }
+        cluster.sync();                                   // all merges of this rank + every CTA's count are visible
+        if (tid < 32) {
+            int v = tid < kBpeCluster ? cluster.map_shared_rank(&s_pub[0], tid)[k & 1] : 0;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (tid == 0) {
+                s_cnt[0][c] += v; s_cnt[0][a] -= v; s_cnt[0][b] -= v;
+            }
         }
-        cluster.sync();
-        if (tid == 0 && m) publish(k & 1, a, b, c, m);    // late copy: read only after the next applied sweep's barrier
+        __syncthreads();
         ++k;
     }
-    cluster.sync();                                       // late publishes + all symbol writes have landed
+    cluster.sync();                                       // no CTA may exit (or reuse s_pub) while peers still read it
 
     // ---- ordered compaction of this CTA's segment; token offset = alive symbols of the lower-ranked segments ----
     const int len_seg = hi - lo;
@@ -459,7 +457,7 @@ bpe_tokenize_cluster_kernel(const BpeParams p, const int seg_cap) {
 int bpe_tokenize(const uint8_t* seq, int64_t pitch, const int32_t* len, int n_win, int max_len,
                  const uint16_t* merge_a, const uint16_t* merge_b, const uint16_t* merge_new, int n_merges,
                  uint16_t* scratch, int64_t scratch_pitch, int32_t* out_tokens, int out_pitch, int out_cap,
-                 int32_t* out_count, int32_t* out_start, int64_t start_pitch, cudaStream_t s) {
+                 int32_t* out_count, int32_t* out_start, int64_t start_pitch, int block_threads, cudaStream_t s) {
     if (n_win == 0) return 0;
     VF_REQUIRE(out_cap <= out_pitch, "bpe_tokenize: out_cap %d > out_pitch %d", out_cap, out_pitch);
     VF_REQUIRE(out_start == nullptr || start_pitch >= max_len, "bpe_tokenize: start_pitch too small");
@@ -485,7 +483,9 @@ int bpe_tokenize(const uint8_t* seq, int64_t pitch, const int32_t* len, int n_wi
         VF_CUDA_OK(cudaLaunchKernelEx(&cfg, bpe_tokenize_cluster_kernel, p, seg_cap));
         return 0;
     }
-    const int threads = max_len <= 1024 ? 128 : 1024;
+    // block size is a pure performance hint (typical window length); any value works for any window
+    const int threads = (block_threads == 128 || block_threads == 256 || block_threads == 512 || block_threads == 1024)
+                            ? block_threads : (max_len <= 1024 ? 128 : 1024);
     const size_t smem = (size_t)kBpeSmemSyms * sizeof(uint16_t);
     bpe_tokenize_kernel<<<n_win, threads, smem, s>>>(p);
     VF_LAUNCH_OK("bpe_tokenize_kernel launch");

@@ -45,6 +45,6 @@ int encode_windows(const uint8_t* genome, const int64_t* win_base, const int32_t
 int bpe_tokenize(const uint8_t* seq, int64_t pitch, const int32_t* len, int n_win, int max_len,
                  const uint16_t* merge_a, const uint16_t* merge_b, const uint16_t* merge_new, int n_merges,
                  uint16_t* scratch, int64_t scratch_pitch, int32_t* out_tokens, int out_pitch, int out_cap,
-                 int32_t* out_count, int32_t* out_start, int64_t start_pitch, cudaStream_t s);
+                 int32_t* out_count, int32_t* out_start, int64_t start_pitch, int block_threads, cudaStream_t s);
 
 }  // namespace vf

@@ -128,7 +128,7 @@ class VCFDataset(Dataset):
         w0 = [w[i][0] for i in order]; w1 = [w[i][1] for i in order]
         seq, lens, err = self.tokenizer.sequences(self._genome(), chroms, w0, w1, [int(minus)] * len(order),
                                                   self._variants(vcf_path))
-        tok, mask, _ = self.tokenizer.tokenize_fixed(seq, lens, seq.shape[1])
+        tok, mask, _ = self.tokenizer.tokenize_fixed(seq, lens, seq.shape[1], typical_len=self.tokenizer.last_max_window)
         self._check(err)
         labels = torch.tensor([self.ref_cre_to_idx[m["cCRE"].iloc[i]] for i in order], dtype=torch.long)
         return tok.long().unsqueeze(1), mask.unsqueeze(1), labels, torch.zeros(len(order), dtype=torch.long)

@@ -233,7 +233,8 @@ class Engine:
         s["gtok"], s["gmsk"], s["glens"] = stage(gene_tokens, gene_masks, None if lens is None else lens[1])
         for tag, ln, W in (("c", s["clens"], self.cre_tok), ("g", s["glens"], self.gene_tok)):
             s[tag + "_cu_tok"] = ops.cu_seqlens(ln, dev)
-            use_tc = ATTENTION_IMPL == "tc" and W.hd in (48, 64) and len(ln) and np.mean(ln) > 160
+            # gene-window chunks are full 200-token sequences (2 query tiles) -> tcgen05; CRE windows (~97 tokens) -> warp-MMA
+            use_tc = ATTENTION_IMPL == "tc" and W.hd in (48, 64) and tag == "g"
             s[tag + "_tiles_tok"] = ops.TileMap(ln, ops.TC_BLOCK_M if use_tc else 64, dev)
         # gene stream layout: per (gene, tissue): [registry(tissue); the gene's chunk embeddings]
         g_off = np.concatenate([[0], np.cumsum(G)])
@@ -252,12 +253,12 @@ class Engine:
         s["cu_gq"] = ops.cu_seqlens(T * (G + 1), dev)                 # one "sequence" per gene: stacked cross queries
         s["cu_cre"] = ops.cu_seqlens(C, dev)
         if ATTENTION_IMPL == "tc" and self.w.hd in (48, 64):
-            # tcgen05 kernel where a work item has >= 2 query tiles and long key ranges; the 201-token gene
-            # self-attention (2 x 2 tiles per item, 38 % padding) is still faster on the warp-MMA kernel
-            s["tiles_gself"] = (ops.TileMap(seq_lens, ops.TC_BLOCK_M, dev) if seq_lens.max() > 256
-                                else ops.TileMap(seq_lens, 64, dev))
+            # The kernel is chosen per ROLE, never per batch content, so results do not depend on how genes are batched:
+            # tcgen05 for the stacked cross-attention and the CRE stream; the <=201-token gene self-attention
+            # (2 x 2 tiles per item, 38 % padding) stays on the warp-MMA kernel, which is faster at that shape.
+            s["tiles_gself"] = ops.TileMap(seq_lens, 64, dev)
             s["tiles_gcross"] = ops.TileMap(T * (G + 1), ops.TC_BLOCK_M, dev, k_lens=C)
-            s["tiles_cself"] = ops.TileMap(C, ops.TC_BLOCK_M if C.max() > 256 else 64, dev)
+            s["tiles_cself"] = ops.TileMap(C, ops.TC_BLOCK_M, dev)
         else:
             s["tiles_gself"] = ops.TileMap(seq_lens, 64, dev)
             s["tiles_gcross"] = ops.TileMap(T * (G + 1), 128, dev, k_lens=C)

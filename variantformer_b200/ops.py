@@ -242,17 +242,20 @@ def encode_windows(genome, win_base, w0, w1, var_lo, var_hi, flags, variants, ma
     return out, out_len, err
 
 
-def bpe_tokenize(seq, lens, max_len, merges, out_pitch, out_cap, want_starts=False):
+def bpe_tokenize(seq, lens, max_len, merges, out_pitch, out_cap, want_starts=False, typical_len=None):
     """seq uint8 [n, pitch]; lens int32 [n]; merges = (a, b, new) uint16 device tensors (viewed as int16 storage)."""
     n, pitch = seq.shape
     dev = seq.device
     out = torch.empty((n, out_pitch), dtype=torch.int32, device=dev)
     cnt = torch.empty(n, dtype=torch.int32, device=dev)
-    scratch = torch.empty((n, max_len), dtype=torch.int16, device=dev) if max_len > 8192 else None
+    scratch = None                      # long windows run on the cluster kernel, which keeps symbols in shared memory
+    t = max_len if typical_len is None else typical_len
+    threads = 128 if t <= 1024 else (256 if t <= 2048 else (512 if t <= 4096 else 1024))
     starts = torch.empty((n, max_len), dtype=torch.int32, device=dev) if want_starts else None
     a, b, c = merges
-    with _timed("stage1_bpe"):
+    with _timed("stage1_bpe_cluster" if max_len > 8192 else "stage1_bpe"):
         check(_lib.lib().vf_bpe_tokenize(ptr(seq), pitch, ptr(lens), n, int(max_len), ptr(a), ptr(b), ptr(c), a.numel(),
                                          ptr(scratch), int(max_len) if scratch is not None else 0, ptr(out), out_pitch,
-                                         out_cap, ptr(cnt), ptr(starts), int(max_len) if want_starts else 0, stream()))
+                                         out_cap, ptr(cnt), ptr(starts), int(max_len) if want_starts else 0, threads,
+                                         stream()))
     return (out, cnt, starts) if want_starts else (out, cnt)

@@ -47,7 +47,7 @@ class HotPath:
                 chroms.append(g.chrom if g.cre_chrom is None else g.cre_chrom[i])
                 w0.append(a0); w1.append(a1); rc.append(int(minus)); owner.append(gi)
         seq, lens, err1 = self.tok.sequences(self.genome, chroms, w0, w1, rc, variants)
-        ctok, cmask, ccnt = self.tok.tokenize_fixed(seq, lens, seq.shape[1])
+        ctok, cmask, ccnt = self.tok.tokenize_fixed(seq, lens, seq.shape[1], typical_len=self.tok.last_max_window)
         gw = [gene_window(g.start, g.end, g.strand, self.up, self.down) for g in genes]
         gseq, glens, err2 = self.tok.sequences(self.genome, [g.chrom for g in genes], [x[0] for x in gw],
                                                [x[1] for x in gw], [int(g.strand == "-") for g in genes], variants)

@@ -145,11 +145,13 @@ class WindowTokenizer:
         out, out_len, err = ops.encode_windows(
             genome.seq, t(base, np.int64), t(w0, np.int32), t(w1, np.int32), t([x[0] for x in lo_hi], np.int32),
             t([x[1] for x in lo_hi], np.int32), t(flags, np.uint8), v.dev, max_window, pitch)
+        self.last_max_window = max_window          # reference span of the longest window (block-size hint)
         return out, out_len, err
 
-    def tokenize_fixed(self, seq, lens, max_len):
+    def tokenize_fixed(self, seq, lens, max_len, typical_len=None):
         """CRE windows: pad/truncate to max_length (vcfdataset.py:198-217).  -> tokens int32 [n, L], mask bool."""
-        tok, cnt = ops.bpe_tokenize(seq, lens, max_len, self.merges, self.max_length, self.max_length)
+        tok, cnt = ops.bpe_tokenize(seq, lens, max_len, self.merges, self.max_length, self.max_length,
+                                    typical_len=typical_len)
         ar = torch.arange(self.max_length, device=self.device)[None, :]
         return tok, ar >= cnt.clamp(max=self.max_length)[:, None], cnt
 
