@@ -12,9 +12,10 @@
 //               O_t += P V : M128 x N(hd) x K128 with P from shared memory (K-major) and V as an MN-major operand.
 //   warps 2-9   two softmax warpgroups (query tile t is owned by warpgroup t&1): ONE THREAD PER QUERY ROW, the row
 //               arrives straight from TMEM (tcgen05.ld 32x32b), so max / sum need no cross-thread reduction.
-// Softmax is two-pass: pass 1 streams all key blocks and keeps only the exact row maxima, pass 2 recomputes S,
-// forms P = exp2(s - m) (never rescaled), accumulates the row sums and O.  The extra QK^T GEMMs ride on a tensor
-// pipe that is otherwise idle (the kernel is exp/MUFU-bound at hd=48) and remove every O-rescale dependency.
+// Softmax is single-pass with a LAZY reference maximum (exact arithmetic, FA4-style): every row keeps a reference
+// m_ref; P = exp2(x - m_ref) may reach 2^8 before m_ref is raised.  m_ref is only raised (and l / O_t rescaled by
+// exp2(m_old - m_new), O_t through tcgen05.ld/st) when a 32-key slab exceeds it by more than 8 in the log2 domain:
+// for free on the first slab of a tile, otherwise by a rare restart of the tile with its exact maximum.
 // TMEM: columns [0,128) S0, [128,256) S1, [256 + 64 t, +64) O_t  (512 columns).
 #include <cuda.h>
 
@@ -47,65 +48,149 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 
-// One 32-column slab of a score row.  PASS 0: running max of the biased, scaled scores.  PASS 1: p = exp2(x - m),
-// row sum, bf16 pack and swizzled store into the P tile.  ALIBI / TAIL are compile-time so the common case
-// (no bias, full key block) is FFMA + EX2 + FADD + half a cvt per element.
-template <int PASS, bool ALIBI, bool TAIL>
-__device__ __forceinline__ void softmax_slab(const uint32_t (&r)[32], float scale, float slope, float d0, int nvalid,
-                                             float m_scaled, float& mx, float& sum, uint8_t* dst, int c, int row) {
-    // d0 = (query position + Sk - Sq) - first key of this slab; key e of the slab is at distance |d0 - e|
-    if constexpr (PASS == 0) {
+constexpr float kLazyThreshold = 8.0f;      // log2 units: P stays below 2^8 between reference-max updates
+
+// scaled (and biased / masked) score of element e of a 32-key slab
+template <bool ALIBI, bool TAIL>
+__device__ __forceinline__ float score(uint32_t raw, int e, float scale, float slope, float d0, int nvalid) {
+    float x = __uint_as_float(raw) * scale;
+    if constexpr (ALIBI) x = fmaf(__uint_as_float(raw), scale, -slope * fabsf(d0 - (float)e));
+    if constexpr (TAIL) { if (e >= nvalid) x = -INFINITY; }
+    return x;
+}
+template <bool ALIBI, bool TAIL>
+__device__ __forceinline__ float slab_max(const uint32_t (&r)[32], float scale, float slope, float d0, int nvalid) {
+    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};     // 4 independent chains (latency, not issue, bound)
+    if constexpr (!ALIBI && !TAIL) {            // scale > 0 commutes with max: one FMNMX per element
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-            float x = __uint_as_float(r[e]);
-            if constexpr (ALIBI) x = fmaf(x, scale, -slope * fabsf(d0 - (float)e));
-            if constexpr (TAIL) { if (e >= nvalid) x = -INFINITY; }
-            mx = fmaxf(mx, x);
-        }
-    } else {
-        uint32_t pk[16];
+        for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(r[e]));
+        return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * scale;
+    } else {                                    // r already holds the finished scores (see softmax_tile)
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-            float x0 = fmaf(__uint_as_float(r[e]), scale, -m_scaled), x1 = fmaf(__uint_as_float(r[e + 1]), scale, -m_scaled);
-            if constexpr (ALIBI) { x0 -= slope * fabsf(d0 - (float)e); x1 -= slope * fabsf(d0 - (float)(e + 1)); }
-            if constexpr (TAIL) { if (e >= nvalid) x0 = -INFINITY; if (e + 1 >= nvalid) x1 = -INFINITY; }
-            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-            sum += p0 + p1;
-            pk[e >> 1] = pack_bf16x2(p0, p1);
-        }
-        // P row -> shared memory, K-major SWIZZLE_128B: sub-tile = 64 keys, 16-byte chunk index XOR (row & 7);
-        // this 32-key slab covers chunks (c&1)*4 .. +3 of sub-tile c>>1
-        uint8_t* base = dst + (c >> 1) * kTileBytes + row * 128;
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-            const int chunk = ((c & 1) * 4 + q4) ^ (row & 7);
-            *reinterpret_cast<uint4*>(base + chunk * 16) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
-        }
+        for (int e = 0; e < 32; ++e) mx[e & 3] = fmaxf(mx[e & 3], __uint_as_float(r[e]));
+        return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
     }
 }
+// p = exp2(x - m_ref) for one slab: row-sum, bf16 pack, swizzled store into the P tile (K-major SWIZZLE_128B:
+// sub-tile = 64 keys, 16-byte chunk index XOR (row & 7); slab c covers chunks (c&1)*4 .. +3 of sub-tile c>>1)
+template <bool ALIBI, bool TAIL>
+__device__ __forceinline__ void slab_exp_store(const uint32_t (&r)[32], float scale, float slope, float d0, int nvalid,
+                                               float m_ref, float& sum, uint8_t* dst, int c, int row) {
+    uint32_t pk[16];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 32; e += 2) {
+        float x0, x1;
+        if constexpr (!ALIBI && !TAIL) {
+            x0 = fmaf(__uint_as_float(r[e]), scale, -m_ref); x1 = fmaf(__uint_as_float(r[e + 1]), scale, -m_ref);
+        } else {
+            x0 = __uint_as_float(r[e]) - m_ref; x1 = __uint_as_float(r[e + 1]) - m_ref;
+        }
+        const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+        acc[(e >> 1) & 3] += p0 + p1;
+        pk[e >> 1] = pack_bf16x2(p0, p1);
+    }
+    sum += (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    uint8_t* base = dst + (c >> 1) * kTileBytes + row * 128;
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+        const int chunk = ((c & 1) * 4 + q4) ^ (row & 7);
+        *reinterpret_cast<uint4*>(base + chunk * 16) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
+    }
+}
+// O_t row *= corr, in tensor memory (warp-collective; lanes that need no change pass corr = 1)
+__device__ __forceinline__ void rescale_o(uint32_t o_addr, float corr) {
+    uint32_t v[32];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        tmem_ld_32x32(o_addr + h * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * corr);
+        tmem_st_32x32(o_addr + h * 32, v);
+    }
+    tmem_st_wait();
+}
 
-// A whole 128 x 128 score tile for this thread's row: pipelined TMEM loads, buffer hand-back after the last load.
-template <int PASS, bool ALIBI, bool TAIL>
-__device__ __forceinline__ void softmax_tile(uint32_t t_addr, uint64_t* s_empty_bar, uint64_t* p_empty_bar,
-                                             uint32_t p_empty_parity, float scale, float slope, float qpos, int key0,
-                                             int Sk, float m_scaled, float& mx, float& sum, uint8_t* dst, int row,
-                                             int lane) {
+// One 128 x 128 score tile for this thread's row.  Returns through m_ref / l / (O_t in TMEM) / the P tile.
+template <bool ALIBI, bool TAIL>
+__device__ __forceinline__ void softmax_tile(uint32_t s_addr, uint32_t o_addr, bool have_o, uint64_t* s_empty_bar,
+                                             float scale, float slope, float qpos, int key0, int Sk, float& m_ref,
+                                             float& l, uint8_t* dst, int row, int lane) {
     uint32_t r[2][32];
-    tmem_ld_32x32(t_addr, r[0]);
+    float sum = 0.f;
+    bool restart = false;
+    float seen = -INFINITY;
+    tmem_ld_32x32(s_addr, r[0]);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         tmem_ld_wait();
-        if (c + 1 < 4) {
-            tmem_ld_32x32(t_addr + (c + 1) * 32, r[(c + 1) & 1]);
-        } else {
-            tc_fence_before();                       // whole S tile is in registers: hand the buffer back
+        if (c + 1 < 4) tmem_ld_32x32(s_addr + (c + 1) * 32, r[(c + 1) & 1]);
+        const float d0 = qpos - (float)(key0 + c * 32);
+        const int nvalid = Sk - (key0 + c * 32);
+        if constexpr (ALIBI || TAIL) {                       // biased / masked scores are computed once, in place
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+                r[c & 1][e] = __float_as_uint(score<ALIBI, TAIL>(r[c & 1][e], e, scale, slope, d0, nvalid));
+        }
+        const float cmax = slab_max<ALIBI, TAIL>(r[c & 1], scale, slope, d0, nvalid);
+        seen = fmaxf(seen, cmax);
+        if (__any_sync(0xffffffffu, cmax > m_ref + kLazyThreshold)) {
+            if (c == 0) {                                    // nothing of this tile is written yet: raise in place
+                const float m_new = fmaxf(m_ref, cmax);
+                const float corr = ex2_approx(m_ref - m_new);             // m_ref = -inf -> 0
+                l *= corr;
+                if (have_o) rescale_o(o_addr, corr);
+                m_ref = m_new;
+            } else {
+                restart = true;                              // warp-uniform
+            }
+        }
+        if (restart) break;
+        if (c == 3) {                                        // whole tile is in registers and accepted: release S
+            tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(s_empty_bar);
         }
-        if (PASS == 1 && c == 0) mbar_wait(p_empty_bar, p_empty_parity);     // P buffer free (PV two tiles back done)
-        softmax_slab<PASS, ALIBI, TAIL>(r[c & 1], scale, slope, qpos - (float)(key0 + c * 32), Sk - (key0 + c * 32),
-                                        m_scaled, mx, sum, dst, c, row);
+        slab_exp_store<ALIBI, TAIL>(r[c & 1], scale, slope, d0, nvalid, m_ref, sum, dst, c, row);
     }
+    if (restart) {
+        // rare: exact maximum of the whole tile first, then one clean pass (no further raise can trigger)
+        tmem_ld_wait();                                      // drain the in-flight prefetch
+        for (int c = 0; c < 4; ++c) {
+            tmem_ld_32x32(s_addr + c * 32, r[0]);
+            tmem_ld_wait();
+            if constexpr (ALIBI || TAIL) {
+#pragma unroll
+                for (int e = 0; e < 32; ++e)
+                    r[0][e] = __float_as_uint(score<ALIBI, TAIL>(r[0][e], e, scale, slope, qpos - (float)(key0 + c * 32), Sk - (key0 + c * 32)));
+            }
+            seen = fmaxf(seen, slab_max<ALIBI, TAIL>(r[0], scale, slope, qpos - (float)(key0 + c * 32), Sk - (key0 + c * 32)));
+        }
+        const float m_new = fmaxf(m_ref, seen);
+        const float corr = ex2_approx(m_ref - m_new);
+        l *= corr;
+        if (have_o) rescale_o(o_addr, corr);
+        m_ref = m_new;
+        sum = 0.f;
+        for (int c = 0; c < 4; ++c) {
+            tmem_ld_32x32(s_addr + c * 32, r[0]);
+            tmem_ld_wait();
+            if constexpr (ALIBI || TAIL) {
+#pragma unroll
+                for (int e = 0; e < 32; ++e)
+                    r[0][e] = __float_as_uint(score<ALIBI, TAIL>(r[0][e], e, scale, slope, qpos - (float)(key0 + c * 32), Sk - (key0 + c * 32)));
+            }
+            if (c == 3) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_empty_bar);
+            }
+            slab_exp_store<ALIBI, TAIL>(r[0], scale, slope, qpos - (float)(key0 + c * 32), Sk - (key0 + c * 32), m_ref,
+                                        sum, dst, c, row);
+        }
+    }
+    l += sum;
 }
 
 template <int HD, bool ALIBI>
@@ -170,19 +255,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 mbar_wait(q_empty, (it & 1) ^ 1);
                 mbar_arrive_expect_tx(q_full, nq * kTileBytes);
                 for (int t = 0; t < nq; ++t) tma_load_2d(sm_q + t * kTileBytes, &tmQ, q_full, col, qbeg + q0 + t * kQT);
-                for (int pass = 0; pass < 2; ++pass) {
-                    for (int j = 0; j < nk; ++j) {
-                        mbar_wait(&k_empty[ks], kph ^ 1);
-                        mbar_arrive_expect_tx(&k_full[ks], kTileBytes);
-                        tma_load_2d(sm_k + ks * kTileBytes, &tmK, &k_full[ks], col, kbeg + j * kKB);
-                        if (++ks == kKStages) { ks = 0; kph ^= 1; }
-                        if (pass == 1) {
-                            mbar_wait(&v_empty[vs], vph ^ 1);
-                            mbar_arrive_expect_tx(&v_full[vs], kTileBytes);
-                            tma_load_2d(sm_v + vs * kTileBytes, &tmV, &v_full[vs], col, kbeg + j * kKB);
-                            if (++vs == kVStages) { vs = 0; vph ^= 1; }
-                        }
-                    }
+                for (int j = 0; j < nk; ++j) {
+                    mbar_wait(&k_empty[ks], kph ^ 1);
+                    mbar_arrive_expect_tx(&k_full[ks], kTileBytes);
+                    tma_load_2d(sm_k + ks * kTileBytes, &tmK, &k_full[ks], col, kbeg + j * kKB);
+                    if (++ks == kKStages) { ks = 0; kph ^= 1; }
+                    mbar_wait(&v_empty[vs], vph ^ 1);
+                    mbar_arrive_expect_tx(&v_full[vs], kTileBytes);
+                    tma_load_2d(sm_v + vs * kTileBytes, &tmV, &v_full[vs], col, kbeg + j * kKB);
+                    if (++vs == kVStages) { vs = 0; vph ^= 1; }
                 }
             }
         }
@@ -209,15 +290,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + b * kKB, da + 2 * k, db + 2 * k, idesc_qk, k != 0);
                     umma_commit(&s_full[b]);
                 };
-                // ---- pass 1: scores only (row maxima) ----
-                for (int j = 0; j < nk; ++j) {
-                    mbar_wait(&k_full[ks], kph);
-                    tc_fence_after();
-                    for (int t = 0; t < nq; ++t) issue_qk(t, ks);
-                    umma_commit(&k_empty[ks]);
-                    if (++ks == kKStages) { ks = 0; kph ^= 1; }
-                }
-                // ---- pass 2: scores again, then O_t += P V one (j, t) step behind ----
+                // ---- S = Q K^T two steps ahead of O_t += P V ----
                 mbar_wait(o_empty, (it & 1) ^ 1);
                 tc_fence_after();
                 // linearised steps n = j*nq + t.  S(n+2) is issued BEFORE waiting for P(n): the warpgroup that owns
@@ -282,34 +355,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             decode(w, seq, head, q0, qbeg, Sq, kbeg, Sk, nq, nk);
             const float slope = ALIBI ? p.slopes[head] * 1.4426950408889634f : 0.f;
             const int shift = Sk - Sq;
-            // pass 0 keeps raw-score maxima when there is no bias (scale > 0 commutes with max)
-            float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
-            for (int pass = 0; pass < 2; ++pass) {
-                for (int j = 0; j < nk; ++j) {
-                    const int key0 = j * kKB;
-                    const bool tail = key0 + kKB > Sk;            // block holds keys beyond the sequence
-                    for (int tt = 0; wg + 2 * tt < nq; ++tt) {
-                        const int t = wg + 2 * tt;
-                        const float qpos = (float)(q0 + t * kQT + row + shift);
-                        mbar_wait(&s_full[wg], n_s & 1); ++n_s;
-                        tc_fence_after();
-                        const uint32_t t_addr = t_lane + wg * kKB;
-                        float mx = m_run[tt], sum = 0.f;
-                        if (pass == 0) {
-                            if (tail) softmax_tile<0, ALIBI, true>(t_addr, &s_empty[wg], nullptr, 0, p.scale_log2, slope, qpos, key0, Sk, 0.f, mx, sum, my_p, row, lane);
-                            else      softmax_tile<0, ALIBI, false>(t_addr, &s_empty[wg], nullptr, 0, p.scale_log2, slope, qpos, key0, Sk, 0.f, mx, sum, my_p, row, lane);
-                            m_run[tt] = mx;
-                        } else {
-                            const float m_scaled = ALIBI ? mx : mx * p.scale_log2;
-                            const uint32_t par = (n_p & 1) ^ 1; ++n_p;
-                            if (tail) softmax_tile<1, ALIBI, true>(t_addr, &s_empty[wg], &p_empty[wg], par, p.scale_log2, slope, qpos, key0, Sk, m_scaled, mx, sum, my_p, row, lane);
-                            else      softmax_tile<1, ALIBI, false>(t_addr, &s_empty[wg], &p_empty[wg], par, p.scale_log2, slope, qpos, key0, Sk, m_scaled, mx, sum, my_p, row, lane);
-                            l_run[tt] += sum;
-                            fence_proxy_async_smem();             // generic-proxy writes -> visible to the UMMA (async proxy)
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&p_full[wg]);
-                        }
-                    }
+            float m_ref[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+            for (int j = 0; j < nk; ++j) {
+                const int key0 = j * kKB;
+                const bool tail = key0 + kKB > Sk;                // block holds keys beyond the sequence
+                for (int tt = 0; wg + 2 * tt < nq; ++tt) {
+                    const int t = wg + 2 * tt;
+                    const float qpos = (float)(q0 + t * kQT + row + shift);
+                    mbar_wait(&s_full[wg], n_s & 1); ++n_s;
+                    // P buffer free <=> the PV two of this warpgroup's tiles back has retired; every earlier PV
+                    // (in particular the last one that wrote O_t) has then retired too, so O_t may be rescaled
+                    mbar_wait(&p_empty[wg], (n_p & 1) ^ 1); ++n_p;
+                    tc_fence_after();
+                    const uint32_t s_addr = t_lane + wg * kKB, o_addr = t_lane + 256 + t * 64;
+                    if (tail) softmax_tile<ALIBI, true>(s_addr, o_addr, j > 0, &s_empty[wg], p.scale_log2, slope, qpos, key0, Sk, m_ref[tt], l_run[tt], my_p, row, lane);
+                    else      softmax_tile<ALIBI, false>(s_addr, o_addr, j > 0, &s_empty[wg], p.scale_log2, slope, qpos, key0, Sk, m_ref[tt], l_run[tt], my_p, row, lane);
+                    fence_proxy_async_smem();                     // generic-proxy writes -> visible to the UMMA (async proxy)
+                    tc_fence_before();                            // orders a possible tcgen05.st rescale before the PV
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&p_full[wg]);
                 }
             }
             // ---- epilogue: O_t / l -> bf16 -> global ----
