@@ -77,7 +77,10 @@ def attention(q, k, v, cu_q, cu_k, tiles, heads, head_dim, slopes=None, out=None
 
 
 TC_BLOCK_M = 512
-attention_tc = attention
+
+
+def attention_tc(q, k, v, cu_q, cu_k, tiles, heads, head_dim, slopes=None, out=None, key_block=64):
+    return attention(q, k, v, cu_q, cu_k, tiles, heads, head_dim, slopes, out)
 
 
 def label_attention(q, kv9, logc, row_seq, heads, head_dim, out=None):

@@ -139,21 +139,23 @@ def test_cross_attention_stacked_queries(H, hd):
     (32, 48, True, [1024, 201]),
     (8, 64, True, [1300]),
 ])
-def test_tc_self_attention(H, hd, alibi, lens):
+@pytest.mark.parametrize("key_block", [64, 128])
+def test_tc_self_attention(H, hd, alibi, lens, key_block):
     n, d = sum(lens), H * hd
     g = torch.Generator(device="cpu").manual_seed(H * hd + len(lens))
     qkv = torch.randn(n, 3 * d, generator=g).to(DEV).bfloat16()
     slopes = torch.tensor([2 ** (-8 * (h + 1) / H) for h in range(H)], device=DEV) if alibi else None
     cu = ops.cu_seqlens(lens, DEV)
     items = ops.TileMap(lens, ops.TC_BLOCK_M, DEV)
-    got = ops.attention_tc(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu, cu, items, H, hd, slopes)
+    got = ops.attention_tc(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu, cu, items, H, hd, slopes, key_block=key_block)
     want = _ref_attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], lens, lens, H, hd, slopes)
     torch.cuda.synchronize()
     assert torch.allclose(got.float(), want, atol=2e-2, rtol=2e-2), _describe_mismatch(got.float(), want, 2e-2)
 
 
 @pytest.mark.parametrize("H,hd", [(4, 48), (32, 48), (4, 64)])
-def test_tc_cross_attention_stacked_queries(H, hd):
+@pytest.mark.parametrize("key_block", [64, 128])
+def test_tc_cross_attention_stacked_queries(H, hd, key_block):
     lens_q = [3 * 41, 5 * 17, 201 * 5, 700]; lens_k = [300, 64, 1024, 129]
     d = H * hd
     g = torch.Generator(device="cpu").manual_seed(12)
@@ -161,7 +163,7 @@ def test_tc_cross_attention_stacked_queries(H, hd):
     kv = torch.randn(sum(lens_k), 2 * d, generator=g).to(DEV).bfloat16()
     items = ops.TileMap(lens_q, ops.TC_BLOCK_M, DEV, k_lens=lens_k)
     got = ops.attention_tc(q, kv[:, :d], kv[:, d:], ops.cu_seqlens(lens_q, DEV), ops.cu_seqlens(lens_k, DEV), items,
-                           H, hd, None)
+                           H, hd, None, key_block=key_block)
     want = _ref_attention(q, kv[:, :d], kv[:, d:], lens_q, lens_k, H, hd, None)
     torch.cuda.synchronize()
     assert torch.allclose(got.float(), want, atol=2e-2, rtol=2e-2), _describe_mismatch(got.float(), want, 2e-2)

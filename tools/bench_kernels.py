@@ -76,9 +76,10 @@ def main():
         print(json.dumps(res[-1])); sys.stdout.flush()
         try:
             items = ops.TileMap(lens_q, ops.TC_BLOCK_M, DEV, k_lens=lens_k)
-            ms = timeit(lambda: ops.attention_tc(q, k, v, cq, ck, items, H, hd, slopes, out=o))
-            res.append(dict(kernel="attention_tc", name=name, ms=ms, tflops=fl / ms / 1e9))
-            print(json.dumps(res[-1])); sys.stdout.flush()
+            for kb in (64, 128):
+                ms = timeit(lambda: ops.attention_tc(q, k, v, cq, ck, items, H, hd, slopes, out=o, key_block=kb))
+                res.append(dict(kernel=f"attention_tc{kb}", name=name, ms=ms, tflops=fl / ms / 1e9))
+                print(json.dumps(res[-1])); sys.stdout.flush()
         except Exception as e:
             print("attention_tc failed:", e)
     # layernorm bandwidth

@@ -20,6 +20,11 @@ int attention_tc_varlen(const void* q, int ldq, const void* k, int ldk, const vo
                         const int* item_q0, int n_items, int heads, int head_dim, const float* slopes,
                         cudaStream_t stream);
 
+int attention_tc128_varlen(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
+                           long rows_q, long rows_k, const int* cu_q, const int* cu_k, const int* item_seq,
+                           const int* item_q0, int n_items, int heads, int head_dim, const float* slopes,
+                           cudaStream_t stream);
+
 int layernorm(const float* x, int ldx, const float* gamma, const float* beta, int M, int d, float eps, void* out,
               int ldo, int act_gelu, cudaStream_t s);
 int window_lengths(const uint8_t* pad_mask, int n_win, int L, int* lens, cudaStream_t s);

@@ -300,9 +300,11 @@ class Engine:
         kv = ws.get("g_kv", (nC, 2 * D), torch.bfloat16)
         cu_gseq, cu_gq, cu_cre = s["cu_gseq"], s["cu_gq"], s["cu_cre"]
 
-        def attn(q, k, v, cu_q, cu_k, tiles, slopes, out):
-            fn = ops.attention_tc if tiles.block_m == ops.TC_BLOCK_M else ops.attention
-            fn(q, k, v, cu_q, cu_k, tiles, H, hd, slopes, out=out)
+        def attn(q, k, v, cu_q, cu_k, tiles, slopes, out, key_block=64):
+            if tiles.block_m == ops.TC_BLOCK_M:
+                ops.attention_tc(q, k, v, cu_q, cu_k, tiles, H, hd, slopes, out=out, key_block=key_block)
+            else:
+                ops.attention(q, k, v, cu_q, cu_k, tiles, H, hd, slopes, out=out)
 
         def gene_self(qkv, out):
             attn(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], cu_gseq, cu_gseq, s["tiles_gself"], w.slopes, out)
@@ -314,7 +316,7 @@ class Engine:
             ops.gemm(cre_bf, L["kv"].w, EPI_BIAS_BF16, bias=L["kv"].b, out=kv)      # shared by every tissue copy
 
             def cross(q, out):
-                attn(q, kv[:, :D], kv[:, D:], cu_gq, cu_cre, s["tiles_gcross"], None, out)
+                attn(q, kv[:, :D], kv[:, D:], cu_gq, cu_cre, s["tiles_gcross"], None, out, key_block=128)
             self._layer(L, gx, Mg, gene_self, cross, "g")
 
         def cre_layer(L):

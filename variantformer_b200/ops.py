@@ -128,7 +128,7 @@ def attention(q, k, v, cu_q, cu_k, tiles: TileMap, heads, head_dim, slopes=None,
 TC_BLOCK_M = 512          # tcgen05 attention: work items of up to 4 x 128 query rows
 
 
-def attention_tc(q, k, v, cu_q, cu_k, items: TileMap, heads, head_dim, slopes=None, out=None):
+def attention_tc(q, k, v, cu_q, cu_k, items: TileMap, heads, head_dim, slopes=None, out=None, key_block=64):
     """Varlen attention on the tcgen05 path (vf_attention_tc_varlen); `items` = TileMap(..., TC_BLOCK_M, ...)."""
     for t in (q, k, v):
         assert t.is_cuda and t.dtype == torch.bfloat16 and t.stride(1) == 1
@@ -139,7 +139,7 @@ def attention_tc(q, k, v, cu_q, cu_k, items: TileMap, heads, head_dim, slopes=No
         check(_lib.lib().vf_attention_tc_varlen(ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0),
                                                 ptr(out), out.stride(0), q.shape[0], k.shape[0], ptr(cu_q), ptr(cu_k),
                                                 ptr(items.tile_seq), ptr(items.tile_q0), items.n_tiles, heads,
-                                                head_dim, ptr(slopes), stream()))
+                                                head_dim, ptr(slopes), key_block, stream()))
     return out
 
 
