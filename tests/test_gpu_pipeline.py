@@ -138,3 +138,67 @@ def test_vcfprocessor_surface_end_to_end(tmp_path):
     out2 = vp2.predict(model2, ckpt2, trainer2, dl2, ds2)
     for i in range(2):           # same weights through the checkpoint path, different batching -> identical
         assert np.array_equal(out2["embeddings"].iloc[i], out["embeddings"].iloc[i])
+
+
+def test_vep_triplet_matches_reference_semantics():
+    """(ref, het, hom) batches vs the oracle applied to Python strings built with the reference's own rule
+    (vepdataset.py:94-131: het = one base -> IUPAC code or N, hom = one base -> ALT string), and the full
+    variant_prediction surface of the model."""
+    from variantformer_b200.datasets.vepdataset import VEPBatchBuilder, Variant, get_iupac_code
+    from variantformer_b200.seq2gene.model_combined_modulator import Seq2GenePredictorCombinedModulator, attach_trainer
+    from variantformer_b200.seq2reg.model import Seq2RegPredictor
+    chroms, var, genes = _world(seed=79, n_genes=2, n_cres=30)
+    genome = Genome.from_arrays(chroms, "cuda")
+    builder = VEPBatchBuilder(genome)
+    bpe = O.OracleBPE()
+    chrom = chroms["chr1"]
+    sd = random_init.make_state_dict(CFG, HP, seed=5)
+    model = Seq2GenePredictorCombinedModulator(cre_tokenizer=Seq2RegPredictor(**HP), gene_tokenizer=Seq2RegPredictor(**HP), **CFG)
+    model.load_state_dict(sd); model.eval().to("cuda"); model.vep = True; attach_trainer(model)
+    for g in genes:
+        minus = g.strand == "-"
+        order = np.argsort(g.cre_start, kind="stable"); order = order[::-1] if minus else order
+        k = 3
+        a0, a1 = cre_window(g.cre_start[order[k]], g.cre_end[order[k]], 50)
+        g0, g1 = gene_window(g.start, g.end, g.strand, 1000, 300000)
+        for pos0, alt in ((a0 + 7, None), (g0 + 1234, "ACG"), (a1 + 3, None), (g0 + 4321, None), (g0 - 5000, None)):
+            ref = chr(chrom[pos0]).upper()
+            alt = alt or [c for c in "ACGT" if c != ref][0]
+            v = Variant("chr1", pos0 + 1, ref, alt, tissue=[62, 3])
+            het_c = get_iupac_code(ref, alt)
+            if g0 < v.pos <= g1 and (het_c == "N" or ref not in "ACGT"):
+                # the reference raises here too: encode_with_position rejects a non-IUPAC character (seq.py:93-97)
+                with pytest.raises(ValueError, match="invalid character"):
+                    builder.build(g, v)
+                continue
+            batch = builder.build(g, v)
+            in_cre = any(cre_window(g.cre_start[i], g.cre_end[i], 50)[0] < v.pos <= cre_window(g.cre_start[i], g.cre_end[i], 50)[1] for i in order)
+            in_gene = g0 < v.pos <= g1
+            if not in_cre and not in_gene:
+                assert batch["variant_type"] == "No overlap" and batch["cre_sequences"] == []
+                continue
+            for s_idx, rep in enumerate((None, het_c, alt)):
+                def window(w0, w1):
+                    s = chrom[w0:w1].tobytes().decode()
+                    if rep is not None and w0 <= pos0 < w1:
+                        s = s[:pos0 - w0] + rep + s[pos0 - w0 + 1:]
+                    return O.reverse_complement(s) if minus else s
+                toks = np.stack([O.adjust_length(bpe.encode(window(*cre_window(g.cre_start[i], g.cre_end[i], 50))), 200)[0] for i in order])
+                assert (batch["cre_sequences"][s_idx][:, 0].cpu().numpy() == toks).all(), f"CRE tokens sample {s_idx}"
+                gseq = window(g0, g1)
+                gt, gm = O.chunkify(bpe.encode(gseq), 200, 200)
+                assert (batch["gene_embeddings"][s_idx][:, 0].cpu().numpy() == gt).all()
+                assert (batch["gene_attention_masks"][s_idx][:, 0].cpu().numpy() == gm).all()
+                if in_gene:
+                    p = pos0 - g0
+                    p = len(gseq) - p - 1 if minus else p
+                    want = min(bpe.token_at(gseq, p) // 200, 199)
+                    assert int(batch["gene_token_position"][s_idx, 0]) == want
+            if in_cre:
+                hit = [kk for kk, i in enumerate(order) if cre_window(g.cre_start[i], g.cre_end[i], 50)[0] < v.pos <= cre_window(g.cre_start[i], g.cre_end[i], 50)[1]][0]
+                assert int(batch["cre_token_position"][0, 0]) == hit
+            out = model.predict_step(batch, 0)
+            assert len(out["pred_gene_exp"]) == 3 and out["pred_gene_exp"][0].shape == (2, 1)
+            assert out["embd"][1].shape == (2, CFG["emb_dim"]) and out["variant_type"] == batch["variant_type"]
+            # the three samples of the triplet differ only where the variant falls: ref vs hom predictions differ
+            assert np.isfinite(out["pred_gene_exp"][2]).all()
