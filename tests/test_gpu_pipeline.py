@@ -83,9 +83,7 @@ def test_hotpath_tokens_bit_exact_and_outputs_within_tolerance():
     assert rel_err(emb, w_emb) <= 1e-2 and pearson(emb, w_emb) >= 0.9999 and rel_err(pred, w_pred) <= 1e-2
 
 
-def test_vcfprocessor_surface_end_to_end(tmp_path):
-    from variantformer_b200.processors.vcfprocessor import VCFProcessor
-    chroms, var, genes = _world(seed=78, n_genes=2, n_cres=24)
+def _write_artifacts(tmp_path, chroms, var, genes):
     art = tmp_path / "_artifacts"; (art / "gene_cre_manifests").mkdir(parents=True)
     with open(art / "GRCh38_no_alt_analysis_set_GCA_000001405.15.fasta.gz", "wb") as f:     # plain text is accepted too
         f.write(b">chr1 synthetic\n")
@@ -105,6 +103,13 @@ def test_vcfprocessor_surface_end_to_end(tmp_path):
         pd.DataFrame(dict(chromosome="chr1", start_cre=g.cre_start, end_cre=g.cre_end,
                           cre_name=[REF_CREs[l] for l in g.cre_labels])).to_csv(art / "gene_cre_manifests" / f"{gid}.csv", index=False)
     pd.DataFrame(rows).to_csv(art / "all_genes_v1_pcg_gencodeV24.csv", index=False)
+    return art, rows
+
+
+def test_vcfprocessor_surface_end_to_end(tmp_path):
+    from variantformer_b200.processors.vcfprocessor import VCFProcessor
+    chroms, var, genes = _world(seed=78, n_genes=2, n_cres=24)
+    art, rows = _write_artifacts(tmp_path, chroms, var, genes)
     over = dict(CFG, random_init=5, seq2reg_hyper_parameters=HP)
     vp = VCFProcessor("v4_pcg", base_dir=str(tmp_path), model_overrides=over)
     assert "whole blood" in vp.get_tissues() and len(vp.get_genes()) == 2
@@ -202,3 +207,31 @@ def test_vep_triplet_matches_reference_semantics():
             assert out["embd"][1].shape == (2, CFG["emb_dim"]) and out["variant_type"] == batch["variant_type"]
             # the three samples of the triplet differ only where the variant falls: ref vs hom predictions differ
             assert np.isfinite(out["pred_gene_exp"][2]).all()
+
+
+def test_variantprocessor_surface(tmp_path):
+    from variantformer_b200.processors.variantprocessor import VariantProcessor
+    chroms, var, genes = _world(seed=80, n_genes=2, n_cres=20)
+    art, rows = _write_artifacts(tmp_path, chroms, var, genes)
+    g = genes[0]
+    order = np.argsort(g.cre_start, kind="stable")
+    pos0 = int(g.cre_start[order[2]]) + 11                      # inside a CRE window
+    while chr(chroms["chr1"][pos0]).upper() not in "ACGT":
+        pos0 += 1
+    ref = chr(chroms["chr1"][pos0]).upper(); alt = [c for c in "ACGT" if c != ref][1]
+    var_df = pd.DataFrame({"chr": ["chr1", "chr1"], "pos": [pos0 + 1, 5], "ref": [ref, "A"], "alt": [alt, "C"],
+                           "tissue": ["whole blood,thyroid", "whole blood"], "gene_id": [rows[0]["gene_id"]] * 2})
+    vp = VariantProcessor("v4_pcg", base_dir=str(tmp_path), model_overrides=dict(CFG, random_init=5, seq2reg_hyper_parameters=HP))
+    out = vp.predict(var_df, str(tmp_path / "out"))
+    assert list(out.columns) == ["chrom", "pos", "ref", "alt", "genes", "tissues", "variant_type", "population",
+                                 "sample_name", "zygosity", "gene_exp", "gene_emb", "gene_token_embedding", "cre_token_embedding"]
+    hit = out[out["pos"] == pos0 + 1]
+    assert len(hit) == 6 and set(hit["zygosity"]) == {"0", "1", "2"} and set(hit["tissues"]) == {"whole blood", "thyroid"}
+    assert hit["variant_type"].iloc[0] in ("CRE overlap only", "Gene and CRE overlap")
+    assert np.isfinite(hit["gene_exp"]).all() and hit["gene_emb"].iloc[0].shape == (CFG["emb_dim"],)
+    miss = out[out["pos"] == 5]
+    assert (miss["variant_type"] == "No overlap").all() and miss["gene_exp"].isna().all()
+    scores = VariantProcessor.format_scores(hit)
+    assert {"log2fc_1", "log2fc_2"} <= set(scores.columns) and np.isfinite(scores["log2fc_2"]).all()
+    with pytest.raises(FileExistsError):
+        vp.predict(var_df, str(tmp_path / "out"))               # refuses to overwrite, like the reference
