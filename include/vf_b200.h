@@ -74,13 +74,14 @@ int vf_attention_varlen(const void* q, int ldq, const void* k, int ldk, const vo
  * thread per query row, two-pass exact softmax).  Work items are blocks of up to 4 x 128 query rows of one sequence:
  * item_seq/item_q0 int32 [n_items] (a tile map built with 512 rows per item).  rows_q / rows_k = total rows of the
  * q and k/v tensors (TMA bounds).  head_dim in {48, 64}.  key_block: keys per softmax step, 64 (two S/P buffers per
- * softmax warpgroup; best for short sequences) or 128 (best for long key ranges).  Same reference call sites as
- * vf_attention_varlen.
+ * softmax warpgroup; best for short sequences) or 128 (best for long key ranges).  short_items != 0 promises that
+ * every work item has at most 2 query tiles (all query sequences <= 256 rows): the 64-key kernel then double-buffers
+ * Q and O across consecutive items.  Same reference call sites as vf_attention_varlen.
  */
 int vf_attention_tc_varlen(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
                            int64_t rows_q, int64_t rows_k, const int32_t* cu_q, const int32_t* cu_k,
                            const int32_t* item_seq, const int32_t* item_q0, int n_items, int heads, int head_dim,
-                           const float* slopes, int key_block, void* stream);
+                           const float* slopes, int key_block, int short_items, void* stream);
 
 /*
  * CRE x reference-label cross-attention collapsed to the 9 cCRE classes (exact identity):

@@ -138,6 +138,8 @@ def test_cross_attention_stacked_queries(H, hd):
     (2, 64, False, [200, 97, 300]),
     (32, 48, True, [1024, 201]),
     (8, 64, True, [1300]),
+    (32, 48, True, [201] * 9 + [73, 1, 256]),      # every item <= 2 query tiles: Q/O double-buffered across items
+    (8, 64, False, [200, 97, 130, 200, 200, 8]),
 ])
 @pytest.mark.parametrize("key_block", [64, 128])
 def test_tc_self_attention(H, hd, alibi, lens, key_block):

@@ -19,8 +19,8 @@ slopes = torch.tensor([2 ** (-8 * (h + 1) / H) for h in range(H)], device=DEV) i
 cq, ck = ops.cu_seqlens(lens_q, DEV), ops.cu_seqlens(lk, DEV)
 items = ops.TileMap(lens_q, ops.TC_BLOCK_M, DEV, k_lens=lens_k)
 for _ in range(3):
-    ops.attention_tc(q, k, v, cq, ck, items, H, hd, slopes, out=o)
+    ops.attention_tc(q, k, v, cq, ck, items, H, hd, slopes, out=o, key_block=int(sys.argv[2]) if len(sys.argv) > 2 else 64)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); ops.attention_tc(q, k, v, cq, ck, items, H, hd, slopes, out=o); e1.record(); torch.cuda.synchronize()
+e0.record(); ops.attention_tc(q, k, v, cq, ck, items, H, hd, slopes, out=o, key_block=int(sys.argv[2]) if len(sys.argv) > 2 else 64); e1.record(); torch.cuda.synchronize()
 print(which, "tc ms", e0.elapsed_time(e1))

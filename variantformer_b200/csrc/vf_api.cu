@@ -50,13 +50,13 @@ int vf_attention_varlen(const void* q, int ldq, const void* k, int ldk, const vo
 int vf_attention_tc_varlen(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
                            int64_t rows_q, int64_t rows_k, const int32_t* cu_q, const int32_t* cu_k,
                            const int32_t* item_seq, const int32_t* item_q0, int n_items, int heads, int head_dim,
-                           const float* slopes, int key_block, void* stream) {
+                           const float* slopes, int key_block, int short_items, void* stream) {
     VF_REQUIRE(key_block == 64 || key_block == 128, "attention_tc: key_block must be 64 or 128");
     if (key_block == 128)
         return attention_tc128_varlen(q, ldq, k, ldk, v, ldv, o, ldo, (long)rows_q, (long)rows_k, cu_q, cu_k, item_seq,
                                       item_q0, n_items, heads, head_dim, slopes, ST(stream));
     return attention_tc_varlen(q, ldq, k, ldk, v, ldv, o, ldo, (long)rows_q, (long)rows_k, cu_q, cu_k, item_seq,
-                               item_q0, n_items, heads, head_dim, slopes, ST(stream));
+                               item_q0, n_items, heads, head_dim, slopes, short_items, ST(stream));
 }
 int vf_label_attention(const void* q, int ldq, const float* kv9, const float* logc, const int32_t* row_seq, int n_rows,
                        int heads, int head_dim, void* out, int ldo, void* stream) {

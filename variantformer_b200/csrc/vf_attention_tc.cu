@@ -31,7 +31,7 @@ constexpr int kKStages = 4, kVStages = 4;
 constexpr uint32_t kTileBytes = 128 * 64 * 2;                 // one [128 x 64] bf16 tile (Q tile, P buffer)
 constexpr uint32_t kKvBytes = kKB * 64 * 2;                   // one [64 keys x 64] bf16 tile
 constexpr int kAttnThreads = 64 + 256;
-constexpr int kNumBars = 2 + 2 * kKStages + 2 * kVStages + 16 + 2;
+constexpr int kNumBars = 4 + 2 * kKStages + 2 * kVStages + 16 + 4;
 constexpr size_t kAttnSmem = 1024 + (size_t)kMaxQT * kTileBytes + (size_t)(kKStages + kVStages) * kKvBytes +
                              4 * kTileBytes + kNumBars * 8 + 64;
 
@@ -167,7 +167,10 @@ __device__ __forceinline__ void softmax_tile(uint32_t s_addr, uint32_t o_addr, b
     l += sum;
 }
 
-template <int HD, bool ALIBI>
+// SHORT: every work item has <= 2 query tiles (e.g. the 201-token gene self-attention).  Q slots and O accumulators
+// are then double-buffered across consecutive items (slot / accumulator base 2*(item&1)), so the TMA producer and
+// the MMA warp run into the next item while the softmax warps still drain the previous one.
+template <int HD, bool ALIBI, bool SHORT>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
@@ -178,27 +181,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint8_t* sm_v = sm_k + kKStages * kKvBytes;                   // kVStages tiles of 8 KB
     uint8_t* sm_p = sm_v + kVStages * kKvBytes;                   // [warpgroup][buffer] tiles of 16 KB
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm_p + 4 * kTileBytes);
-    uint64_t* q_full = bars + 0;  uint64_t* q_empty = bars + 1;
-    uint64_t* k_full = bars + 2;                 uint64_t* k_empty = k_full + kKStages;
+    uint64_t* q_full = bars + 0;  uint64_t* q_empty = bars + 2;                        // [2] each (index item&1 if SHORT)
+    uint64_t* k_full = bars + 4;                 uint64_t* k_empty = k_full + kKStages;
     uint64_t* v_full = k_empty + kKStages;       uint64_t* v_empty = v_full + kVStages;
     uint64_t* s_full = v_empty + kVStages;       uint64_t* s_empty = s_full + 4;       // [wg * 2 + buf]
     uint64_t* p_full = s_empty + 4;              uint64_t* p_empty = p_full + 4;       // [wg * 2 + buf]
-    uint64_t* o_full = p_empty + 4;              uint64_t* o_empty = o_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+    uint64_t* o_full = p_empty + 4;              uint64_t* o_empty = o_full + 2;       // [2] each
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_work = p.n_items * p.heads;
 
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-        mbar_init(q_full, 1); mbar_init(q_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 8);
+        }
         for (int i = 0; i < kKStages; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
         for (int i = 0; i < kVStages; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
         for (int i = 0; i < 4; ++i) {
             mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
             mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1);
         }
-        mbar_init(o_full, 1); mbar_init(o_empty, 8);
         fence_barrier_init();
     }
     if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -226,9 +230,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 int seq, head, q0, qbeg, Sq, kbeg, Sk, nq, nk;
                 decode(w, seq, head, q0, qbeg, Sq, kbeg, Sk, nq, nk);
                 const int col = head * HD;
-                mbar_wait(q_empty, (it & 1) ^ 1);
-                mbar_arrive_expect_tx(q_full, nq * kTileBytes);
-                for (int t = 0; t < nq; ++t) tma_load_2d(sm_q + t * kTileBytes, &tmQ, q_full, col, qbeg + q0 + t * kQT);
+                const int ib = SHORT ? (it & 1) : 0;                       // Q slot pair / barrier index of this item
+                const uint32_t ipar = SHORT ? ((it >> 1) & 1) : (it & 1);
+                mbar_wait(&q_empty[ib], ipar ^ 1);
+                mbar_arrive_expect_tx(&q_full[ib], nq * kTileBytes);
+                for (int t = 0; t < nq; ++t)
+                    tma_load_2d(sm_q + (ib * 2 + t) * kTileBytes, &tmQ, &q_full[ib], col, qbeg + q0 + t * kQT);
                 for (int j = 0; j < nk; ++j) {
                     mbar_wait(&k_empty[ks], kph ^ 1);
                     mbar_arrive_expect_tx(&k_full[ks], kKvBytes);
@@ -252,8 +259,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
                 int seq, head, q0, qbeg, Sq, kbeg, Sk, nq, nk;
                 decode(w, seq, head, q0, qbeg, Sq, kbeg, Sk, nq, nk);
-                mbar_wait(q_full, it & 1);
-                mbar_wait(o_empty, (it & 1) ^ 1);                   // previous item's O has been read out
+                const int ib = SHORT ? (it & 1) : 0;
+                const uint32_t ipar = SHORT ? ((it >> 1) & 1) : (it & 1);
+                mbar_wait(&q_full[ib], ipar);
+                mbar_wait(&o_empty[ib], ipar ^ 1);                  // the O accumulators of this slot pair have been read out
                 tc_fence_after();
                 // linearised steps n = j*nq + t (key block j, query tile t, warpgroup t&1)
                 const int N = nk * nq;
@@ -271,7 +280,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const int buf = m & 1;
                     mbar_wait(&s_empty[wg * 2 + buf], ((m >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    const uint64_t da = umma_desc_kmajor_sw128(smem_u32(sm_q + t * kTileBytes));
+                    const uint64_t da = umma_desc_kmajor_sw128(smem_u32(sm_q + (ib * 2 + t) * kTileBytes));
                     const uint64_t db = umma_desc_kmajor_sw128(smem_u32(sm_k + ks_of[j & 3] * kKvBytes));
 #pragma unroll
                     for (int k = 0; k < HD / 16; ++k)
@@ -291,7 +300,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const int buf = m & 1;
                     mbar_wait(&p_full[wg * 2 + buf], (m >> 1) & 1);
                     tc_fence_after();
-                    const uint32_t d = tmem_base + 256 + t * 64;
+                    const uint32_t d = tmem_base + 256 + (ib * 2 + t) * 64;
                     const uint64_t da = umma_desc_kmajor_sw128(smem_u32(sm_p + (wg * 2 + buf) * kTileBytes));
                     const uint32_t vb = smem_u32(sm_v + vs_of[j & 3] * kKvBytes);
 #pragma unroll
@@ -308,8 +317,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     if (n + LA < N) qk_step(n + LA);
                     pv_step(n);
                 }
-                umma_commit(o_full);
-                umma_commit(q_empty);
+                umma_commit(&o_full[ib]);
+                umma_commit(&q_empty[ib]);
             }
         }
         __syncwarp();
@@ -325,6 +334,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             decode(w, seq, head, q0, qbeg, Sq, kbeg, Sk, nq, nk);
             const float slope = ALIBI ? p.slopes[head] * 1.4426950408889634f : 0.f;
             const int shift = Sk - Sq;
+            const int ib = SHORT ? (it & 1) : 0;
+            const uint32_t ipar = SHORT ? ((it >> 1) & 1) : (it & 1);
             float m_ref[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
             for (int j = 0; j < nk; ++j) {
                 const int key0 = j * kKB;
@@ -337,7 +348,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const uint32_t par = (m >> 1) & 1;
                     mbar_wait(&s_full[bar], par);
                     tc_fence_after();
-                    const uint32_t s_addr = t_lane + wg * 128 + buf * kKB, o_addr = t_lane + 256 + t * 64;
+                    const uint32_t s_addr = t_lane + wg * 128 + buf * kKB, o_addr = t_lane + 256 + (ib * 2 + t) * 64;
                     uint8_t* my_p = sm_p + bar * kTileBytes;
                     uint64_t* prev_bar = m > 0 ? &p_empty[bar ^ 1] : nullptr;       // PV of this warpgroup's step m-1
                     const uint32_t prev_par = ((m - 1) >> 1) & 1;
@@ -350,13 +361,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 }
             }
             // ---- epilogue: O_t / l -> bf16 -> global ----
-            mbar_wait(o_full, it & 1);
+            mbar_wait(&o_full[ib], ipar);
             tc_fence_after();
             for (int tt = 0; wg + 2 * tt < nq; ++tt) {
                 const int t = wg + 2 * tt;
                 uint32_t o0[32], o1[32];
-                tmem_ld_32x32(t_lane + 256 + t * 64, o0);
-                tmem_ld_32x32(t_lane + 256 + t * 64 + 32, o1);
+                tmem_ld_32x32(t_lane + 256 + (ib * 2 + t) * 64, o0);
+                tmem_ld_32x32(t_lane + 256 + (ib * 2 + t) * 64 + 32, o1);
                 tmem_ld_wait();
                 const int qi = q0 + t * kQT + row;
                 if (qi < Sq) {
@@ -380,7 +391,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(o_empty);
+            if (lane == 0) mbar_arrive(&o_empty[ib]);
         }
     }
 
@@ -415,12 +426,12 @@ static int make_tmap_rows64(CUtensorMap* tm, const void* base, long rows, int co
     return 0;
 }
 
-template <int HD, bool ALIBI>
+template <int HD, bool ALIBI, bool SHORT>
 static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p,
                           cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        VF_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<HD, ALIBI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        VF_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<HD, ALIBI, SHORT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)kAttnSmem));
         attr_set = true;
     }
@@ -429,7 +440,7 @@ static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CU
     VF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const long work = (long)p.n_items * p.heads;
     const int grid = (int)(work < sms ? work : sms);
-    attention_tc_kernel<HD, ALIBI><<<grid, kAttnThreads, kAttnSmem, s>>>(tq, tk, tv, p);
+    attention_tc_kernel<HD, ALIBI, SHORT><<<grid, kAttnThreads, kAttnSmem, s>>>(tq, tk, tv, p);
     VF_LAUNCH_OK("attention_tc_kernel launch");
     return 0;
 }
@@ -437,7 +448,7 @@ static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CU
 int attention_tc_varlen(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
                         long rows_q, long rows_k, const int* cu_q, const int* cu_k, const int* item_seq,
                         const int* item_q0, int n_items, int heads, int head_dim, const float* slopes,
-                        cudaStream_t stream) {
+                        int short_items, cudaStream_t stream) {
     VF_REQUIRE(head_dim == 48 || head_dim == 64, "attention_tc: head_dim %d not supported (48/64)", head_dim);
     VF_REQUIRE(ldo % 8 == 0, "attention_tc: output stride must keep 16-byte alignment");
     if (n_items == 0) return 0;
@@ -450,8 +461,14 @@ int attention_tc_varlen(const void* q, int ldq, const void* k, int ldk, const vo
     p.cu_q = cu_q; p.cu_k = cu_k; p.item_seq = item_seq; p.item_q0 = item_q0; p.n_items = n_items; p.heads = heads;
     p.o = (__nv_bfloat16*)o; p.ldo = ldo; p.slopes = slopes;
     p.scale_log2 = (1.0f / sqrtf((float)head_dim)) * 1.4426950408889634f;
-    if (head_dim == 48) return slopes ? launch_attn_tc<48, true>(tq, tk, tv, p, stream) : launch_attn_tc<48, false>(tq, tk, tv, p, stream);
-    return slopes ? launch_attn_tc<64, true>(tq, tk, tv, p, stream) : launch_attn_tc<64, false>(tq, tk, tv, p, stream);
+#define VF_ATTN_DISPATCH(HD_)                                                                                     \
+    if (short_items) return slopes ? launch_attn_tc<HD_, true, true>(tq, tk, tv, p, stream)                      \
+                                   : launch_attn_tc<HD_, false, true>(tq, tk, tv, p, stream);                    \
+    return slopes ? launch_attn_tc<HD_, true, false>(tq, tk, tv, p, stream)                                      \
+                  : launch_attn_tc<HD_, false, false>(tq, tk, tv, p, stream);
+    if (head_dim == 48) { VF_ATTN_DISPATCH(48) }
+    VF_ATTN_DISPATCH(64)
+#undef VF_ATTN_DISPATCH
 }
 
 }  // namespace vf

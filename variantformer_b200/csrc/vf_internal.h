@@ -18,7 +18,7 @@ int attention_varlen(const void* q, int ldq, const void* k, int ldk, const void*
 int attention_tc_varlen(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
                         long rows_q, long rows_k, const int* cu_q, const int* cu_k, const int* item_seq,
                         const int* item_q0, int n_items, int heads, int head_dim, const float* slopes,
-                        cudaStream_t stream);
+                        int short_items, cudaStream_t stream);
 
 int attention_tc128_varlen(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
                            long rows_q, long rows_k, const int* cu_q, const int* cu_k, const int* item_seq,

@@ -254,9 +254,9 @@ class Engine:
         s["cu_cre"] = ops.cu_seqlens(C, dev)
         if ATTENTION_IMPL == "tc" and self.w.hd in (48, 64):
             # The kernel is chosen per ROLE, never per batch content, so results do not depend on how genes are batched:
-            # tcgen05 for the stacked cross-attention and the CRE stream; the <=201-token gene self-attention
-            # (2 x 2 tiles per item, 38 % padding) stays on the warp-MMA kernel, which is faster at that shape.
-            s["tiles_gself"] = ops.TileMap(seq_lens, 64, dev)
+            # tcgen05 for every seq2gene attention (stacked cross-attention with 128-key blocks; CRE and gene
+            # self-attention with 64-key blocks, the <=201-token gene items double-buffered across items).
+            s["tiles_gself"] = ops.TileMap(seq_lens, ops.TC_BLOCK_M, dev)
             s["tiles_gcross"] = ops.TileMap(T * (G + 1), ops.TC_BLOCK_M, dev, k_lens=C)
             s["tiles_cself"] = ops.TileMap(C, ops.TC_BLOCK_M, dev)
         else:

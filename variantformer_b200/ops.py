@@ -100,6 +100,7 @@ class TileMap:
         first = np.cumsum(nt) - nt
         q0 = (np.arange(int(nt.sum())) - np.repeat(first, nt)) * block_m
         self.block_m = block_m
+        self.max_rows = int(q_lens.max()) if len(q_lens) else 0
         self.n_tiles = int(nt.sum())
         self.tile_seq = torch.from_numpy(seq.astype(np.int32)).to(device, non_blocking=True)
         self.tile_q0 = torch.from_numpy(q0.astype(np.int32)).to(device, non_blocking=True)
@@ -139,7 +140,8 @@ def attention_tc(q, k, v, cu_q, cu_k, items: TileMap, heads, head_dim, slopes=No
         check(_lib.lib().vf_attention_tc_varlen(ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0),
                                                 ptr(out), out.stride(0), q.shape[0], k.shape[0], ptr(cu_q), ptr(cu_k),
                                                 ptr(items.tile_seq), ptr(items.tile_q0), items.n_tiles, heads,
-                                                head_dim, ptr(slopes), key_block, stream()))
+                                                head_dim, ptr(slopes), key_block, int(key_block == 64 and items.max_rows <= 256),
+                                                stream()))
     return out
 
 
