@@ -69,6 +69,55 @@ class HotPath:
         return dict(cre_tok=cre_tok, cre_msk=cre_msk, gene_tok=gene_tok, gene_msk=gene_msk, labels=labels,
                     lens=(ccnt_h, glen_h), err=errs)
 
+    def prepare(self, genes, variants: SampleVariants = None):
+        """Stage 1 + all host bookkeeping for one slab -> a prepared slab for Engine.run."""
+        t = self.tokenize(genes, variants)
+        tissues = [torch.as_tensor(g.tissues, dtype=torch.long) for g in genes]
+        slab = self.engine.prepare(t["cre_tok"], t["cre_msk"], t["gene_tok"], t["gene_msk"], tissues, t["labels"],
+                                   lens=t["lens"])
+        slab["err"] = t["err"]
+        return slab
+
+    def predict_pipelined(self, slabs, variants: SampleVariants = None, to_host=True):
+        """Generator over an iterable of gene lists: while the model (stages 2-4) of slab i runs on the current
+        stream, stage 1 and the host bookkeeping of slab i+1 run on a side stream, so their device->host count reads
+        and host work no longer leave the GPU idle between slabs.  Yields (pred, emb[, err]) per slab in order."""
+        main = torch.cuda.current_stream(self.engine.device)
+        if not hasattr(self, "_side"):
+            self._side = torch.cuda.Stream(self.engine.device)
+        side = self._side
+        side.wait_stream(main)                          # genome / variants / merge tables were uploaded on `main`
+
+        def stage(genes):
+            with torch.cuda.stream(side):
+                slab = self.prepare(genes, variants)
+                ev = torch.cuda.Event(); ev.record(side)
+            for v in slab.values():                     # tensors born on the side stream are consumed on `main`
+                for x in (v if isinstance(v, (list, tuple)) else [v]):
+                    if torch.is_tensor(x) and x.is_cuda:
+                        x.record_stream(main)
+                    elif hasattr(x, "tile_seq"):
+                        x.tile_seq.record_stream(main); x.tile_q0.record_stream(main)
+            return slab, ev
+
+        it = iter(slabs)
+        try:
+            nxt = stage(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            slab, ev = nxt
+            main.wait_event(ev)
+            out = self.engine.run(slab)                 # asynchronous launches on `main`
+            try:
+                nxt = stage(next(it))                   # overlaps with the launches above
+            except StopIteration:
+                nxt = None
+            if to_host:
+                yield out["pred"].cpu().numpy(), out["emb"].cpu().numpy()
+            else:
+                yield out["pred"], out["emb"], slab["err"]
+
     def predict(self, genes, variants: SampleVariants = None, to_host=True):
         """-> (pred [sum T], emb [sum T, D]) as numpy (to_host) or device tensors."""
         t = self.tokenize(genes, variants)
