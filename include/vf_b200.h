@@ -57,6 +57,26 @@ int vf_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, i
                  void* stream);
 
 /*
+ * Same GEMM with the LayerNorm that precedes the Linear folded in, and/or row statistics of the output:
+ *   ln_stats (fp32 [M, ln_parts, 2] = partial per-row sums and sums of squares of the fp32 rows that A mirrors in bf16;
+ *   the partials of a row are added in index order), ln_colsum (fp32 [N], column sums of the gamma-folded weight, same
+ *   layout as bias), ln_dim (normalised width), ln_eps:
+ *     out = epilogue( rstd_r * (A·W'^T - mean_r * colsum) + bias' ),  W' = W*gamma, bias' = bias + W·beta
+ *   which equals Linear(LayerNorm(x)) (seq2reg/modules.py:143-147,176-189; seq2gene/modules/layers.py:74-76,116-163).
+ *   Allowed with the bf16 epilogues only.  NULL ln_stats = plain GEMM.
+ *   stats_out (fp32 [M, 2*ceil(N/256), 2]): the fp32 epilogues store one partial (sum, sum of squares) of every output
+ *   row per 128-column half tile (plain stores: deterministic), i.e. the ln_stats of the next folded GEMM with
+ *   ln_parts = 2*ceil(N/256).  NULL = off.
+ */
+int vf_gemm_bf16_ln(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int epilogue,
+                    const float* bias, const float* resid, int ldr, void* out, int ldo, void* out2_bf16, int ldo2,
+                    const float* ln_stats, int ln_parts, const float* ln_colsum, int ln_dim, float ln_eps,
+                    float* stats_out, void* stream);
+/* Per-row (sum, sum of squares) of an fp32 matrix [M,d] into stats [M,1,2] + optional bf16 mirror: the statistics of a
+ * stream at the point it is assembled (seq2reg/model.py:214-220 embeddings; layers.py:508-521 registry prepend). */
+int vf_rowstats(const float* x, int ldx, int M, int d, float* stats, void* out_bf16, int ldo, void* stream);
+
+/*
  * Variable-length non-causal attention, one launch for all sequences and heads.
  * q/k/v/o: bf16, head h at columns [h*head_dim, (h+1)*head_dim) of each row; packed QKV/KV buffers are
  * addressed by passing offset base pointers.  cu_q/cu_k: int32 [n_seq+1] row prefix sums.

@@ -22,8 +22,14 @@ def _store(out, val):
     return out
 
 
-def gemm(a, w, epilogue, bias=None, resid=None, out=None, out2=None):
+def gemm(a, w, epilogue, bias=None, resid=None, out=None, out2=None, ln=None, stats_out=None):
     y = a.float() @ w.float().t()
+    if ln is not None:                       # LayerNorm fold: rstd * (acc - mean * colsum)
+        stats, colsum, dim, eps = ln
+        st = stats.sum(1)
+        mean = st[:, 0] / dim
+        rstd = torch.rsqrt((st[:, 1] / dim - mean * mean).clamp_min(0) + eps)
+        y = rstd[:, None] * (y - mean[:, None] * colsum[None, :])
     if bias is not None:
         y = y + bias
     if epilogue == EPI_BIAS_GEGLU_BF16:
@@ -41,6 +47,9 @@ def gemm(a, w, epilogue, bias=None, resid=None, out=None, out2=None):
         dt = torch.float32
     if out2 is not None:
         out2.copy_(y.to(torch.bfloat16))
+    if stats_out is not None:
+        stats_out.zero_()
+        stats_out[:, 0].copy_(torch.stack([y.sum(1), (y * y).sum(1)], 1))
     if out is None:
         return y.to(dt)
     assert out.dtype == dt
@@ -97,6 +106,17 @@ def layernorm(x, gamma, beta, eps=1e-5, gelu=False, out=None):
     if gelu:
         y = F.gelu(y)
     return _store(out, y) if out is not None else y.bfloat16()
+
+
+def stats_parts(n):
+    return 2 * ((n + 255) // 256)
+
+
+def rowstats(x, stats=None, out_bf16=None):
+    st = torch.stack([x.sum(1), (x * x).sum(1)], 1)[:, None, :]
+    if out_bf16 is not None:
+        out_bf16.copy_(x.bfloat16())
+    return _store(stats, st) if stats is not None else st
 
 
 def window_lengths(pad_mask_u8):

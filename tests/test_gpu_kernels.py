@@ -87,6 +87,62 @@ def test_gemm_inplace_residual_and_strided_output():
     assert big[:, :N].abs().max() == 0 and big[:, 2 * N:].abs().max() == 0
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 512, 512), (1000, 1536, 1536), (4099, 4608, 1536), (77, 256, 192)])
+def test_gemm_stats_out_and_layernorm_fold(M, N, K):
+    """The epilogue of an fp32 GEMM accumulates each output row's (sum, sum of squares); a following GEMM on the bf16
+    mirror with gamma/beta folded into W/bias reproduces Linear(LayerNorm(x)) (layers.py:116-163)."""
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = (torch.randn(M, K, generator=g) * 0.5).to(DEV).bfloat16()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV).bfloat16()
+    bias = torch.randn(N, generator=g).to(DEV)
+    resid = (torch.randn(M, N, generator=g) * 0.7 + 0.3).to(DEV)
+    x = torch.empty(M, N, device=DEV); xb = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    st = torch.full((M, ops.stats_parts(N), 2), 7.0, device=DEV)           # every partial is overwritten
+    ops.gemm(a, w, EPI_BIAS_RESID_F32, bias=bias, resid=resid, out=x, out2=xb, stats_out=st)
+    torch.cuda.synchronize()
+    want_x = a.float() @ w.float().t() + bias + resid
+    assert torch.allclose(x, want_x, atol=2e-3, rtol=2e-3)
+    tot = st.sum(1)
+    assert torch.allclose(tot[:, 0], x.sum(1), atol=2e-2, rtol=1e-4), (tot[:4, 0], x.sum(1)[:4])
+    assert torch.allclose(tot[:, 1], (x * x).sum(1), atol=2e-2, rtol=1e-4)
+    st2 = ops.rowstats(x)                                                   # the stand-alone statistics kernel agrees
+    torch.cuda.synchronize()
+    assert torch.allclose(st2[:, 0], tot, atol=2e-2, rtol=1e-4)
+    st_again = torch.empty_like(st)                                         # plain stores in a fixed order: bit-reproducible
+    ops.gemm(a, w, EPI_BIAS_RESID_F32, bias=bias, resid=resid, out=torch.empty_like(x), stats_out=st_again)
+    torch.cuda.synchronize()
+    assert torch.equal(st, st_again)
+    # consumer: Linear(LayerNorm(x)) with a [N2, N] weight
+    N2 = 512
+    gamma = (1 + 0.2 * torch.randn(N, generator=g)).to(DEV); beta = (0.1 * torch.randn(N, generator=g)).to(DEV)
+    w2 = (torch.randn(N2, N, generator=g) / math.sqrt(N)).to(DEV); b2 = torch.randn(N2, generator=g).to(DEV)
+    want = F.linear(F.layer_norm(x, (N,), gamma, beta, 1e-5), w2, b2)
+    wf = (w2 * gamma[None, :]).bfloat16(); cs = wf.float().sum(1).contiguous(); bf = (b2 + w2 @ beta).contiguous()
+    got = ops.gemm(xb, wf.contiguous(), EPI_BIAS_BF16, bias=bf, ln=(st, cs, N, 1e-5))
+    torch.cuda.synchronize()
+    assert torch.allclose(got.float(), want, atol=4e-2, rtol=2e-2), _describe_mismatch(got.float(), want, 4e-2)
+    # GeGLU consumer (tile-interleaved weight / bias / column sums)
+    w3 = (torch.randn(2048, N, generator=g) / math.sqrt(N)).to(DEV); b3 = torch.randn(2048, generator=g).to(DEV)
+    y = F.linear(F.layer_norm(x, (N,), gamma, beta, 1e-5), w3, b3)
+    u, gate = y.chunk(2, -1)
+    want3 = u * F.gelu(gate)
+    wf3 = (w3 * gamma[None, :]).bfloat16(); cs3 = wf3.float().sum(1); bf3 = b3 + w3 @ beta
+    got3 = ops.gemm(xb, interleave_geglu(wf3), EPI_BIAS_GEGLU_BF16, bias=interleave_geglu(bf3),
+                    ln=(st, interleave_geglu(cs3), N, 1e-5))
+    torch.cuda.synchronize()
+    assert torch.allclose(got3.float(), want3, atol=5e-2, rtol=3e-2), _describe_mismatch(got3.float(), want3, 5e-2)
+
+
+def test_rowstats_mirror():
+    x = torch.randn(1001, 1536, device=DEV) * 2 + 0.5
+    xb = torch.empty(1001, 1536, dtype=torch.bfloat16, device=DEV)
+    st = ops.rowstats(x, None, xb)
+    torch.cuda.synchronize()
+    assert torch.equal(xb, x.bfloat16())
+    assert st.shape == (1001, 1, 2)
+    assert torch.allclose(st[:, 0, 0], x.sum(1), rtol=1e-5, atol=1e-2) and torch.allclose(st[:, 0, 1], (x * x).sum(1), rtol=1e-5)
+
+
 def _ref_attention(q, k, v, lens_q, lens_k, H, hd, slopes):
     out = torch.empty(q.shape[0], H * hd, device=q.device)
     qs = ks = 0

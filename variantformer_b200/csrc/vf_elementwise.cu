@@ -92,6 +92,42 @@ int layernorm(const float* x, int ldx, const float* gamma, const float* beta, in
 }
 
 // ---------------------------------------------------------------------------------
+// Row statistics of a freshly assembled fp32 stream: (sum, sum of squares) per row and
+// the bf16 mirror that the LayerNorm-folded GEMMs read as their A operand (vf_gemm.cu).
+// Used once where a stream is born (token embedding, registry-token assembly); every
+// later LayerNorm input gets its statistics from the GEMM epilogue that produced it.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rowstats_kernel(const float* __restrict__ x, int ldx, int M, int d, float* __restrict__ stats,
+                __nv_bfloat16* __restrict__ out, int ldo) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    const float* xr = x + (size_t)row * ldx;
+    float s = 0.f, q = 0.f;
+    for (int c = lane * 4; c < d; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + c);
+        s += (v.x + v.y) + (v.z + v.w);
+        q += fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w);
+        if (out) {
+            uint2 pk; pk.x = pack_bf16x2(v.x, v.y); pk.y = pack_bf16x2(v.z, v.w);
+            *reinterpret_cast<uint2*>(out + (size_t)row * ldo + c) = pk;
+        }
+    }
+    s = warp_sum(s); q = warp_sum(q);
+    if (lane == 0) { stats[2 * (size_t)row] = s; stats[2 * (size_t)row + 1] = q; }
+}
+
+int rowstats(const float* x, int ldx, int M, int d, float* stats, void* out_bf16, int ldo, cudaStream_t s) {
+    if (M == 0) return 0;
+    VF_REQUIRE(d % 4 == 0 && ldx % 4 == 0 && (!out_bf16 || ldo % 4 == 0) && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+               "rowstats: width and strides must be multiples of 4 elements, 16-byte aligned input");
+    rowstats_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, ldx, M, d, stats, (__nv_bfloat16*)out_bf16, ldo);
+    VF_LAUNCH_OK("rowstats_kernel launch");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
 // Window unpadding (flash_attn.bert_padding.unpad_input at seq2reg/modules.py:156-161):
 // valid tokens of each [L]-token window are compacted in order; `pos` keeps the
 // original in-window position for the positional encoding.  One warp per window.

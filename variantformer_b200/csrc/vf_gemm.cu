@@ -8,13 +8,23 @@
 //   seq2gene/model_combined_modulator.py:502-507 (gene_map, cre_map),
 //   seq2gene/modules/layers.py:1078-1087 (head Linear layers).
 //
-// Kernel shape: persistent, one CTA per SM, 320 threads:
-//   warp 0   : TMA producer (one elected lane)       smem ring of kStages x (A 128x64 + W 256x64) bf16
-//   warp 1   : TMEM allocator + tcgen05.mma issuer   UMMA 128x256x16, 4 per k-block
-//   warps 2-9: epilogue (TMEM lane quadrant = warp%4, two warps per quadrant): pipelined tcgen05.ld, bias /
-//              GeGLU / GELU / +residual, transposed through a swizzled smem tile for fully coalesced stores
+// Kernel shape: persistent, one CTA per SM, 384 threads = 3 warpgroups:
+//   warp 0    : TMA producer (one elected lane)       smem ring of kStages x (A 128x64 + W 256x64) bf16;
+//               also bulk-prefetches the fp32 residual tile of the tile it is loading into L2
+//   warp 1    : TMEM allocator + tcgen05.mma issuer   UMMA 128x256x16, 4 per k-block
+//   warps 2-3 : idle (they only exist so that warpgroup 0 can give its registers away with setmaxnreg)
+//   warps 4-11: epilogue (TMEM lane quadrant = warp%4, two warps per quadrant), 232 registers each: pipelined
+//               tcgen05.ld, LayerNorm fold / bias / GeGLU / GELU / +residual, transposed through a swizzled smem
+//               tile for fully coalesced stores, optional bf16 mirror and per-row (sum, sum of squares)
 // Two 256-column fp32 accumulators (all 512 TMEM columns) double-buffer the
 // epilogue of tile i against the mainloop of tile i+1.
+//
+// LayerNorm fold (seq2reg/modules.py:143-144, layers.py:74-76 feed every LN straight into a Linear):
+//   LN(x) W^T + b = rstd_r * (x (W*gamma)^T - mean_r * colsum(W*gamma)) + (b + W beta)
+// so a GEMM whose A operand is the bf16 mirror of the un-normalised fp32 stream, with gamma folded into W at load
+// time, only needs the per-row (sum, sum of squares) of x in its epilogue.  Those are written by the epilogue
+// of the GEMM that PRODUCED x (stats_out) as one partial per (column tile, epilogue half) — plain stores, summed in a
+// fixed order by the consumer, so results are bit-reproducible — and no separate LayerNorm pass ever reads the stream.
 #include <cuda.h>
 #include <stdio.h>
 
@@ -25,7 +35,8 @@ namespace vf {
 
 constexpr int BM = 128, BN = 256, BK = 64, kStages = 4;
 constexpr int kEpiWarps = 8;                          // two warps per TMEM lane quadrant
-constexpr int kGemmThreads = 64 + kEpiWarps * 32;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kFirstEpiWarp = 4;                      // warpgroup 0 = TMA + MMA (+2 idle warps), warpgroups 1-2 = epilogue
+constexpr int kGemmThreads = (kFirstEpiWarp + kEpiWarps) * 32;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
 constexpr uint32_t kStageOutBytes = 32 * 32 * 4;      // per-epilogue-warp staging tile: 32 rows x 32 fp32 columns
@@ -41,6 +52,11 @@ struct GemmParams {
     int ldo;
     __nv_bfloat16* out2;     // optional bf16 mirror of an fp32 output (row stride ldo2)
     int ldo2;
+    const float* ln_stats;   // LayerNorm fold: fp32 [M, ln_parts, 2] partial (sum, sum of squares) of the rows A mirrors
+    int ln_parts;            //                 (nullptr = no fold)
+    const float* ln_colsum;  //                 fp32 [N] column sums of the gamma-folded weight (layout of `bias`)
+    float ln_inv_d, ln_eps;  //                 1 / normalised width, eps
+    float* stats_out;        // fp32 outputs: partial (sum, sum of squares) of every output row -> [M, 2*n_tiles, 2], or nullptr
 };
 
 template <int EPI>
@@ -55,8 +71,8 @@ constexpr bool epi_is_bf16() {
 // 16-byte chunks are XOR-swizzled inside the tile so both the row-wise writes and the column-wise reads are
 // bank-conflict free.
 // Residual slab prefetch: the 8 float4 this lane will add in the coalesced phase (4 rows x 128 B per warp request).
-// Issued as one batch well before they are needed so DRAM latency overlaps the TMEM load and the staging writes
-// (loads cannot be hoisted by the compiler itself: `out` may alias `resid`).
+// Issued as one batch well before they are needed so the (L2, see the producer's bulk prefetch) latency overlaps the
+// TMEM load and the staging writes (loads cannot be hoisted by the compiler itself: `out` may alias `resid`).
 __device__ __forceinline__ void load_resid_slab(const GemmParams& p, int row0, int col0, int lane, float4 (&rr4)[8]) {
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
@@ -67,9 +83,42 @@ __device__ __forceinline__ void load_resid_slab(const GemmParams& p, int row0, i
     }
 }
 
+// Per-warp running (sum, sum of squares) of the fp32 rows it stores: lane holds the partial of rows it*4 + (lane>>3)
+// over its own 4 columns of every slab; reduced over the 8 lanes of a row group once per tile.
+struct RowStats {
+    float s1[8], s2[8];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+    }
+    // 8 values x 8 lanes -> lane k of each 8-lane group ends with the group total of value k (7 shuffles per array)
+    static __device__ __forceinline__ float reduce8(const float (&s)[8], int lane) {
+        float t[4], u[2];
+        const bool b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float mine = b4 ? s[i + 4] : s[i], other = b4 ? s[i] : s[i + 4];
+            t[i] = mine + __shfl_xor_sync(0xffffffffu, other, 4);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float mine = b2 ? t[i + 2] : t[i], other = b2 ? t[i] : t[i + 2];
+            u[i] = mine + __shfl_xor_sync(0xffffffffu, other, 2);
+        }
+        const float mine = b1 ? u[1] : u[0], other = b1 ? u[0] : u[1];
+        return mine + __shfl_xor_sync(0xffffffffu, other, 1);
+    }
+    __device__ __forceinline__ void flush(float* stats_out, int row0, int M, int part, int parts, int lane) {
+        const float a = reduce8(s1, lane), b = reduce8(s2, lane);
+        const int grow = row0 + (lane & 7) * 4 + (lane >> 3);          // lane publishes row (lane&7)*4 + (lane>>3)
+        if (grow < M) *reinterpret_cast<float2*>(stats_out + 2 * ((size_t)grow * parts + part)) = make_float2(a, b);
+    }
+};
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_store_slab(const GemmParams& p, uint8_t* stage, int row0, int col0, int n_out,
-                                                    const float (&v)[32], int lane, const float4 (&rr4)[8]) {
+                                                    const float (&v)[32], int lane, const float4 (&rr4)[8],
+                                                    RowStats& rs) {
     if constexpr (epi_is_bf16<EPI>()) {
         uint4* st = reinterpret_cast<uint4*>(stage);                    // [32 rows][4 chunks of 16 B]
 #pragma unroll
@@ -110,6 +159,8 @@ __device__ __forceinline__ void epilogue_store_slab(const GemmParams& p, uint8_t
                     uint2 h; h.x = pack_bf16x2(q.x, q.y); h.y = pack_bf16x2(q.z, q.w);
                     *reinterpret_cast<uint2*>(p.out2 + (size_t)grow * p.ldo2 + gcol) = h;
                 }
+                rs.s1[it] += (q.x + q.y) + (q.z + q.w);
+                rs.s2[it] += fmaf(q.x, q.x, q.y * q.y) + fmaf(q.z, q.z, q.w * q.w);
             }
         }
         __syncwarp();
@@ -119,7 +170,7 @@ __device__ __forceinline__ void epilogue_store_slab(const GemmParams& p, uint8_t
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;                                  // kStages x 16 KB
@@ -140,6 +191,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if constexpr (EPI == VF_EPI_BIAS_RESID_F32) tma_prefetch_desc(&tmR);
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kEpiWarps); }
         fence_barrier_init();
@@ -153,65 +205,92 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        // ================= TMA producer =================
-        if (elect_one()) {
-            int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full[stage], kStageBytes);
-                    tma_load_2d(smem_a + stage * kABytes, &tmA, &full[stage], kb * BK, m0);
-                    tma_load_2d(smem_b + stage * kBBytes, &tmB, &full[stage], kb * BK, n0);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-            int stage = 0; uint32_t phase = 0; int it = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-                const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
-                    const uint64_t da = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * kABytes));
-                    const uint64_t db = umma_desc_kmajor_sw128(smem_u32(smem_b + stage * kBBytes));
+    if (warp < kFirstEpiWarp) {
+        reg_dealloc<40>();                                   // warpgroup 0 hands its registers to the epilogue warps
+        if (warp == 0) {
+            // ================= TMA producer =================
+            if (elect_one()) {
+                int stage = 0; uint32_t phase = 0;
+                for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                    const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+                    if constexpr (EPI == VF_EPI_BIAS_RESID_F32) {
+                        // the epilogue of this tile runs one mainloop from now: pull its residual into L2 meanwhile
+                        if (p.resid) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // +32 bytes per UMMA_K step inside the 128-byte swizzle row (start address is in 16 B units)
-                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                            for (int c = 0; c < BN; c += 64)
+                                if (n0 + c < p.N) tma_prefetch_l2_2d(&tmR, n0 + c, m0);
+                        }
                     }
-                    umma_commit(&empty[stage]);                      // frees the smem slot when these MMAs retire
-                    if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    for (int kb = 0; kb < k_blocks; ++kb) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&full[stage], kStageBytes);
+                        tma_load_2d(smem_a + stage * kABytes, &tmA, &full[stage], kb * BK, m0);
+                        tma_load_2d(smem_b + stage * kBBytes, &tmB, &full[stage], kb * BK, n0);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
                 }
             }
+            __syncwarp();
+        } else if (warp == 1) {
+            // ================= MMA issuer =================
+            if (elect_one()) {
+                constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+                int stage = 0; uint32_t phase = 0; int it = 0;
+                for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+                    const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
+                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * BN;
+                    for (int kb = 0; kb < k_blocks; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint64_t da = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * kABytes));
+                        const uint64_t db = umma_desc_kmajor_sw128(smem_u32(smem_b + stage * kBBytes));
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // +32 bytes per UMMA_K step inside the 128-byte swizzle row (start address is in 16 B units)
+                            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        umma_commit(&empty[stage]);                      // frees the smem slot when these MMAs retire
+                        if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+            __syncwarp();
         }
-        __syncwarp();
     } else {
         // ================= epilogue warps =================
         // warp%4 selects the TMEM lane quadrant (hardware rule); the two warps of a quadrant interleave the
         // 32-column slabs (even / odd).  TMEM loads are software-pipelined: slab i+1 is in flight while slab i is
         // converted and stored.
+        reg_alloc<232>();
         const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int half = (warp - kFirstEpiWarp) >> 2;
         const int lane = threadIdx.x & 31;
-        uint8_t* stage_out = smem_out + (warp - 2) * kStageOutBytes;
+        uint8_t* stage_out = smem_out + (warp - kFirstEpiWarp) * kStageOutBytes;
         constexpr int kSlabs = (EPI == VF_EPI_BIAS_GEGLU_BF16) ? 2 : 4;      // per warp per tile
         const int n_out = (EPI == VF_EPI_BIAS_GEGLU_BF16) ? p.N / 2 : p.N;
+        const bool ln = epi_is_bf16<EPI>() && p.ln_stats != nullptr;
+        const bool want_stats = !epi_is_bf16<EPI>() && p.stats_out != nullptr;
+        RowStats rs;
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
             const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
             const int row0 = m0 + quad * 32;
+            // LayerNorm fold: this thread's row is normalised as  ln_a * acc + ln_c * colsum[n] + bias'[n]
+            float ln_a = 1.f, ln_c = 0.f;
+            if (ln && row0 + lane < p.M) {
+                const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + (size_t)(row0 + lane) * p.ln_parts;
+                float2 st = __ldg(sp);
+                for (int i = 1; i < p.ln_parts; ++i) { const float2 t2 = __ldg(sp + i); st.x += t2.x; st.y += t2.y; }
+                const float mean = st.x * p.ln_inv_d;
+                const float var = fmaxf(fmaf(st.y, p.ln_inv_d, -mean * mean), 0.f);
+                ln_a = rsqrtf(var + p.ln_eps);
+                ln_c = -ln_a * mean;
+            }
+            rs.clear();
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
@@ -238,13 +317,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             bu = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c * 32 + j));
                             bg = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 128 + c * 32 + j));
                         }
-                        v[j + 0] = (__uint_as_float(ru[i & 1][j + 0]) + bu.x) * gelu_erf(__uint_as_float(rg[i & 1][j + 0]) + bg.x);
-                        v[j + 1] = (__uint_as_float(ru[i & 1][j + 1]) + bu.y) * gelu_erf(__uint_as_float(rg[i & 1][j + 1]) + bg.y);
-                        v[j + 2] = (__uint_as_float(ru[i & 1][j + 2]) + bu.z) * gelu_erf(__uint_as_float(rg[i & 1][j + 2]) + bg.z);
-                        v[j + 3] = (__uint_as_float(ru[i & 1][j + 3]) + bu.w) * gelu_erf(__uint_as_float(rg[i & 1][j + 3]) + bg.w);
+                        if (ln) {
+                            const float4 su = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + c * 32 + j));
+                            const float4 sg = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + 128 + c * 32 + j));
+                            bu.x = fmaf(ln_c, su.x, bu.x); bu.y = fmaf(ln_c, su.y, bu.y);
+                            bu.z = fmaf(ln_c, su.z, bu.z); bu.w = fmaf(ln_c, su.w, bu.w);
+                            bg.x = fmaf(ln_c, sg.x, bg.x); bg.y = fmaf(ln_c, sg.y, bg.y);
+                            bg.z = fmaf(ln_c, sg.z, bg.z); bg.w = fmaf(ln_c, sg.w, bg.w);
+                        }
+                        v[j + 0] = fmaf(__uint_as_float(ru[i & 1][j + 0]), ln_a, bu.x) * gelu_erf(fmaf(__uint_as_float(rg[i & 1][j + 0]), ln_a, bg.x));
+                        v[j + 1] = fmaf(__uint_as_float(ru[i & 1][j + 1]), ln_a, bu.y) * gelu_erf(fmaf(__uint_as_float(rg[i & 1][j + 1]), ln_a, bg.y));
+                        v[j + 2] = fmaf(__uint_as_float(ru[i & 1][j + 2]), ln_a, bu.z) * gelu_erf(fmaf(__uint_as_float(rg[i & 1][j + 2]), ln_a, bg.z));
+                        v[j + 3] = fmaf(__uint_as_float(ru[i & 1][j + 3]), ln_a, bu.w) * gelu_erf(fmaf(__uint_as_float(rg[i & 1][j + 3]), ln_a, bg.w));
                     }
                     float4 none[8];
-                    epilogue_store_slab<EPI>(p, stage_out, row0, out0 + c * 32, n_out, v, lane, none);
+                    epilogue_store_slab<EPI>(p, stage_out, row0, out0 + c * 32, n_out, v, lane, none, rs);
                 }
             } else {
                 uint32_t r[2][32];
@@ -269,14 +356,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int j = 0; j < 32; j += 4) {
                         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (p.bias && col0 + j + 4 <= p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                        v[j + 0] = __uint_as_float(r[i & 1][j + 0]) + b.x; v[j + 1] = __uint_as_float(r[i & 1][j + 1]) + b.y;
-                        v[j + 2] = __uint_as_float(r[i & 1][j + 2]) + b.z; v[j + 3] = __uint_as_float(r[i & 1][j + 3]) + b.w;
+                        if constexpr (epi_is_bf16<EPI>()) {
+                            if (ln && col0 + j + 4 <= p.N) {
+                                const float4 sc = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0 + j));
+                                b.x = fmaf(ln_c, sc.x, b.x); b.y = fmaf(ln_c, sc.y, b.y);
+                                b.z = fmaf(ln_c, sc.z, b.z); b.w = fmaf(ln_c, sc.w, b.w);
+                            }
+                        }
+                        v[j + 0] = fmaf(__uint_as_float(r[i & 1][j + 0]), ln_a, b.x);
+                        v[j + 1] = fmaf(__uint_as_float(r[i & 1][j + 1]), ln_a, b.y);
+                        v[j + 2] = fmaf(__uint_as_float(r[i & 1][j + 2]), ln_a, b.z);
+                        v[j + 3] = fmaf(__uint_as_float(r[i & 1][j + 3]), ln_a, b.w);
                     }
                     if constexpr (EPI == VF_EPI_BIAS_GELU_BF16) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
                     }
-                    epilogue_store_slab<EPI>(p, stage_out, row0, col0, n_out, v, lane, rr4[i & 1]);
+                    epilogue_store_slab<EPI>(p, stage_out, row0, col0, n_out, v, lane, rr4[i & 1], rs);
                 }
             }
             // all TMEM reads of this accumulator are complete (wait::ld above) -> hand it back to the MMA warp
@@ -284,6 +380,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if constexpr (!epi_is_bf16<EPI>()) {
+                if (want_stats) rs.flush(p.stats_out, row0, p.M, (t % n_tiles) * 2 + half, 2 * n_tiles, lane);
+            }
         }
     }
 
@@ -325,14 +424,25 @@ __global__ void gemm_simt_epilogue_kernel(const float* __restrict__ C, const Gem
     const size_t total = (size_t)p.M * n_out;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int row = (int)(i / n_out), col = (int)(i % n_out);
-        float v;
+        float v, ln_a = 1.f, ln_c = 0.f;
+        if (p.ln_stats) {
+            float s1 = 0.f, s2 = 0.f;
+            for (int i = 0; i < p.ln_parts; ++i) {
+                s1 += p.ln_stats[2 * ((size_t)row * p.ln_parts + i)]; s2 += p.ln_stats[2 * ((size_t)row * p.ln_parts + i) + 1];
+            }
+            const float mean = s1 * p.ln_inv_d;
+            const float var = fmaxf(s2 * p.ln_inv_d - mean * mean, 0.f);
+            ln_a = rsqrtf(var + p.ln_eps); ln_c = -ln_a * mean;
+        }
         if constexpr (EPI == VF_EPI_BIAS_GEGLU_BF16) {
             const int cu = (col / 128) * 256 + (col % 128), cg = cu + 128;   // tile-interleaved columns
             float u = C[(size_t)row * p.N + cu], g = C[(size_t)row * p.N + cg];
+            if (p.ln_stats) { u = ln_a * u + ln_c * p.ln_colsum[cu]; g = ln_a * g + ln_c * p.ln_colsum[cg]; }
             if (p.bias) { u += p.bias[cu]; g += p.bias[cg]; }
             v = u * gelu_erf(g);
         } else {
             v = C[(size_t)row * p.N + col];
+            if (p.ln_stats && EPI != VF_EPI_BIAS_RESID_F32 && EPI != VF_EPI_BIAS_F32) v = ln_a * v + ln_c * p.ln_colsum[col];
             if (p.bias) v += p.bias[col];
             if (EPI == VF_EPI_BIAS_RESID_F32 && p.resid) v += p.resid[(size_t)row * p.ldr + col];
             if (EPI == VF_EPI_BIAS_GELU_BF16) v = gelu_erf(v);
@@ -342,6 +452,10 @@ __global__ void gemm_simt_epilogue_kernel(const float* __restrict__ C, const Gem
         } else {
             reinterpret_cast<float*>(p.out)[(size_t)row * p.ldo + col] = v;
             if (p.out2) p.out2[(size_t)row * p.ldo2 + col] = __float2bfloat16_rn(v);
+            if (p.stats_out) {      // debug path: everything lands in part 0 (the buffer was zeroed by the launcher)
+                const int parts = 2 * ((p.N + BN - 1) / BN);
+                atomicAdd(p.stats_out + 2 * (size_t)row * parts, v); atomicAdd(p.stats_out + 2 * (size_t)row * parts + 1, v * v);
+            }
         }
     }
 }
@@ -383,12 +497,31 @@ static int make_tmap_kmajor(CUtensorMap* tm, const void* base, int rows, int col
     return 0;
 }
 
+// fp32 residual [rows, cols] -> plain (unswizzled) map with box {64, 128}, used for L2 prefetch only.
+static int make_tmap_resid(CUtensorMap* tm, const float* base, int rows, int cols, int ld) {
+    PFN_encodeTiled enc = get_encode_fn();
+    VF_REQUIRE(enc, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
+    VF_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld % 4) == 0,
+               "GEMM residual must be 16-byte aligned with a row stride that is a multiple of 4 elements");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)(cols < 64 ? cols : 64), (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VF_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (residual) failed with CUresult %d (rows=%d cols=%d ld=%d)",
+               (int)r, rows, cols, ld);
+    return 0;
+}
+
 static int g_num_sms = 0;
 static bool g_debug_simt = false;
 static bool g_inited = false;
 
 template <int EPI>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const GemmParams& p,
+                     cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
         VF_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -397,7 +530,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
     }
     const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    gemm_tcgen05_kernel<EPI><<<grid, kGemmThreads, kGemmSmem, s>>>(ta, tb, p);
+    gemm_tcgen05_kernel<EPI><<<grid, kGemmThreads, kGemmSmem, s>>>(ta, tb, tr, p);
     VF_LAUNCH_OK("gemm_tcgen05_kernel launch");
     return 0;
 }
@@ -417,7 +550,8 @@ static int launch_simt(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
 }
 
 int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int epi, const float* bias,
-              const float* resid, int ldr, void* out, int ldo, void* out2, int ldo2, cudaStream_t stream) {
+              const float* resid, int ldr, void* out, int ldo, void* out2, int ldo2, const float* ln_stats,
+              int ln_parts, const float* ln_colsum, int ln_dim, float ln_eps, float* stats_out, cudaStream_t stream) {
     if (!g_inited) {
         int dev = 0;
         VF_CUDA_OK(cudaGetDevice(&dev));
@@ -436,7 +570,15 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
     GemmParams p;
     p.M = M; p.N = N; p.K = K; p.bias = bias; p.resid = resid; p.ldr = ldr; p.out = out; p.ldo = ldo;
     p.out2 = reinterpret_cast<__nv_bfloat16*>(out2); p.ldo2 = ldo2;
+    const bool out_bf16 = epi == VF_EPI_BIAS_BF16 || epi == VF_EPI_BIAS_GEGLU_BF16 || epi == VF_EPI_BIAS_GELU_BF16;
+    VF_REQUIRE(!ln_stats || (out_bf16 && ln_colsum && ln_dim > 0 && ln_parts > 0),
+               "gemm: the LayerNorm fold needs a bf16 epilogue, column sums, the normalised width and the partial count");
+    VF_REQUIRE(!stats_out || !out_bf16, "gemm: row statistics are produced by the fp32 epilogues only");
+    p.ln_stats = ln_stats; p.ln_parts = ln_parts; p.ln_colsum = ln_colsum;
+    p.ln_inv_d = ln_dim > 0 ? 1.0f / (float)ln_dim : 0.f; p.ln_eps = ln_eps; p.stats_out = stats_out;
     if (g_debug_simt) {
+        if (stats_out)
+            VF_CUDA_OK(cudaMemsetAsync(stats_out, 0, (size_t)M * 2 * ((N + BN - 1) / BN) * 2 * sizeof(float), stream));
         const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(A);
         const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(W);
         switch (epi) {
@@ -447,15 +589,20 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
             default: return launch_simt<VF_EPI_BIAS_F32>(a, lda, w, ldw, p, stream);
         }
     }
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, tr;
     if (make_tmap_kmajor(&ta, A, M, K, lda, BM)) return -1;
     if (make_tmap_kmajor(&tb, W, N, K, ldw, BN)) return -1;
+    if (epi == VF_EPI_BIAS_RESID_F32 && resid) {
+        if (make_tmap_resid(&tr, resid, M, N, ldr)) return -1;
+    } else {
+        tr = ta;                                                       // never dereferenced
+    }
     switch (epi) {
-        case VF_EPI_BIAS_BF16: return launch_tc<VF_EPI_BIAS_BF16>(ta, tb, p, stream);
-        case VF_EPI_BIAS_GEGLU_BF16: return launch_tc<VF_EPI_BIAS_GEGLU_BF16>(ta, tb, p, stream);
-        case VF_EPI_BIAS_RESID_F32: return launch_tc<VF_EPI_BIAS_RESID_F32>(ta, tb, p, stream);
-        case VF_EPI_BIAS_GELU_BF16: return launch_tc<VF_EPI_BIAS_GELU_BF16>(ta, tb, p, stream);
-        default: return launch_tc<VF_EPI_BIAS_F32>(ta, tb, p, stream);
+        case VF_EPI_BIAS_BF16: return launch_tc<VF_EPI_BIAS_BF16>(ta, tb, tr, p, stream);
+        case VF_EPI_BIAS_GEGLU_BF16: return launch_tc<VF_EPI_BIAS_GEGLU_BF16>(ta, tb, tr, p, stream);
+        case VF_EPI_BIAS_RESID_F32: return launch_tc<VF_EPI_BIAS_RESID_F32>(ta, tb, tr, p, stream);
+        case VF_EPI_BIAS_GELU_BF16: return launch_tc<VF_EPI_BIAS_GELU_BF16>(ta, tb, tr, p, stream);
+        default: return launch_tc<VF_EPI_BIAS_F32>(ta, tb, tr, p, stream);
     }
 }
 

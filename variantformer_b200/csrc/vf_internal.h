@@ -9,7 +9,8 @@
 namespace vf {
 
 int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int epi, const float* bias,
-              const float* resid, int ldr, void* out, int ldo, void* out2, int ldo2, cudaStream_t stream);
+              const float* resid, int ldr, void* out, int ldo, void* out2, int ldo2, const float* ln_stats,
+              int ln_parts, const float* ln_colsum, int ln_dim, float ln_eps, float* stats_out, cudaStream_t stream);
 
 int attention_varlen(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
                      const int* cu_q, const int* cu_k, const int* tile_seq, const int* tile_q0, int n_tiles,
@@ -27,6 +28,7 @@ int attention_tc128_varlen(const void* q, int ldq, const void* k, int ldk, const
 
 int layernorm(const float* x, int ldx, const float* gamma, const float* beta, int M, int d, float eps, void* out,
               int ldo, int act_gelu, cudaStream_t s);
+int rowstats(const float* x, int ldx, int M, int d, float* stats, void* out_bf16, int ldo, cudaStream_t s);
 int window_lengths(const uint8_t* pad_mask, int n_win, int L, int* lens, cudaStream_t s);
 int compact_tokens(const int* tokens, const uint8_t* pad_mask, const int* cu, int n_win, int L, int* out_ids,
                    int* out_pos, cudaStream_t s);

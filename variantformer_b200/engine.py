@@ -14,7 +14,10 @@ Schedule differences from the reference (results identical, oracle/model_fp32.py
     stacked on the M axis of a single cross-attention problem;
   * the CRE x label cross-attention is collapsed to the 9 label classes;
   * only valid (unpadded) tokens are ever materialised.
-Numerics: bf16 GEMM/attention operands, fp32 accumulation, fp32 residual stream and LayerNorm.
+  * every LayerNorm that feeds a Linear is folded into that GEMM: gamma into the weight, beta into the bias, and
+    the per-row mean / rstd applied in the GEMM epilogue from (sum, sum of squares) that the epilogue of the GEMM
+    which produced the row accumulated.  No LayerNorm pass reads the streams.
+Numerics: bf16 GEMM/attention operands, fp32 accumulation, fp32 residual stream and LayerNorm statistics.
 """
 import math
 import os
@@ -62,6 +65,28 @@ class _Linear:
         self.b = b.to(device=device, dtype=torch.float32).contiguous()
 
 
+class _LnLinear:
+    """Linear(LayerNorm(x)) with the norm folded in (vf_gemm.cu header): w = bf16(W * gamma), cs = row sums of that
+    bf16 weight (what the tensor cores will actually multiply the row mean by), b = bias + W beta."""
+    __slots__ = ("w", "b", "cs", "dim", "eps")
+
+    def __init__(self, sd, name, norm, device, geglu=False, eps=1e-5):
+        w, b = sd[name + ".weight"].float(), sd[name + ".bias"].float()
+        g, beta = sd[norm + ".weight"].float(), sd[norm + ".bias"].float()
+        wf = (w * g[None, :]).to(torch.bfloat16)
+        cs = wf.float().sum(1)
+        bf = b + w @ beta
+        if geglu:
+            wf, cs, bf = interleave_geglu(wf), interleave_geglu(cs), interleave_geglu(bf)
+        self.w = wf.to(device).contiguous()
+        self.cs = cs.to(device=device, dtype=torch.float32).contiguous()
+        self.b = bf.to(device=device, dtype=torch.float32).contiguous()
+        self.dim, self.eps = w.shape[1], eps
+
+    def ln(self, stats):
+        return (stats, self.cs, self.dim, self.eps)
+
+
 class _Norm:
     __slots__ = ("g", "b")
 
@@ -106,9 +131,9 @@ class Seq2RegWeights:
         for l in range(self.L):
             p = f"{prefix}transformer_encoder.{l}."
             self.layers.append(dict(
-                qkv=_Linear(sd, p + "MHA.Wqkv", device), out=_Linear(sd, p + "MHA.out_proj", device),
-                n1=_Norm(sd, p + "norm1", device), n2=_Norm(sd, p + "norm2", device),
-                g1=_Linear(sd, p + "linear_geglu_1", device, geglu=True), g2=_Linear(sd, p + "linear_geglu_2", device)))
+                qkv=_LnLinear(sd, p + "MHA.Wqkv", p + "norm1", device), out=_Linear(sd, p + "MHA.out_proj", device),
+                g1=_LnLinear(sd, p + "linear_geglu_1", p + "norm2", device, geglu=True),
+                g2=_Linear(sd, p + "linear_geglu_2", device)))
 
 
 class Seq2GeneWeights:
@@ -127,11 +152,13 @@ class Seq2GeneWeights:
         emb9 = sd["combined_modulator.second_level_context_embedding.weight"].to(device=device, dtype=torch.bfloat16)
 
         def layer(p, with_kv9):
-            L = dict(qkv=_Linear(sd, p + "mixer.MHA.Wqkv", device), out=_Linear(sd, p + "mixer.MHA.out_proj", device),
-                     q=_Linear(sd, p + "crossMHA.MHA.Wq", device), kv=_Linear(sd, p + "crossMHA.MHA.Wkv", device),
+            L = dict(qkv=_LnLinear(sd, p + "mixer.MHA.Wqkv", p + "norm1", device),
+                     out=_Linear(sd, p + "mixer.MHA.out_proj", device),
+                     q=_LnLinear(sd, p + "crossMHA.MHA.Wq", p + "norm2", device),
+                     kv=_Linear(sd, p + "crossMHA.MHA.Wkv", device),
                      out2=_Linear(sd, p + "crossMHA.MHA.out_proj", device),
-                     n1=_Norm(sd, p + "norm1", device), n2=_Norm(sd, p + "norm2", device), n3=_Norm(sd, p + "norm3", device),
-                     g1=_Linear(sd, p + "linear_geglu_1", device, geglu=True), g2=_Linear(sd, p + "linear_geglu_2", device))
+                     g1=_LnLinear(sd, p + "linear_geglu_1", p + "norm3", device, geglu=True),
+                     g2=_Linear(sd, p + "linear_geglu_2", device))
             if with_kv9:
                 # K/V of the 9 label embeddings depend on weights only: computed once here with the same GEMM
                 L["kv9"] = ops.gemm(emb9.contiguous(), L["kv"].w, EPI_BIAS_F32, bias=L["kv"].b)
@@ -168,43 +195,48 @@ class Engine:
         ids, pos = ops.compact_tokens(tokens_i32, mask_u8, cu, n_tok)
         x = ops.embed_tokens(ids, pos, W.emb, W.pe)
         d, H, hd = W.d, W.H, W.hd
-        h = ws.get("r_h", (n_tok, d), torch.bfloat16)
+        xb = ws.get("r_xb", (n_tok, d), torch.bfloat16)                  # bf16 mirror of x / of x1
+        P = ops.stats_parts(d)
+        xs0 = ws.get("r_xs0", (n_tok, 1, 2), torch.float32)              # row (sum, sum of squares) of the embeddings
+        xs = ws.get("r_xs", (n_tok, P, 2), torch.float32)                # ... of x as the FFN GEMM epilogue leaves them
+        s1 = ws.get("r_s1", (n_tok, P, 2), torch.float32)                # ... of x1
         qkv = ws.get("r_qkv", (n_tok, 3 * d), torch.bfloat16)
         a = ws.get("r_a", (n_tok, d), torch.bfloat16)
         x1 = ws.get("r_x1", (n_tok, d), torch.float32)
         f = ws.get("r_f", (n_tok, W.layers[0]["g2"].w.shape[1]), torch.bfloat16)
-        for L in W.layers:
-            ops.layernorm(x, L["n1"].g, L["n1"].b, out=h)
-            ops.gemm(h, L["qkv"].w, EPI_BIAS_BF16, bias=L["qkv"].b, out=qkv)
+        ops.rowstats(x, xs0, xb)
+        for li, L in enumerate(W.layers):
+            ops.gemm(xb, L["qkv"].w, EPI_BIAS_BF16, bias=L["qkv"].b, out=qkv,
+                     ln=L["qkv"].ln(xs0 if li == 0 else xs))                                           # Wqkv(norm1(x))
             attn = ops.attention_tc if tiles.block_m == ops.TC_BLOCK_M else ops.attention
             attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu, cu, tiles, H, hd, W.slopes, out=a)
-            ops.gemm(a, L["out"].w, EPI_BIAS_RESID_F32, bias=L["out"].b, resid=x, out=x1)
-            ops.layernorm(x1, L["n2"].g, L["n2"].b, out=h)
-            ops.gemm(h, L["g1"].w, EPI_BIAS_GEGLU_BF16, bias=L["g1"].b, out=f)
-            ops.gemm(f, L["g2"].w, EPI_BIAS_RESID_F32, bias=L["g2"].b, resid=x, out=x)      # + layer input, in place
+            ops.gemm(a, L["out"].w, EPI_BIAS_RESID_F32, bias=L["out"].b, resid=x, out=x1, out2=xb, stats_out=s1)
+            ops.gemm(xb, L["g1"].w, EPI_BIAS_GEGLU_BF16, bias=L["g1"].b, out=f, ln=L["g1"].ln(s1))      # GeGLU(norm2(x1))
+            ops.gemm(f, L["g2"].w, EPI_BIAS_RESID_F32, bias=L["g2"].b, resid=x, out=x, out2=xb, stats_out=xs)  # + layer input
         return ops.masked_meanpool(x, cu, n_win)
 
     # ---------------------------------------------------------------- one encoder layer of seq2gene
-    def _layer(self, L, x, M, self_attn, cross_attn, tag, mirror=None):
-        """ContextFlashAttentionEncoderLayer on an unpadded fp32 stream x [M, D] (updated in place)."""
+    def _layer(self, L, x, xb, xs, M, self_attn, cross_attn, tag):
+        """ContextFlashAttentionEncoderLayer on an unpadded fp32 stream x [M, D] with its bf16 mirror xb and row
+        statistics xs (all three updated in place)."""
         ws, D = self.ws, self.w.D
-        h = ws.get(tag + "_h", (M, D), torch.bfloat16)
+        hb = ws.get(tag + "_hb", (M, D), torch.bfloat16)                 # bf16 mirror of x1
+        s1 = ws.get(tag + "_s1", (M, ops.stats_parts(D), 2), torch.float32)     # row statistics of x1
+        xs_out = ws.get(tag + "_xs", (M, ops.stats_parts(D), 2), torch.float32)  # ... of the layer output
         qkv = ws.get(tag + "_qkv", (M, 3 * D), torch.bfloat16)
         a = ws.get(tag + "_a", (M, D), torch.bfloat16)
         x1 = ws.get(tag + "_x1", (M, D), torch.float32)
         f = ws.get(tag + "_f", (M, L["g2"].w.shape[1]), torch.bfloat16)
-        ops.layernorm(x, L["n1"].g, L["n1"].b, out=h)
-        ops.gemm(h, L["qkv"].w, EPI_BIAS_BF16, bias=L["qkv"].b, out=qkv)
+        ops.gemm(xb, L["qkv"].w, EPI_BIAS_BF16, bias=L["qkv"].b, out=qkv, ln=L["qkv"].ln(xs))          # Wqkv(norm1(x))
         self_attn(qkv, a)
-        ops.gemm(a, L["out"].w, EPI_BIAS_RESID_F32, bias=L["out"].b, resid=x, out=x1)
-        ops.layernorm(x1, L["n2"].g, L["n2"].b, out=h)
+        ops.gemm(a, L["out"].w, EPI_BIAS_RESID_F32, bias=L["out"].b, resid=x, out=x1, out2=hb, stats_out=s1)
         q = qkv[:, :D]                                                  # reuse the qkv buffer for the cross query
-        ops.gemm(h, L["q"].w, EPI_BIAS_BF16, bias=L["q"].b, out=q)
+        ops.gemm(hb, L["q"].w, EPI_BIAS_BF16, bias=L["q"].b, out=q, ln=L["q"].ln(s1))                  # Wq(norm2(x1))
         cross_attn(q, a)
-        ops.gemm(a, L["out2"].w, EPI_BIAS_RESID_F32, bias=L["out2"].b, resid=x1, out=x1)
-        ops.layernorm(x1, L["n3"].g, L["n3"].b, out=h)
-        ops.gemm(h, L["g1"].w, EPI_BIAS_GEGLU_BF16, bias=L["g1"].b, out=f)
-        ops.gemm(f, L["g2"].w, EPI_BIAS_RESID_F32, bias=L["g2"].b, resid=x, out=x, out2=mirror)
+        ops.gemm(a, L["out2"].w, EPI_BIAS_RESID_F32, bias=L["out2"].b, resid=x1, out=x1, out2=hb, stats_out=s1)
+        ops.gemm(hb, L["g1"].w, EPI_BIAS_GEGLU_BF16, bias=L["g1"].b, out=f, ln=L["g1"].ln(s1))         # GeGLU(norm3(x1))
+        ops.gemm(f, L["g2"].w, EPI_BIAS_RESID_F32, bias=L["g2"].b, resid=x, out=x, out2=xb, stats_out=xs_out)
+        return xs_out
 
     # ---------------------------------------------------------------- slab preparation (host bookkeeping + H2D)
     def prepare(self, cre_tokens, cre_masks, gene_tokens, gene_masks, tissues, ref_labels,
@@ -293,10 +325,14 @@ class Engine:
         cre_bf = ws.get("cre_bf", (nC, D), torch.bfloat16)                           # bf16 mirror = cross-attn context
         if w.cre_map is None:
             raise NotImplementedError("token_dim == emb_dim (no cre_map) is not wired on the B200 path")
+        cxs = ws.get("cxs", (nC, ops.stats_parts(D), 2), torch.float32)
         cx = ops.gemm(cre_pooled, w.cre_map.w, EPI_BIAS_F32, bias=w.cre_map.b, out=ws.get("cx", (nC, D), torch.float32),
-                      out2=cre_bf)
+                      out2=cre_bf, stats_out=cxs)
         gene_emb = ops.gemm(gene_pooled, w.gene_map.w, EPI_BIAS_F32, bias=w.gene_map.b)
         gx, _ = ops.gather_rows(gene_emb, w.registry, s["gene_idx"])
+        gxb = ws.get("gxb", (Mg, D), torch.bfloat16)
+        gxs = ops.rowstats(gx, ws.get("gxs0", (Mg, 1, 2), torch.float32), gxb)
+        st = {"g": gxs, "c": cxs}                                      # current row statistics of each stream
         kv = ws.get("g_kv", (nC, 2 * D), torch.bfloat16)
         cu_gseq, cu_gq, cu_cre = s["cu_gseq"], s["cu_gq"], s["cu_cre"]
 
@@ -317,12 +353,12 @@ class Engine:
 
             def cross(q, out):
                 attn(q, kv[:, :D], kv[:, D:], cu_gq, cu_cre, s["tiles_gcross"], None, out, key_block=128)
-            self._layer(L, gx, Mg, gene_self, cross, "g")
+            st["g"] = self._layer(L, gx, gxb, st["g"], Mg, gene_self, cross, "g")
 
         def cre_layer(L):
             def cross(q, out):
                 ops.label_attention(q, L["kv9"], s["logc"], s["row_seq"], H, hd, out=out)
-            self._layer(L, cx, nC, cre_self, cross, "c", mirror=cre_bf)
+            st["c"] = self._layer(L, cx, cre_bf, st["c"], nC, cre_self, cross, "c")
 
         gene_layer(w.gene_layers[0])
         for i in range(w.NL - 1):

@@ -66,8 +66,11 @@ def _chk_bf16(t):
     assert t.is_cuda and t.dtype == torch.bfloat16 and t.stride(-1) == 1, "expected a row-major CUDA bf16 tensor"
 
 
-def gemm(a, w, epilogue, bias=None, resid=None, out=None, out2=None):
-    """out = epilogue(a[M,K] @ w[N,K]^T).  a, w bf16; bias fp32 [N]; resid fp32 [M,N]."""
+def gemm(a, w, epilogue, bias=None, resid=None, out=None, out2=None, ln=None, stats_out=None):
+    """out = epilogue(a[M,K] @ w[N,K]^T).  a, w bf16; bias fp32 [N]; resid fp32 [M,N].
+    ln = (stats fp32 [M,P,2], colsum fp32 [N], width, eps): LayerNorm of the rows `a` mirrors, folded into the epilogue
+    (w, bias must be the gamma/beta-folded ones); stats_out fp32 [M, stats_parts(N), 2]: partial row (sum, sum of
+    squares) of an fp32 output."""
     _chk_bf16(a); _chk_bf16(w)
     M, K = a.shape
     N = w.shape[0]
@@ -82,11 +85,43 @@ def gemm(a, w, epilogue, bias=None, resid=None, out=None, out2=None):
         assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
     if out2 is not None:
         assert out2.dtype == torch.bfloat16 and out2.shape == (M, N) and out2.stride(1) == 1
+    ln_stats = ln_colsum = None
+    ln_dim, ln_eps, ln_parts = 0, 0.0, 0
+    if ln is not None:
+        ln_stats, ln_colsum, ln_dim, ln_eps = ln
+        assert ln_stats.dtype == torch.float32 and ln_stats.dim() == 3 and ln_stats.shape[0] == M and \
+            ln_stats.shape[2] == 2 and ln_stats.is_contiguous()
+        ln_parts = ln_stats.shape[1]
+        assert ln_colsum.dtype == torch.float32 and ln_colsum.numel() == N and ln_colsum.is_contiguous()
+    if stats_out is not None:
+        assert stats_out.dtype == torch.float32 and stats_out.shape == (M, stats_parts(N), 2) and stats_out.is_contiguous()
     with _timed("gemm", 2.0 * M * N * K):
-        check(_lib.lib().vf_gemm_bf16(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, epilogue, ptr(bias),
-                                      ptr(resid), resid.stride(0) if resid is not None else 0, ptr(out), out.stride(0),
-                                      ptr(out2), out2.stride(0) if out2 is not None else 0, stream()))
+        check(_lib.lib().vf_gemm_bf16_ln(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, epilogue, ptr(bias),
+                                         ptr(resid), resid.stride(0) if resid is not None else 0, ptr(out),
+                                         out.stride(0), ptr(out2), out2.stride(0) if out2 is not None else 0,
+                                         ptr(ln_stats), ln_parts, ptr(ln_colsum), int(ln_dim), float(ln_eps),
+                                         ptr(stats_out), stream()))
     return out
+
+
+def stats_parts(n):
+    """Partials per row that an fp32 GEMM epilogue with N = n output columns writes into `stats_out`."""
+    return 2 * ((n + 255) // 256)
+
+
+def rowstats(x, stats=None, out_bf16=None):
+    """Per-row (sum, sum of squares) of fp32 x [M,d] -> stats [M,1,2]; optional bf16 mirror of x."""
+    assert x.dtype == torch.float32 and x.stride(1) == 1
+    M, d = x.shape
+    if stats is None:
+        stats = torch.empty((M, 1, 2), dtype=torch.float32, device=x.device)
+    assert stats.shape == (M, 1, 2) and stats.is_contiguous()
+    if out_bf16 is not None:
+        assert out_bf16.dtype == torch.bfloat16 and out_bf16.shape == (M, d) and out_bf16.stride(1) == 1
+    with _timed("misc"):
+        check(_lib.lib().vf_rowstats(ptr(x), x.stride(0), M, d, ptr(stats), ptr(out_bf16),
+                                     out_bf16.stride(0) if out_bf16 is not None else 0, stream()))
+    return stats
 
 
 class TileMap:
