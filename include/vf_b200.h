@@ -104,6 +104,19 @@ int vf_attention_tc_varlen(const void* q, int ldq, const void* k, int ldk, const
                            const float* slopes, int key_block, int short_items, void* stream);
 
 /*
+ * Same operation, two co-resident CTAs per SM (16 softmax warps per SM): the kernel the engine uses for every
+ * attention of the hot path.  A work item has two SLOTS, each a query tile of up to 128 rows of one sequence.
+ * slots: int32 [n_items][2][8], 16-byte aligned, per slot {first query row (absolute row of q/o), valid rows (0 = empty
+ * slot), first key row (absolute row of k/v), number of keys, i + Sk - Sq of the tile's first row (ALiBi position),
+ * 0, 0, 0}.  Two slots with the same key range share one K/V stream; slots of different sequences stream their own
+ * keys, which keeps both softmax warpgroups busy on sequences of <= 128 rows.  head_dim in {48, 64}.
+ * Same reference call sites as above.
+ */
+int vf_attention_mc_varlen(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
+                           int64_t rows_q, int64_t rows_k, const int32_t* slots, int n_items, int heads,
+                           int head_dim, const float* slopes, void* stream);
+
+/*
  * CRE x reference-label cross-attention collapsed to the 9 cCRE classes (exact identity):
  * q bf16 [n_rows, H*HD]; kv9 fp32 [9, 2*H*HD] = Wkv·Emb9 + b ((two,h,d) order); logc fp32 [n_seq,9] =
  * log(#CREs of the class in the row's gene) (-inf when absent); row_seq int32 [n_rows].

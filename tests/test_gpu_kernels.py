@@ -227,6 +227,51 @@ def test_tc_cross_attention_stacked_queries(H, hd, key_block):
     assert torch.allclose(got.float(), want, atol=2e-2, rtol=2e-2), _describe_mismatch(got.float(), want, 2e-2)
 
 
+@pytest.mark.parametrize("H,hd,alibi,lens", [
+    (4, 48, True, [201] * 5), (4, 48, False, [1, 97, 128, 129, 64, 65, 7, 200, 33]), (32, 48, True, [201, 640, 33, 1024]),
+    (8, 64, False, [97, 130, 200, 12, 128, 77, 200]), (2, 64, True, [300, 5, 257]), (4, 48, True, [1000]),
+])
+def test_mc_self_attention(H, hd, alibi, lens):
+    n, d = sum(lens), H * hd
+    g = torch.Generator(device="cpu").manual_seed(H * hd + len(lens))
+    qkv = torch.randn(n, 3 * d, generator=g).to(DEV).bfloat16()
+    slopes = torch.tensor([2 ** (-8 * (h + 1) / H) for h in range(H)], device=DEV) if alibi else None
+    slots = ops.SlotMap(lens, DEV)
+    got = ops.attention_mc(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], slots, H, hd, slopes)
+    want = _ref_attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], lens, lens, H, hd, slopes)
+    torch.cuda.synchronize()
+    assert torch.allclose(got.float(), want, atol=2e-2, rtol=2e-2), _describe_mismatch(got.float(), want, 2e-2)
+
+
+@pytest.mark.parametrize("H,hd", [(4, 48), (32, 48), (4, 64)])
+def test_mc_cross_attention_stacked_queries(H, hd):
+    lens_q, lens_k = [603, 201, 1500, 128], [300, 64, 1024, 1]
+    d = H * hd
+    g = torch.Generator(device="cpu").manual_seed(17 + H)
+    q = torch.randn(sum(lens_q), d, generator=g).to(DEV).bfloat16()
+    kv = torch.randn(sum(lens_k), 2 * d, generator=g).to(DEV).bfloat16()
+    slots = ops.SlotMap(lens_q, DEV, k_lens=lens_k)
+    got = ops.attention_mc(q, kv[:, :d], kv[:, d:], slots, H, hd, None)
+    want = _ref_attention(q, kv[:, :d], kv[:, d:], lens_q, lens_k, H, hd, None)
+    torch.cuda.synchronize()
+    assert torch.allclose(got.float(), want, atol=2e-2, rtol=2e-2), _describe_mismatch(got.float(), want, 2e-2)
+
+
+def test_mc_large_scores_raise_the_lazy_maximum():
+    """Scores that grow along the key axis force the reference maximum to be raised (O rescaled in TMEM) many times."""
+    H, hd, lens = 4, 48, [700, 130]
+    n, d = sum(lens), H * hd
+    g = torch.Generator(device="cpu").manual_seed(3)
+    q = (torch.randn(n, d, generator=g) * 3).to(DEV).bfloat16()
+    k = (torch.randn(n, d, generator=g) * 3 * torch.linspace(0.2, 3.0, n)[:, None]).to(DEV).bfloat16()
+    v = torch.randn(n, d, generator=g).to(DEV).bfloat16()
+    slots = ops.SlotMap(lens, DEV)
+    got = ops.attention_mc(q, k, v, slots, H, hd, None)
+    want = _ref_attention(q, k, v, lens, lens, H, hd, None)
+    torch.cuda.synchronize()
+    assert torch.allclose(got.float(), want, atol=3e-2, rtol=3e-2), _describe_mismatch(got.float(), want, 3e-2)
+
+
 def test_label_attention_equals_full_attention_over_labels():
     H, hd, C = 4, 48, [37, 120]
     D = H * hd

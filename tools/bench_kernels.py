@@ -95,6 +95,13 @@ def main():
                 print(json.dumps(res[-1])); sys.stdout.flush()
         except Exception as e:
             print("attention_tc failed:", e)
+        try:
+            slots = ops.SlotMap(lens_q, DEV, k_lens=lens_k)
+            ms = timeit(lambda: ops.attention_mc(q, k, v, slots, H, hd, slopes, out=o))
+            res.append(dict(kernel="attention_mc", name=name, ms=ms, tflops=fl / ms / 1e9))
+            print(json.dumps(res[-1])); sys.stdout.flush()
+        except Exception as e:
+            print("attention_mc failed:", e)
     # layernorm bandwidth
     x = torch.randn(101304, 1536, device=DEV); g = torch.ones(1536, device=DEV); b = torch.zeros(1536, device=DEV)
     o = torch.empty(101304, 1536, device=DEV, dtype=torch.bfloat16)

@@ -49,8 +49,12 @@ def attn(name, kb):
     slopes = torch.tensor([2 ** (-8 * (h + 1) / H) for h in range(H)], device=DEV) if alibi else None
     cq, ck = ops.cu_seqlens(lens_q, DEV), ops.cu_seqlens(lk, DEV)
     items = ops.TileMap(lens_q, ops.TC_BLOCK_M, DEV, k_lens=lens_k)
+    slots = ops.SlotMap(lens_q, DEV, k_lens=lens_k)
     for _ in range(3):
-        ops.attention_tc(q, k, v, cq, ck, items, H, hd, slopes, out=o, key_block=kb)
+        if kb == 0:
+            ops.attention_mc(q, k, v, slots, H, hd, slopes, out=o)
+        else:
+            ops.attention_tc(q, k, v, cq, ck, items, H, hd, slopes, out=o, key_block=kb)
     torch.cuda.synchronize()
 
 

@@ -27,6 +27,8 @@ SIGNATURES = {
                              _vp, _vp], _i32),
     "vf_attention_tc_varlen": ([_vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _i32,
                                 _i32, _vp, _i32, _i32, _vp], _i32),
+    "vf_attention_mc_varlen": ([_vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _i64, _i64, _vp, _i32, _i32, _i32, _vp,
+                                _vp], _i32),
     "vf_label_attention": ([_vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp], _i32),
     "vf_layernorm": ([_vp, _i32, _vp, _vp, _i32, _i32, C.c_float, _vp, _i32, _i32, _vp], _i32),
     "vf_window_lengths": ([_vp, _i32, _i32, _vp, _vp], _i32),

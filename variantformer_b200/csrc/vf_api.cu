@@ -69,6 +69,12 @@ int vf_attention_tc_varlen(const void* q, int ldq, const void* k, int ldk, const
     return attention_tc_varlen(q, ldq, k, ldk, v, ldv, o, ldo, (long)rows_q, (long)rows_k, cu_q, cu_k, item_seq,
                                item_q0, n_items, heads, head_dim, slopes, short_items, ST(stream));
 }
+int vf_attention_mc_varlen(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
+                           int64_t rows_q, int64_t rows_k, const int32_t* slots, int n_items, int heads,
+                           int head_dim, const float* slopes, void* stream) {
+    return attention_mc_varlen(q, ldq, k, ldk, v, ldv, o, ldo, (long)rows_q, (long)rows_k, slots, n_items, heads,
+                               head_dim, slopes, ST(stream));
+}
 int vf_label_attention(const void* q, int ldq, const float* kv9, const float* logc, const int32_t* row_seq, int n_rows,
                        int heads, int head_dim, void* out, int ldo, void* stream) {
     return label_attention(q, ldq, kv9, logc, row_seq, n_rows, heads, head_dim, out, ldo, ST(stream));

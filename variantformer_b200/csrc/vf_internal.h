@@ -26,6 +26,10 @@ int attention_tc128_varlen(const void* q, int ldq, const void* k, int ldk, const
                            const int* item_q0, int n_items, int heads, int head_dim, const float* slopes,
                            cudaStream_t stream);
 
+int attention_mc_varlen(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
+                        long rows_q, long rows_k, const int* slots, int n_items, int heads, int head_dim,
+                        const float* slopes, cudaStream_t stream);
+
 int layernorm(const float* x, int ldx, const float* gamma, const float* beta, int M, int d, float eps, void* out,
               int ldo, int act_gelu, cudaStream_t s);
 int rowstats(const float* x, int ldx, int M, int d, float* stats, void* out_bf16, int ldo, cudaStream_t s);

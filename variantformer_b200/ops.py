@@ -180,6 +180,52 @@ def attention_tc(q, k, v, cu_q, cu_k, items: TileMap, heads, head_dim, slopes=No
     return out
 
 
+class SlotMap:
+    """Work items of vf_attention_mc_varlen for a batch of variable-length sequences (host-built, device-resident).
+
+    Every sequence is cut into 128-row query tiles; consecutive tiles of a sequence are paired into one item (they
+    share the sequence's K/V stream), and the odd tiles left over (all of them when sequences have <= 128 rows) are
+    paired with each other, each slot then streaming its own keys.  Record layout: include/vf_b200.h."""
+
+    def __init__(self, q_lens, device, k_lens=None):
+        q_lens = np.asarray(q_lens, np.int64)
+        k_lens = q_lens if k_lens is None else np.asarray(k_lens, np.int64)
+        self.qk_pairs = float((q_lens * k_lens).sum())
+        n = len(q_lens)
+        cu_q = np.concatenate([[0], np.cumsum(q_lens)]); cu_k = np.concatenate([[0], np.cumsum(k_lens)])
+        nt = (q_lens + 127) // 128
+        seq = np.repeat(np.arange(n), nt)
+        t = np.arange(int(nt.sum())) - np.repeat(np.cumsum(nt) - nt, nt)
+        rec = np.zeros((len(seq), 8), np.int32)
+        rec[:, 0] = cu_q[seq] + 128 * t
+        rec[:, 1] = np.minimum(128, q_lens[seq] - 128 * t)
+        rec[:, 2] = cu_k[seq]
+        rec[:, 3] = k_lens[seq]
+        rec[:, 4] = 128 * t + k_lens[seq] - q_lens[seq]
+        rec = rec[rec[:, 3] > 0]                                          # a sequence without keys has no output
+        odd = (t == nt[seq] - 1) & (nt[seq] % 2 == 1)
+        odd = odd[(k_lens[seq] > 0)]
+        pairs, singles = rec[~odd], rec[odd]
+        if len(singles) % 2:
+            singles = np.concatenate([singles, np.zeros((1, 8), np.int32)])
+        items = np.concatenate([pairs.reshape(-1, 2, 8), singles.reshape(-1, 2, 8)])
+        self.n_items = int(items.shape[0])
+        self.table = torch.from_numpy(np.ascontiguousarray(items)).to(device, non_blocking=True)
+
+
+def attention_mc(q, k, v, slots: SlotMap, heads, head_dim, slopes=None, out=None):
+    """Varlen attention on the two-CTAs-per-SM tcgen05 kernel (vf_attention_mc_varlen)."""
+    for t in (q, k, v):
+        assert t.is_cuda and t.dtype == torch.bfloat16 and t.stride(1) == 1
+    if out is None:
+        out = torch.empty((q.shape[0], heads * head_dim), dtype=torch.bfloat16, device=q.device)
+    with _timed("attention", 4.0 * slots.qk_pairs * heads * head_dim):
+        check(_lib.lib().vf_attention_mc_varlen(ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0),
+                                                ptr(out), out.stride(0), q.shape[0], k.shape[0], ptr(slots.table),
+                                                slots.n_items, heads, head_dim, ptr(slopes), stream()))
+    return out
+
+
 def label_attention(q, kv9, logc, row_seq, heads, head_dim, out=None):
     assert q.dtype == torch.bfloat16 and kv9.dtype == torch.float32 and logc.dtype == torch.float32
     assert row_seq.dtype == torch.int32 and kv9.is_contiguous() and logc.is_contiguous()
