@@ -257,6 +257,25 @@ def test_mc_cross_attention_stacked_queries(H, hd):
     assert torch.allclose(got.float(), want, atol=2e-2, rtol=2e-2), _describe_mismatch(got.float(), want, 2e-2)
 
 
+@pytest.mark.parametrize("H,hd,alibi,n_seq,lo,hi", [(8, 64, False, 1200, 60, 128), (8, 64, True, 700, 1, 200),
+                                                    (32, 48, True, 60, 150, 420), (32, 48, False, 40, 1, 700)])
+def test_mc_many_items_per_cta(H, hd, alibi, n_seq, lo, hi):
+    """More work items than resident CTAs: every CTA walks a long stream of items (ring / phase bookkeeping across
+    items, shared and split K/V streams mixed)."""
+    rng = np.random.default_rng(n_seq + hi)
+    lens = rng.integers(lo, hi + 1, n_seq).tolist()
+    n, d = sum(lens), H * hd
+    g = torch.Generator(device="cpu").manual_seed(n_seq)
+    qkv = torch.randn(n, 3 * d, generator=g).to(DEV).bfloat16()
+    slopes = torch.tensor([2 ** (-8 * (h + 1) / H) for h in range(H)], device=DEV) if alibi else None
+    slots = ops.SlotMap(lens, DEV)
+    assert slots.n_items * H > 2 * 148 * 3
+    got = ops.attention_mc(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], slots, H, hd, slopes)
+    torch.cuda.synchronize()
+    want = _ref_attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], lens, lens, H, hd, slopes)
+    assert torch.allclose(got.float(), want, atol=2e-2, rtol=2e-2), _describe_mismatch(got.float(), want, 2e-2)
+
+
 def test_mc_large_scores_raise_the_lazy_maximum():
     """Scores that grow along the key axis force the reference maximum to be raised (O rescaled in TMEM) many times."""
     H, hd, lens = 4, 48, [700, 130]

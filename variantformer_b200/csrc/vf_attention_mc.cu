@@ -12,14 +12,14 @@
 // One CTA = 384 threads = 3 warpgroups:
 //   warp 0      TMA producer: Q tiles of the item's (up to) two SLOTS, K / V blocks of 64 keys through 3- / 2-stage
 //               rings; all tiles are [rows, 64 cols] bf16, SWIZZLE_128B (hd=48 over-fetches 16 columns never read)
-//   warps 1-3   idle: they exist so that warpgroup 0 can hand its registers to the softmax warps (setmaxnreg)
+//   warps 1, 2  tcgen05.mma issuers, ONE PER SLOT (neither slot waits behind the other's barriers):
+//               S_s = Q_s K^T (M128 x N64 x K=hd) into slot s's TMEM score buffer, issued as soon as the previous
+//               scores are in registers; O_s += P_s V (M128 x N=hd x K64), P from shared memory (K-major), V as an
+//               MN-major operand
+//   warp 3      idle (warpgroup 0 hands its registers to the softmax warps with setmaxnreg)
 //   warps 4-11  two softmax warpgroups, warpgroup s owns slot s: ONE THREAD PER QUERY ROW, the 64 scores of a row
-//               come straight from TMEM (tcgen05.ld 32x32b) into registers.  There is NO separate MMA warp: one
-//               thread of each warpgroup issues its slot's tcgen05.mma the moment the warpgroup (named barrier) has
-//               the previous scores in registers / has written P, so no hand-shake with another warp sits on the
-//               critical path:  S_s = Q_s K^T (M128 x N64 x K=hd) into slot s's TMEM score buffer;
-//               O_s += P_s V (M128 x N=hd x K64), P from shared memory (K-major), V as an MN-major operand.
-//               The first Q K^T of the next item is issued during the last tile of the current one.
+//               come straight from TMEM (tcgen05.ld 32x32b) into registers; the 8 warps never synchronise with each
+//               other, only with their slot's issuer through mbarriers
 // A work item is (head, two slots); a slot is a 128-row query tile of some sequence, described by a host-built record
 // {first query row, valid rows, first key row, keys, ALiBi position of row 0} (absolute row numbers: no cu_seqlens
 // lookups on the device).  Two slots with the same key range share one K/V stream (long sequences: every K/V block
@@ -48,7 +48,7 @@ constexpr uint32_t kKvBytes = kKB * 64 * 2;                   // one [64 keys x 
 constexpr int kThreads = 384;
 constexpr int kFirstSoftmaxWarp = 4;
 constexpr uint32_t kTmemCols = 256;
-constexpr size_t kSmem = 1024 + 2 * kQBytes + (size_t)(kKStages + kVStages) * kKvBytes + 2 * kQBytes + 256;
+constexpr size_t kSmem = 1024 + 2 * kQBytes + (size_t)(kKStages + kVStages) * kKvBytes + 2 * kQBytes + 384;
 constexpr float kLazyThreshold = 8.0f;      // log2 units: P stays below 2^8 between reference-max updates
 
 // one slot of a work item (32 bytes): nrows == 0 marks an empty slot
@@ -114,7 +114,7 @@ __device__ __forceinline__ void exponents(uint32_t (&r)[64], float scale, float 
 template <int HD, bool ALIBI>
 __device__ __forceinline__ void softmax_tile(uint32_t (&r)[64], uint32_t o_addr, bool first, uint64_t* p_empty_bar,
                                              uint32_t p_empty_parity, float scale, float slope, float qpos, int key0,
-                                             int Sk, float& m_ref, float& l, uint8_t* dst, int row, int lane) {
+                                             int Sk, float& m_ref, float& l, uint32_t p_row, int row, int lane) {
     const float base = first ? 0.f : m_ref;                  // exponents are first taken against `base`
     const float d0 = qpos - (float)key0;                     // query position minus the block's first key
     const int nvalid = Sk - key0;
@@ -144,7 +144,6 @@ __device__ __forceinline__ void softmax_tile(uint32_t (&r)[64], uint32_t o_addr,
         for (int e = 0; e < 64; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) - delta);
     }
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    uint8_t* prow = dst + row * 128;
 #pragma unroll
     for (int q8 = 0; q8 < 8; ++q8) {                          // 8 scores -> one 16-byte chunk of the P row
         uint32_t pk[4];
@@ -155,7 +154,8 @@ __device__ __forceinline__ void softmax_tile(uint32_t (&r)[64], uint32_t o_addr,
             acc[h] += p0 + p1;
             pk[h] = pack_bf16x2(p0, p1);
         }
-        *reinterpret_cast<uint4*>(prow + ((q8 ^ (row & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + ((q8 ^ (row & 7)) * 16)), "r"(pk[0]),
+                     "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
     }
     l += (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
@@ -179,11 +179,15 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint8_t* sm_p = sm_v + kVStages * kKvBytes;                   // 2 slots x 16 KB
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm_p + 2 * kQBytes);
     uint64_t* q_full = bars + 0;   uint64_t* q_empty = bars + 2;                   // [slot]
-    uint64_t* s_full = bars + 4;   uint64_t* p_empty = bars + 6;                   // [slot]
-    uint64_t* o_full = bars + 8;                                                   // [slot]
-    uint64_t* k_full = bars + 10;  uint64_t* k_empty = k_full + kKStages;
-    uint64_t* v_full = k_empty + kKStages;   uint64_t* v_empty = v_full + kVStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + kVStages);
+    uint64_t* s_full = bars + 4;   uint64_t* s_empty = bars + 6;                   // [slot]
+    uint64_t* p_full = bars + 8;   uint64_t* p_empty = bars + 10;                  // [slot]
+    uint64_t* o_full = bars + 12;  uint64_t* o_empty = bars + 14;                  // [slot]
+    // a K / V stage has TWO release barriers, one per slot: both slots arrive (tcgen05.commit) when they share the
+    // block, its only user arrives on both otherwise.  (Two commits on ONE barrier with count 2 are not reliable: when
+    // both are pending on the same MMAs they can be merged into a single arrival.)
+    uint64_t* k_full = bars + 16;  uint64_t* k_empty = k_full + kKStages;          // k_empty[2 * stage + slot]
+    uint64_t* v_full = k_empty + 2 * kKStages;   uint64_t* v_empty = v_full + kVStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + 2 * kVStages);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_work = p.n_items * p.heads;
@@ -191,13 +195,13 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&p_empty[i], 1);
-            mbar_init(&o_full[i], 1);
+            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
+            mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);      // 4 softmax warps per slot
+            mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1);
+            mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4);
         }
-        // a K / V stage is released by TWO tcgen05.commit arrivals: one per slot when the slots share the block, both
-        // from its only user otherwise
-        for (int i = 0; i < kKStages; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 2); }
-        for (int i = 0; i < kVStages; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 2); }
+        for (int i = 0; i < kKStages; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[2 * i], 1); mbar_init(&k_empty[2 * i + 1], 1); }
+        for (int i = 0; i < kVStages; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[2 * i], 1); mbar_init(&v_empty[2 * i + 1], 1); }
         fence_barrier_init();
     }
     if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
@@ -231,20 +235,22 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     mbar_arrive_expect_tx(&q_full[s], kQBytes);
                     tma_load_2d(sm_q + s * kQBytes, &tmQ, &q_full[s], col, qrow[s]);
                 }
-                // K / V blocks in exactly the order the warpgroups consume them: K of block j+1 before V of block j
+                // K / V blocks in exactly the order the MMA warps consume them: K of block j+1 before V of block j
                 const int nkmax = max(nk[0], nk[1]);
                 const uint32_t base = ring;
                 auto load_k = [&](int j, int s) {
                     const uint32_t idx = base + ring_offset(j, s, same, nk[0], nk[1]);
                     const uint32_t st = idx % kKStages;
-                    mbar_wait(&k_empty[st], ((idx / kKStages) & 1) ^ 1);
+                    mbar_wait(&k_empty[2 * st], ((idx / kKStages) & 1) ^ 1);
+                    mbar_wait(&k_empty[2 * st + 1], ((idx / kKStages) & 1) ^ 1);
                     mbar_arrive_expect_tx(&k_full[st], kKvBytes);
                     tma_load_2d(sm_k + st * kKvBytes, &tmK, &k_full[st], col, krow[s] + j * kKB);
                 };
                 auto load_v = [&](int j, int s) {
                     const uint32_t idx = base + ring_offset(j, s, same, nk[0], nk[1]);
                     const uint32_t st = idx % kVStages;
-                    mbar_wait(&v_empty[st], ((idx / kVStages) & 1) ^ 1);
+                    mbar_wait(&v_empty[2 * st], ((idx / kVStages) & 1) ^ 1);
+                    mbar_wait(&v_empty[2 * st + 1], ((idx / kVStages) & 1) ^ 1);
                     mbar_arrive_expect_tx(&v_full[st], kKvBytes);
                     tma_load_2d(sm_v + st * kKvBytes, &tmV, &v_full[st], col, krow[s] + j * kKB);
                 };
@@ -258,89 +264,118 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 }
                 ring += same ? nk[0] : nk[0] + nk[1];
             }
+        } else if (warp == 1 || warp == 2) {
+            // ============================ MMA issuer of slot s = warp - 1 ============================
+            // One issuer per slot: neither slot ever waits behind the other's barriers.  S(j+1) = Q K^T is issued as
+            // soon as the four softmax warps have S(j) in registers, i.e. BEFORE waiting for P(j); the first Q K^T of
+            // the next item follows the last P V of the current one.
+            const int s = warp - 1;
+            constexpr uint32_t idesc_qk = umma_idesc_bf16(128, kKB);                         // A, B K-major
+            constexpr uint32_t idesc_pv = umma_idesc_bf16(128, HD) | (1u << 16);            // B (= V) MN-major
+            const uint32_t s_tmem = tmem_base + s * kKB, o_tmem = tmem_base + 128 + s * 64;
+            const uint64_t q_desc = umma_desc_kmajor_sw128(smem_u32(sm_q + s * kQBytes));
+            const uint64_t p_desc = umma_desc_kmajor_sw128(smem_u32(sm_p + s * kQBytes));
+            struct It { int nk0, nk1, my_nk; uint32_t base, tile0; bool same; };
+            uint32_t ring = 0, n_tiles = 0, n_q = 0, n_done = 0;      // ring position, score tiles / items started / finished
+            int w = blockIdx.x;
+            // next work item in which this slot is occupied (the ring position advances over every item)
+            auto next_valid = [&](It& it) -> bool {
+                for (; w < n_work; w += gridDim.x) {
+                    const int item = w % p.n_items;
+                    const int4 r0 = __ldg(recs + 4 * item), r1 = __ldg(recs + 4 * item + 2);
+                    it.nk0 = r0.y > 0 ? (r0.w + kKB - 1) / kKB : 0;
+                    it.nk1 = r1.y > 0 ? (r1.w + kKB - 1) / kKB : 0;
+                    it.same = it.nk0 > 0 && it.nk1 > 0 && r0.z == r1.z;
+                    it.base = ring;
+                    ring += it.same ? it.nk0 : it.nk0 + it.nk1;
+                    it.my_nk = s == 0 ? it.nk0 : it.nk1;
+                    if (it.my_nk > 0) { w += gridDim.x; return true; }
+                }
+                return false;
+            };
+            auto ready = [&](uint64_t* bar, uint32_t parity, bool blocking) -> bool {
+                if (blocking) { mbar_wait(bar, parity); return true; }
+                return mbar_try_wait(bar, parity);
+            };
+            // S(j) = Q K(j)^T of item `it`; non-blocking mode gives up (nothing issued) if an input has not landed yet
+            auto issue_qk = [&](It& it, int j, bool blocking) -> bool {
+                const uint32_t idx = it.base + ring_offset(j, s, it.same, it.nk0, it.nk1);
+                const uint32_t st = idx % kKStages;
+                if (j == 0 && !ready(&q_full[s], n_q & 1, blocking)) return false;
+                if (!ready(&k_full[st], (idx / kKStages) & 1, blocking)) return false;
+                if (!ready(&s_empty[s], (n_tiles & 1) ^ 1, blocking)) return false;      // previous scores are in registers
+                if (j == 0) { ++n_q; it.tile0 = n_tiles; }
+                ++n_tiles;
+                tc_fence_after();
+                if (elect_one()) {                            // the whole warp keeps the (uniform) books, one lane issues
+                    const uint64_t db = umma_desc_kmajor_sw128(smem_u32(sm_k + st * kKvBytes));
+#pragma unroll
+                    for (int k = 0; k < HD / 16; ++k) umma_bf16(s_tmem, q_desc + 2 * k, db + 2 * k, idesc_qk, k != 0);
+                    umma_commit(&s_full[s]);
+                    umma_commit(&k_empty[2 * st + s]);
+                    if (!it.same) umma_commit(&k_empty[2 * st + (s ^ 1)]);    // sole user: the other slot's release too
+                    if (j + 1 == it.my_nk) umma_commit(&q_empty[s]);          // last Q K^T of the item: Q slot may be refilled
+                }
+                __syncwarp();
+                return true;
+            };
+            It cur, nxt;
+            bool have = next_valid(cur);
+            if (have) issue_qk(cur, 0, true);
+            while (have) {
+                const bool have_next = next_valid(nxt);
+                bool next_started = false;
+                for (int j = 0; j < cur.my_nk; ++j) {
+                    // S(j+1) is issued as soon as the four softmax warps have S(j) in registers, i.e. BEFORE waiting for
+                    // P(j).  At the last block the first score tile of the NEXT item goes out instead — but only if its
+                    // inputs have already landed: blocking on them here could deadlock (the producer may need the V
+                    // block this slot is about to release before it can reach the next item's loads).
+                    if (j + 1 < cur.my_nk) issue_qk(cur, j + 1, true);
+                    else if (have_next) next_started = issue_qk(nxt, 0, false);
+                    // ---- O += P(j) V(j) ----
+                    const uint32_t idx = cur.base + ring_offset(j, s, cur.same, cur.nk0, cur.nk1);
+                    const uint32_t st = idx % kVStages;
+                    if (j == 0) mbar_wait(&o_empty[s], (n_done & 1) ^ 1);   // previous item's O has been read out
+                    mbar_wait(&v_full[st], (idx / kVStages) & 1);
+                    mbar_wait(&p_full[s], (cur.tile0 + j) & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t vb = smem_u32(sm_v + st * kKvBytes);
+#pragma unroll
+                        for (int kk = 0; kk < kKB / 16; ++kk)
+                            umma_bf16(o_tmem, p_desc + 2 * kk, umma_desc_kmajor_sw128(vb + kk * 2048), idesc_pv, (j | kk) != 0);
+                        umma_commit(&p_empty[s]);
+                        umma_commit(&v_empty[2 * st + s]);
+                        if (!cur.same) umma_commit(&v_empty[2 * st + (s ^ 1)]);
+                        if (j + 1 == cur.my_nk) umma_commit(&o_full[s]);
+                    }
+                    __syncwarp();
+                }
+                ++n_done;
+                if (have_next && !next_started) issue_qk(nxt, 0, true);   // everything of `cur` is consumed: blocking is safe
+                cur = nxt;
+                have = have_next;
+            }
         }
     } else {
-        // ============================ softmax warpgroups (they also issue their slot's MMAs) ============================
+        // ============================ softmax warps (fully independent of each other) ============================
         reg_alloc<104>();
         const int s = (warp - kFirstSoftmaxWarp) >> 2;        // slot owned by this warpgroup
         const int quad = warp & 3;                            // TMEM lane quadrant of this warp
         const int row = quad * 32 + lane;                     // row inside the 128-row query tile
-        const bool issuer = (threadIdx.x & 127) == 0;         // the one thread of the warpgroup that issues tcgen05.mma
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
         const uint32_t s_addr = t_lane + s * kKB, o_addr = t_lane + 128 + s * 64;
-        uint8_t* my_p = sm_p + s * kQBytes;
-        constexpr uint32_t idesc_qk = umma_idesc_bf16(128, kKB);                         // A, B K-major
-        constexpr uint32_t idesc_pv = umma_idesc_bf16(128, HD) | (1u << 16);            // B (= V) MN-major
-        uint32_t ring = 0;                                    // K / V blocks the CTA has consumed before this item
-        uint32_t n_tiles = 0, n_items_mine = 0;               // score tiles / items this slot has processed so far
-
-        auto wg_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + s) : "memory"); };
-        // S = Q K^T for key block j of an item (issuer thread only)
-        auto issue_qk = [&](uint32_t base, int j, bool same, int nk0, int nk1, bool first_of_item, bool last_of_item) {
-            const uint32_t idx = base + ring_offset(j, s, same, nk0, nk1);
-            const uint32_t st = idx % kKStages;
-            if (first_of_item) mbar_wait(&q_full[s], n_items_mine & 1);
-            mbar_wait(&k_full[st], (idx / kKStages) & 1);
-            tc_fence_after();
-            const uint64_t da = umma_desc_kmajor_sw128(smem_u32(sm_q + s * kQBytes));
-            const uint64_t db = umma_desc_kmajor_sw128(smem_u32(sm_k + st * kKvBytes));
-#pragma unroll
-            for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + s * kKB, da + 2 * k, db + 2 * k, idesc_qk, k != 0);
-            umma_commit(&s_full[s]);
-            umma_commit(&k_empty[st]);
-            if (!same) umma_commit(&k_empty[st]);             // sole user of the block: both release arrivals
-            if (last_of_item) umma_commit(&q_empty[s]);       // the Q slot may be refilled
-        };
-        auto issue_pv = [&](uint32_t base, int j, bool same, int nk0, int nk1, bool last_of_item) {
-            const uint32_t idx = base + ring_offset(j, s, same, nk0, nk1);
-            const uint32_t st = idx % kVStages;
-            mbar_wait(&v_full[st], (idx / kVStages) & 1);
-            tc_fence_after();
-            const uint64_t da = umma_desc_kmajor_sw128(smem_u32(my_p));
-            const uint32_t vb = smem_u32(sm_v + st * kKvBytes);
-#pragma unroll
-            for (int kk = 0; kk < kKB / 16; ++kk)
-                umma_bf16(tmem_base + 128 + s * 64, da + 2 * kk, umma_desc_kmajor_sw128(vb + kk * 2048), idesc_pv,
-                          (j | kk) != 0);
-            umma_commit(&p_empty[s]);
-            umma_commit(&v_empty[st]);
-            if (!same) umma_commit(&v_empty[st]);
-            if (last_of_item) umma_commit(&o_full[s]);
-        };
-        struct Item { int qrow, nrows, Sk, qpos0, nk0, nk1, head; bool same; };
-        auto fetch = [&](int w, Item& it) {
-            it.head = w / p.n_items;
-            const int item = w - it.head * p.n_items;
-            const int4 r0 = __ldg(recs + 4 * item), r1 = __ldg(recs + 4 * item + 2);
-            it.nk0 = r0.y > 0 ? (r0.w + kKB - 1) / kKB : 0;
-            it.nk1 = r1.y > 0 ? (r1.w + kKB - 1) / kKB : 0;
-            it.same = it.nk0 > 0 && it.nk1 > 0 && r0.z == r1.z;
-            const int4 me = s == 0 ? r0 : r1;
-            it.qrow = me.x; it.nrows = me.y; it.Sk = me.w;
-            it.qpos0 = __ldg(reinterpret_cast<const int*>(recs + 4 * item + 2 * s + 1));
-        };
-
-        Item cur;
-        int w = blockIdx.x;
-        bool have = w < n_work;
-        if (have) {
-            fetch(w, cur);
-            const int my_nk = s == 0 ? cur.nk0 : cur.nk1;
-            if (issuer && my_nk > 0) issue_qk(ring, 0, cur.same, cur.nk0, cur.nk1, true, my_nk == 1);
-        }
-        while (have) {
-            const int my_nk = s == 0 ? cur.nk0 : cur.nk1;
-            const uint32_t base = ring;
-            const uint32_t next_base = base + (cur.same ? cur.nk0 : cur.nk0 + cur.nk1);
-            Item nxt;
-            const int w_next = w + gridDim.x;
-            const bool have_next = w_next < n_work;
-            if (have_next) fetch(w_next, nxt);
-            const int next_nk = have_next ? (s == 0 ? nxt.nk0 : nxt.nk1) : 0;
-            const float slope = ALIBI ? p.slopes[cur.head] * 1.4426950408889634f : 0.f;
-            const float qpos = (float)(cur.qpos0 + row);
+        const uint32_t my_p = smem_u32(sm_p + s * kQBytes) + row * 128;    // this row of the P tile (shared-space address)
+        uint32_t n_tiles = 0, n_mine = 0;                     // score tiles / items this slot has processed so far
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int head = w / p.n_items, item = w - head * p.n_items;
+            const int4 me = __ldg(recs + 4 * item + 2 * s);                       // {qrow, nrows, krow, Sk}
+            const int my_nk = me.y > 0 ? (me.w + kKB - 1) / kKB : 0;
+            if (my_nk == 0) continue;
+            const int qpos0 = __ldg(reinterpret_cast<const int*>(recs + 4 * item + 2 * s + 1));
+            const float slope = ALIBI ? p.slopes[head] * 1.4426950408889634f : 0.f;
+            const float qpos = (float)(qpos0 + row);
             float m_ref = 0.f, l_run = 0.f;
-            bool next_issued = false;                         // issuer only: next item's first Q K^T already issued
             for (int j = 0; j < my_nk; ++j) {
                 const uint32_t m = n_tiles++;
                 mbar_wait(&s_full[s], m & 1);
@@ -351,71 +386,45 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 tmem_ld_32x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
                 tmem_ld_wait();
                 tc_fence_before();
-                wg_sync();
-                if (issuer) {
-                    if (j + 1 < my_nk) {
-                        issue_qk(base, j + 1, cur.same, cur.nk0, cur.nk1, false, j + 2 == my_nk);
-                    } else if (next_nk > 0) {
-                        // run into the next item: its first score tile — but only if its Q tile and K block have
-                        // already landed.  Blocking here could deadlock: the producer may need the V block this
-                        // warpgroup is about to consume before it can reach the next item's loads.
-                        const uint32_t idx = next_base + ring_offset(0, s, nxt.same, nxt.nk0, nxt.nk1);
-                        if (mbar_try_wait(&q_full[s], (n_items_mine + 1) & 1) &&
-                            mbar_try_wait(&k_full[idx % kKStages], (idx / kKStages) & 1)) {
-                            ++n_items_mine;
-                            issue_qk(next_base, 0, nxt.same, nxt.nk0, nxt.nk1, true, next_nk == 1);
-                            --n_items_mine;
-                            next_issued = true;
-                        }
-                    }
-                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[s]);
                 softmax_tile<HD, ALIBI>(r, o_addr, j == 0, &p_empty[s], (m & 1) ^ 1, p.scale_log2, slope, qpos, j * kKB,
-                                        cur.Sk, m_ref, l_run, my_p, row, lane);
+                                        me.w, m_ref, l_run, my_p, row, lane);
                 fence_proxy_async_smem();                     // generic-proxy P writes -> visible to the UMMA (async proxy)
                 tc_fence_before();                            // orders a possible tcgen05.st rescale before the PV
-                wg_sync();
-                if (issuer) issue_pv(base, j, cur.same, cur.nk0, cur.nk1, j + 1 == my_nk);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[s]);
             }
-            if (my_nk > 0) {
-                if (issuer && next_nk > 0 && !next_issued) {  // everything of this item is consumed: blocking is safe now
-                    ++n_items_mine;
-                    issue_qk(next_base, 0, nxt.same, nxt.nk0, nxt.nk1, true, next_nk == 1);
-                    --n_items_mine;
-                }
-                // ---- epilogue: O_s / l -> bf16 -> global ----
-                mbar_wait(&o_full[s], n_items_mine & 1);
-                tc_fence_after();
-                uint32_t o0[32], o1[32];
-                tmem_ld_32x32(o_addr, o0);
-                if constexpr (HD > 48) tmem_ld_32x32(o_addr + 32, o1);
-                else tmem_ld_32x16(o_addr + 32, *reinterpret_cast<uint32_t(*)[16]>(&o1[0]));
-                tmem_ld_wait();
-                tc_fence_before();                            // the next item's first PV (issued after a wg_sync) overwrites O_s
-                if (row < cur.nrows) {
-                    const float inv = 1.0f / l_run;
-                    __nv_bfloat16* dst = p.o + (size_t)(cur.qrow + row) * p.ldo + cur.head * HD;
+            // ---- epilogue: O_s / l -> bf16 -> global ----
+            mbar_wait(&o_full[s], n_mine & 1);
+            ++n_mine;
+            tc_fence_after();
+            uint32_t o0[32], o1[32];
+            tmem_ld_32x32(o_addr, o0);
+            if constexpr (HD > 48) tmem_ld_32x32(o_addr + 32, o1);
+            else tmem_ld_32x16(o_addr + 32, *reinterpret_cast<uint32_t(*)[16]>(&o1[0]));
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_empty[s]);          // O_s may be overwritten by the next item's first P V
+            if (row < me.y) {
+                const float inv = 1.0f / l_run;
+                __nv_bfloat16* dst = p.o + (size_t)(me.x + row) * p.ldo + head * HD;
 #pragma unroll
-                    for (int e = 0; e < 32; e += 8)
-                        *reinterpret_cast<uint4*>(dst + e) = make_uint4(
-                            pack_bf16x2(__uint_as_float(o0[e]) * inv, __uint_as_float(o0[e + 1]) * inv),
-                            pack_bf16x2(__uint_as_float(o0[e + 2]) * inv, __uint_as_float(o0[e + 3]) * inv),
-                            pack_bf16x2(__uint_as_float(o0[e + 4]) * inv, __uint_as_float(o0[e + 5]) * inv),
-                            pack_bf16x2(__uint_as_float(o0[e + 6]) * inv, __uint_as_float(o0[e + 7]) * inv));
+                for (int e = 0; e < 32; e += 8)
+                    *reinterpret_cast<uint4*>(dst + e) = make_uint4(
+                        pack_bf16x2(__uint_as_float(o0[e]) * inv, __uint_as_float(o0[e + 1]) * inv),
+                        pack_bf16x2(__uint_as_float(o0[e + 2]) * inv, __uint_as_float(o0[e + 3]) * inv),
+                        pack_bf16x2(__uint_as_float(o0[e + 4]) * inv, __uint_as_float(o0[e + 5]) * inv),
+                        pack_bf16x2(__uint_as_float(o0[e + 6]) * inv, __uint_as_float(o0[e + 7]) * inv));
 #pragma unroll
-                    for (int e = 0; e < HD - 32; e += 8)
-                        *reinterpret_cast<uint4*>(dst + 32 + e) = make_uint4(
-                            pack_bf16x2(__uint_as_float(o1[e]) * inv, __uint_as_float(o1[e + 1]) * inv),
-                            pack_bf16x2(__uint_as_float(o1[e + 2]) * inv, __uint_as_float(o1[e + 3]) * inv),
-                            pack_bf16x2(__uint_as_float(o1[e + 4]) * inv, __uint_as_float(o1[e + 5]) * inv),
-                            pack_bf16x2(__uint_as_float(o1[e + 6]) * inv, __uint_as_float(o1[e + 7]) * inv));
-                }
-                ++n_items_mine;
-            } else if (issuer && next_nk > 0) {
-                // this slot was empty in the current item: nobody issued the next item's first Q K^T yet
-                issue_qk(next_base, 0, nxt.same, nxt.nk0, nxt.nk1, true, next_nk == 1);
+                for (int e = 0; e < HD - 32; e += 8)
+                    *reinterpret_cast<uint4*>(dst + 32 + e) = make_uint4(
+                        pack_bf16x2(__uint_as_float(o1[e]) * inv, __uint_as_float(o1[e + 1]) * inv),
+                        pack_bf16x2(__uint_as_float(o1[e + 2]) * inv, __uint_as_float(o1[e + 3]) * inv),
+                        pack_bf16x2(__uint_as_float(o1[e + 4]) * inv, __uint_as_float(o1[e + 5]) * inv),
+                        pack_bf16x2(__uint_as_float(o1[e + 6]) * inv, __uint_as_float(o1[e + 7]) * inv));
             }
-            ring = next_base;
-            cur = nxt; w = w_next; have = have_next;
         }
     }
 

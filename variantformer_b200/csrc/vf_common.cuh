@@ -10,7 +10,7 @@
 #ifndef VF_WATCHDOG_SPINS
 // mbarrier waits trap instead of hanging the GPU box when a pipeline bug
 // deadlocks a kernel (a hang is a strike on the shared pool).  ~seconds.
-#define VF_WATCHDOG_SPINS (1u << 28)
+#define VF_WATCHDOG_SPINS (1u << 26)
 #endif
 
 namespace vf {
@@ -90,8 +90,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > VF_WATCHDOG_SPINS) {
-            printf("vf: mbarrier watchdog: block %d thread %d bar %p parity %u\n", blockIdx.x, threadIdx.x,
-                   (void*)bar, parity);
+            // report, leave the other stuck threads of the grid a moment to report too, then kill the kernel
+            printf("vf: mbarrier watchdog: block %d thread %d barrier smem+0x%x parity %u\n", blockIdx.x, threadIdx.x,
+                   smem_u32(bar), parity);
+#pragma unroll 1
+            for (int i = 0; i < 2000; ++i) __nanosleep(1000000);
             __trap();
         }
     }
