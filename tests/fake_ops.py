@@ -85,6 +85,17 @@ def attention(q, k, v, cu_q, cu_k, tiles, heads, head_dim, slopes=None, out=None
     return _store(out, res) if out is not None else res.bfloat16()
 
 
+class SlotMap:
+    def __init__(self, q_lens, device, k_lens=None):
+        self.q_lens = np.asarray(q_lens)
+        self.k_lens = self.q_lens if k_lens is None else np.asarray(k_lens)
+
+
+def attention_mc(q, k, v, slots, heads, head_dim, slopes=None, out=None):
+    return attention(q, k, v, cu_seqlens(slots.q_lens, None), cu_seqlens(slots.k_lens, None),
+                     TileMap(slots.q_lens, 128, None), heads, head_dim, slopes, out)
+
+
 TC_BLOCK_M = 512
 
 

@@ -30,8 +30,31 @@ from ._lib import EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GEGLU_BF16, EPI_BIAS_GEL
 from .utils.alibi import alibi_slopes
 
 NUM_REF_CRES = 9
-# "tc" = tcgen05/TMEM attention for the seq2gene streams (default); "legacy" = mma.sync kernel everywhere (debug)
-ATTENTION_IMPL = os.environ.get("VF_ATTENTION", "tc")
+# "mc" = tcgen05/TMEM attention, two CTAs per SM, for every attention of the path (default);
+# "legacy" = the round-1 mma.sync kernel everywhere (debug cross-check only)
+ATTENTION_IMPL = os.environ.get("VF_ATTENTION", "mc")
+
+
+class AttnPlan:
+    """Host-built work decomposition of one attention problem (all sequences of a slab, one launch).  The kernel is
+    chosen per ROLE and head size, never per batch content, so results do not depend on how genes are batched."""
+
+    def __init__(self, q_lens, device, head_dim, k_lens=None):
+        self.mc = ATTENTION_IMPL == "mc" and head_dim in (48, 64)
+        if self.mc:
+            self.slots = ops.SlotMap(q_lens, device, k_lens=k_lens)
+        else:
+            kl = q_lens if k_lens is None else k_lens
+            self.cu_q, self.cu_k = ops.cu_seqlens(q_lens, device), ops.cu_seqlens(kl, device)
+            self.tiles = ops.TileMap(q_lens, 64, device, k_lens=k_lens)
+
+    def device_tensors(self):
+        return [self.slots.table] if self.mc else [self.cu_q, self.cu_k, self.tiles.tile_seq, self.tiles.tile_q0]
+
+    def run(self, q, k, v, heads, head_dim, slopes, out):
+        if self.mc:
+            return ops.attention_mc(q, k, v, self.slots, heads, head_dim, slopes, out=out)
+        return ops.attention(q, k, v, self.cu_q, self.cu_k, self.tiles, heads, head_dim, slopes, out=out)
 
 
 def sinusoidal_pe(d_model: int, length: int) -> torch.Tensor:
@@ -186,9 +209,9 @@ class Engine:
         self.ws = Workspace(self.device)
 
     # ---------------------------------------------------------------- seq2reg
-    def seq2reg(self, W: Seq2RegWeights, tokens_i32, mask_u8, lens_host, cu, tiles):
-        """tokens/mask: device [n_win, L]; lens_host: numpy valid-token counts; cu/tiles: their prefix sums and
-        attention tile map on the device.  -> bf16 [n_win, d] masked mean of the last layer."""
+    def seq2reg(self, W: Seq2RegWeights, tokens_i32, mask_u8, lens_host, cu, plan: AttnPlan):
+        """tokens/mask: device [n_win, L]; lens_host: numpy valid-token counts; cu: their prefix sums on the device;
+        plan: the windows' attention work decomposition.  -> bf16 [n_win, d] masked mean of the last layer."""
         ws = self.ws
         n_win = tokens_i32.shape[0]
         n_tok = int(lens_host.sum())
@@ -208,8 +231,7 @@ class Engine:
         for li, L in enumerate(W.layers):
             ops.gemm(xb, L["qkv"].w, EPI_BIAS_BF16, bias=L["qkv"].b, out=qkv,
                      ln=L["qkv"].ln(xs0 if li == 0 else xs))                                           # Wqkv(norm1(x))
-            attn = ops.attention_tc if tiles.block_m == ops.TC_BLOCK_M else ops.attention
-            attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], cu, cu, tiles, H, hd, W.slopes, out=a)
+            plan.run(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], H, hd, W.slopes, a)
             ops.gemm(a, L["out"].w, EPI_BIAS_RESID_F32, bias=L["out"].b, resid=x, out=x1, out2=xb, stats_out=s1)
             ops.gemm(xb, L["g1"].w, EPI_BIAS_GEGLU_BF16, bias=L["g1"].b, out=f, ln=L["g1"].ln(s1))      # GeGLU(norm2(x1))
             ops.gemm(f, L["g2"].w, EPI_BIAS_RESID_F32, bias=L["g2"].b, resid=x, out=x, out2=xb, stats_out=xs)  # + layer input
@@ -265,9 +287,7 @@ class Engine:
         s["gtok"], s["gmsk"], s["glens"] = stage(gene_tokens, gene_masks, None if lens is None else lens[1])
         for tag, ln, W in (("c", s["clens"], self.cre_tok), ("g", s["glens"], self.gene_tok)):
             s[tag + "_cu_tok"] = ops.cu_seqlens(ln, dev)
-            # gene-window chunks are full 200-token sequences (2 query tiles) -> tcgen05; CRE windows (~97 tokens) -> warp-MMA
-            use_tc = ATTENTION_IMPL == "tc" and W.hd in (48, 64) and tag == "g"
-            s[tag + "_tiles_tok"] = ops.TileMap(ln, ops.TC_BLOCK_M if use_tc else 64, dev)
+            s[tag + "_plan_tok"] = AttnPlan(ln, dev, W.hd)
         # gene stream layout: per (gene, tissue): [registry(tissue); the gene's chunk embeddings]
         g_off = np.concatenate([[0], np.cumsum(G)])
         idx, seq_lens = [], []
@@ -281,20 +301,9 @@ class Engine:
         seq_lens = np.asarray(seq_lens)
         s["Mg"] = int(idx.shape[0])
         s["gene_idx"] = up(idx, np.int32)
-        s["cu_gseq"] = ops.cu_seqlens(seq_lens, dev)                  # one sequence per (gene, tissue): self-attention
-        s["cu_gq"] = ops.cu_seqlens(T * (G + 1), dev)                 # one "sequence" per gene: stacked cross queries
-        s["cu_cre"] = ops.cu_seqlens(C, dev)
-        if ATTENTION_IMPL == "tc" and self.w.hd in (48, 64):
-            # The kernel is chosen per ROLE, never per batch content, so results do not depend on how genes are batched:
-            # tcgen05 for every seq2gene attention (stacked cross-attention with 128-key blocks; CRE and gene
-            # self-attention with 64-key blocks, the <=201-token gene items double-buffered across items).
-            s["tiles_gself"] = ops.TileMap(seq_lens, ops.TC_BLOCK_M, dev)
-            s["tiles_gcross"] = ops.TileMap(T * (G + 1), ops.TC_BLOCK_M, dev, k_lens=C)
-            s["tiles_cself"] = ops.TileMap(C, ops.TC_BLOCK_M, dev)
-        else:
-            s["tiles_gself"] = ops.TileMap(seq_lens, 64, dev)
-            s["tiles_gcross"] = ops.TileMap(T * (G + 1), 128, dev, k_lens=C)
-            s["tiles_cself"] = ops.TileMap(C, 128 if C.max() > 256 else 64, dev)
+        s["plan_gself"] = AttnPlan(seq_lens, dev, self.w.hd)            # one sequence per (gene, tissue): self-attention
+        s["plan_gcross"] = AttnPlan(T * (G + 1), dev, self.w.hd, k_lens=C)   # per gene: stacked tissue queries x its CREs
+        s["plan_cself"] = AttnPlan(C, dev, self.w.hd)
         s["row_seq"] = up(np.repeat(np.arange(B), C), np.int32)
         lab = torch.cat([l.reshape(-1) for l in ref_labels]).detach().cpu().numpy().astype(np.int64)
         counts = np.zeros((B, NUM_REF_CRES), np.float64)
@@ -320,8 +329,8 @@ class Engine:
         nC, Mg = int(s["C"].sum()), s["Mg"]
 
         # ---- stage 2: window encoders ----
-        cre_pooled = self.seq2reg(self.cre_tok, s["ctok"], s["cmsk"], s["clens"], s["c_cu_tok"], s["c_tiles_tok"])
-        gene_pooled = self.seq2reg(self.gene_tok, s["gtok"], s["gmsk"], s["glens"], s["g_cu_tok"], s["g_tiles_tok"])
+        cre_pooled = self.seq2reg(self.cre_tok, s["ctok"], s["cmsk"], s["clens"], s["c_cu_tok"], s["c_plan_tok"])
+        gene_pooled = self.seq2reg(self.gene_tok, s["gtok"], s["gmsk"], s["glens"], s["g_cu_tok"], s["g_plan_tok"])
         cre_bf = ws.get("cre_bf", (nC, D), torch.bfloat16)                           # bf16 mirror = cross-attn context
         if w.cre_map is None:
             raise NotImplementedError("token_dim == emb_dim (no cre_map) is not wired on the B200 path")
@@ -334,25 +343,18 @@ class Engine:
         gxs = ops.rowstats(gx, ws.get("gxs0", (Mg, 1, 2), torch.float32), gxb)
         st = {"g": gxs, "c": cxs}                                      # current row statistics of each stream
         kv = ws.get("g_kv", (nC, 2 * D), torch.bfloat16)
-        cu_gseq, cu_gq, cu_cre = s["cu_gseq"], s["cu_gq"], s["cu_cre"]
-
-        def attn(q, k, v, cu_q, cu_k, tiles, slopes, out, key_block=64):
-            if tiles.block_m == ops.TC_BLOCK_M:
-                ops.attention_tc(q, k, v, cu_q, cu_k, tiles, H, hd, slopes, out=out, key_block=key_block)
-            else:
-                ops.attention(q, k, v, cu_q, cu_k, tiles, H, hd, slopes, out=out)
 
         def gene_self(qkv, out):
-            attn(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], cu_gseq, cu_gseq, s["tiles_gself"], w.slopes, out)
+            s["plan_gself"].run(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], H, hd, w.slopes, out)
 
         def cre_self(qkv, out):
-            attn(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], cu_cre, cu_cre, s["tiles_cself"], w.slopes, out)
+            s["plan_cself"].run(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], H, hd, w.slopes, out)
 
         def gene_layer(L):
             ops.gemm(cre_bf, L["kv"].w, EPI_BIAS_BF16, bias=L["kv"].b, out=kv)      # shared by every tissue copy
 
             def cross(q, out):
-                attn(q, kv[:, :D], kv[:, D:], cu_gq, cu_cre, s["tiles_gcross"], None, out, key_block=128)
+                s["plan_gcross"].run(q, kv[:, :D], kv[:, D:], H, hd, None, out)
             st["g"] = self._layer(L, gx, gxb, st["g"], Mg, gene_self, cross, "g")
 
         def cre_layer(L):

@@ -96,8 +96,9 @@ class HotPath:
                 for x in (v if isinstance(v, (list, tuple)) else [v]):
                     if torch.is_tensor(x) and x.is_cuda:
                         x.record_stream(main)
-                    elif hasattr(x, "tile_seq"):
-                        x.tile_seq.record_stream(main); x.tile_q0.record_stream(main)
+                    elif hasattr(x, "device_tensors"):
+                        for t in x.device_tensors():
+                            t.record_stream(main)
             return slab, ev
 
         it = iter(slabs)

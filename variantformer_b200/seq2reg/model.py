@@ -70,7 +70,7 @@ class Seq2RegPredictor(nn.Module):
         if not only_embed:
             raise NotImplementedError("tissue-classifier logits are a training-time output, outside the hot path")
         from .. import ops
-        from ..engine import Engine
+        from ..engine import AttnPlan, Engine
         W, ws = self._weights()
         b, s, L = x.shape
         dev = self.token_embedding.weight.device
@@ -78,5 +78,5 @@ class Seq2RegPredictor(nn.Module):
         msk = padding_mask.reshape(b * s, L).to(device=dev, dtype=torch.uint8).contiguous()
         lens = ops.window_lengths(msk).cpu().numpy().astype(np.int64)
         eng = Engine.__new__(Engine); eng.device = dev; eng.ws = ws
-        pooled = eng.seq2reg(W, tok, msk, lens, ops.cu_seqlens(lens, dev), ops.TileMap(lens, 64, dev))
+        pooled = eng.seq2reg(W, tok, msk, lens, ops.cu_seqlens(lens, dev), AttnPlan(lens, dev, W.hd))
         return pooled.float().view(b, s, -1)
