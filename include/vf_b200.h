@@ -67,9 +67,13 @@ int vf_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, i
  *   stats_out (fp32 [M, 2*ceil(N/256), 2]): the fp32 epilogues store one partial (sum, sum of squares) of every output
  *   row per 128-column half tile (plain stores: deterministic), i.e. the ln_stats of the next folded GEMM with
  *   ln_parts = 2*ceil(N/256).  NULL = off.
+ *   resid_bf16 != 0: the residual of VF_EPI_BIAS_RESID_F32 is a bf16 matrix (row stride ldr elements).  The fp32
+ *   epilogues accept out == NULL when out2_bf16 is given: only the bf16 mirror (and the statistics) are written.  Both
+ *   serve the intra-layer temporaries x1 = MHA(LN(x)) + x of the encoder layers, which are consumed only through a
+ *   LayerNorm feeding a bf16 GEMM (the layer's residual path is the layer INPUT: layers.py:163, modules.py:189).
  */
 int vf_gemm_bf16_ln(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int epilogue,
-                    const float* bias, const float* resid, int ldr, void* out, int ldo, void* out2_bf16, int ldo2,
+                    const float* bias, const void* resid, int resid_bf16, int ldr, void* out, int ldo, void* out2_bf16, int ldo2,
                     const float* ln_stats, int ln_parts, const float* ln_colsum, int ln_dim, float ln_eps,
                     float* stats_out, void* stream);
 /* Per-row (sum, sum of squares) of an fp32 matrix [M,d] into stats [M,1,2] + optional bf16 mirror: the statistics of a

@@ -22,7 +22,7 @@ def _store(out, val):
     return out
 
 
-def gemm(a, w, epilogue, bias=None, resid=None, out=None, out2=None, ln=None, stats_out=None):
+def gemm(a, w, epilogue, bias=None, resid=None, out=None, out2=None, ln=None, stats_out=None, mirror_only=False):
     y = a.float() @ w.float().t()
     if ln is not None:                       # LayerNorm fold: rstd * (acc - mean * colsum)
         stats, colsum, dim, eps = ln
@@ -43,13 +43,15 @@ def gemm(a, w, epilogue, bias=None, resid=None, out=None, out2=None, ln=None, st
         dt = torch.bfloat16
     else:
         if epilogue == EPI_BIAS_RESID_F32 and resid is not None:
-            y = y + resid
+            y = y + resid.float()
         dt = torch.float32
     if out2 is not None:
         out2.copy_(y.to(torch.bfloat16))
     if stats_out is not None:
         stats_out.zero_()
         stats_out[:, 0].copy_(torch.stack([y.sum(1), (y * y).sum(1)], 1))
+    if mirror_only:
+        return out2
     if out is None:
         return y.to(dt)
     assert out.dtype == dt

@@ -133,6 +133,24 @@ def test_gemm_stats_out_and_layernorm_fold(M, N, K):
     assert torch.allclose(got3.float(), want3, atol=5e-2, rtol=3e-2), _describe_mismatch(got3.float(), want3, 5e-2)
 
 
+@pytest.mark.parametrize("M,N,K", [(515, 512, 512), (3000, 1536, 1024)])
+def test_gemm_bf16_residual_and_mirror_only(M, N, K):
+    """Intra-layer temporaries: x1' = x1 + Linear(a) with x1 held in bf16, in place, only mirror + statistics written."""
+    g = torch.Generator(device="cpu").manual_seed(M + N)
+    a = (torch.randn(M, K, generator=g) * 0.5).to(DEV).bfloat16()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV).bfloat16()
+    bias = torch.randn(N, generator=g).to(DEV)
+    x1 = torch.randn(M, N, generator=g).to(DEV).bfloat16()
+    want = a.float() @ w.float().t() + bias + x1.float()
+    st = torch.empty(M, ops.stats_parts(N), 2, device=DEV)
+    got = ops.gemm(a, w, EPI_BIAS_RESID_F32, bias=bias, resid=x1, out2=x1, stats_out=st, mirror_only=True)
+    torch.cuda.synchronize()
+    assert got.data_ptr() == x1.data_ptr()
+    assert torch.allclose(x1.float(), want, atol=3e-2, rtol=2e-2), _describe_mismatch(x1.float(), want, 3e-2)
+    tot = st.sum(1)                                        # statistics are taken from the fp32 values before rounding
+    assert torch.allclose(tot[:, 0], want.sum(1), atol=5e-2, rtol=1e-3) and torch.allclose(tot[:, 1], (want * want).sum(1), rtol=2e-3)
+
+
 def test_rowstats_mirror():
     x = torch.randn(1001, 1536, device=DEV) * 2 + 0.5
     xb = torch.empty(1001, 1536, dtype=torch.bfloat16, device=DEV)

@@ -20,7 +20,7 @@ SIGNATURES = {
     "vf_abi_version": ([], _i32),
     "vf_device_check": ([_vp], _i32),
     "vf_gemm_bf16": ([_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _vp], _i32),
-    "vf_gemm_bf16_ln": ([_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _i32,
+    "vf_gemm_bf16_ln": ([_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _i32, _vp, _i32,
                          _vp, _i32, _vp, _i32, C.c_float, _vp, _vp], _i32),
     "vf_rowstats": ([_vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp], _i32),
     "vf_attention_varlen": ([_vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,

@@ -39,14 +39,14 @@ int vf_device_check(int* sm_count) {
 
 int vf_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int epilogue, const float* bias,
                  const float* resid, int ldr, void* out, int ldo, void* out2_bf16, int ldo2, void* stream) {
-    return gemm_bf16(A, lda, W, ldw, M, N, K, epilogue, bias, resid, ldr, out, ldo, out2_bf16, ldo2, nullptr, 0, nullptr,
+    return gemm_bf16(A, lda, W, ldw, M, N, K, epilogue, bias, resid, 0, ldr, out, ldo, out2_bf16, ldo2, nullptr, 0, nullptr,
                      0, 0.f, nullptr, ST(stream));
 }
 int vf_gemm_bf16_ln(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int epilogue,
-                    const float* bias, const float* resid, int ldr, void* out, int ldo, void* out2_bf16, int ldo2,
+                    const float* bias, const void* resid, int resid_bf16, int ldr, void* out, int ldo, void* out2_bf16, int ldo2,
                     const float* ln_stats, int ln_parts, const float* ln_colsum, int ln_dim, float ln_eps,
                     float* stats_out, void* stream) {
-    return gemm_bf16(A, lda, W, ldw, M, N, K, epilogue, bias, resid, ldr, out, ldo, out2_bf16, ldo2, ln_stats,
+    return gemm_bf16(A, lda, W, ldw, M, N, K, epilogue, bias, resid, resid_bf16, ldr, out, ldo, out2_bf16, ldo2, ln_stats,
                      ln_parts, ln_colsum, ln_dim, ln_eps, stats_out, ST(stream));
 }
 int vf_rowstats(const float* x, int ldx, int M, int d, float* stats, void* out_bf16, int ldo, void* stream) {

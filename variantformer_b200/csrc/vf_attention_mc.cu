@@ -295,7 +295,7 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             };
             auto ready = [&](uint64_t* bar, uint32_t parity, bool blocking) -> bool {
                 if (blocking) { mbar_wait(bar, parity); return true; }
-                return mbar_try_wait(bar, parity);
+                return mbar_test_wait(bar, parity);
             };
             // S(j) = Q K(j)^T of item `it`; non-blocking mode gives up (nothing issued) if an input has not landed yet
             auto issue_qk = [&](It& it, int j, bool blocking) -> bool {

@@ -7,10 +7,10 @@
 #include <stdint.h>
 #include <stdio.h>
 
-#ifndef VF_WATCHDOG_SPINS
-// mbarrier waits trap instead of hanging the GPU box when a pipeline bug
-// deadlocks a kernel (a hang is a strike on the shared pool).  ~seconds.
-#define VF_WATCHDOG_SPINS (1u << 26)
+#ifndef VF_WATCHDOG_NS
+// mbarrier waits trap instead of hanging the GPU box when a pipeline bug deadlocks a kernel (a hang is a strike on
+// the shared pool): a wait that lasts longer than this many nanoseconds of %globaltimer is reported and killed.
+#define VF_WATCHDOG_NS 4000000000ull
 #endif
 
 namespace vf {
@@ -58,6 +58,17 @@ __device__ __forceinline__ float gelu_erf(float x) {   // nn.GELU() default (exa
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
+// ---- explicit shared-memory accesses (32-bit shared-space addresses).  Going through a generic pointer the
+// compiler emits LD.E / ST.E with 64-bit address arithmetic, tracked on the long scoreboard like global memory. ----
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 // ---- mbarrier ----------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -75,6 +86,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+// Potentially blocking test (the hardware may suspend the thread for a short, implementation-defined time).  An
+// explicit long suspend-time hint was measured: it saves issue slots but wakes the waiter late (attention and the
+// K=512 GEMMs 5-15 % slower), so the default stays.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -86,16 +100,39 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking test of a phase.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
+    uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > VF_WATCHDOG_SPINS) {
-            // report, leave the other stuck threads of the grid a moment to report too, then kill the kernel
-            printf("vf: mbarrier watchdog: block %d thread %d barrier smem+0x%x parity %u\n", blockIdx.x, threadIdx.x,
-                   smem_u32(bar), parity);
+        if ((++spins & 255u) == 0) {                         // look at the clock only now and then
+            const uint64_t now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > VF_WATCHDOG_NS) {
+                // report, leave the other stuck threads of the grid a moment to report too, then kill the kernel
+                printf("vf: mbarrier watchdog: block %d thread %d barrier smem+0x%x parity %u\n", blockIdx.x, threadIdx.x,
+                       smem_u32(bar), parity);
 #pragma unroll 1
-            for (int i = 0; i < 2000; ++i) __nanosleep(1000000);
-            __trap();
+                for (int i = 0; i < 1000; ++i) __nanosleep(1000000);
+                __trap();
+            }
         }
     }
 }

@@ -9,8 +9,7 @@
 //   seq2gene/modules/layers.py:1078-1087 (head Linear layers).
 //
 // Kernel shape: persistent, one CTA per SM, 384 threads = 3 warpgroups:
-//   warp 0    : TMA producer (one elected lane)       smem ring of kStages x (A 128x64 + W 256x64) bf16;
-//               also bulk-prefetches the fp32 residual tile of the tile it is loading into L2
+//   warp 0    : TMA producer (one elected lane)       smem ring of kStages x (A 128x64 + W 256x64) bf16
 //   warp 1    : TMEM allocator + tcgen05.mma issuer   UMMA 128x256x16, 4 per k-block
 //   warps 2-3 : idle (they only exist so that warpgroup 0 can give its registers away with setmaxnreg)
 //   warps 4-11: epilogue (TMEM lane quadrant = warp%4, two warps per quadrant), 232 registers each: pipelined
@@ -47,6 +46,7 @@ struct GemmParams {
     int M, N, K;
     const float* bias;       // [N] (GeGLU: tile-interleaved like W) or nullptr
     const float* resid;      // fp32 [M, ldr] or nullptr
+    const __nv_bfloat16* resid16;   // ... or a bf16 residual [M, ldr] (intra-layer temporaries, see engine.py)
     int ldr;
     void* out;               // bf16 or fp32, row stride ldo (elements)
     int ldo;
@@ -57,6 +57,8 @@ struct GemmParams {
     const float* ln_colsum;  //                 fp32 [N] column sums of the gamma-folded weight (layout of `bias`)
     float ln_inv_d, ln_eps;  //                 1 / normalised width, eps
     float* stats_out;        // fp32 outputs: partial (sum, sum of squares) of every output row -> [M, 2*n_tiles, 2], or nullptr
+    int prefetch_resid;      // producer warp bulk-prefetches the residual tile into L2 (VF_GEMM_RESID_PREFETCH=1; off by
+                             // default: measured 5-10 % slower than the epilogue's own one-slab-ahead register prefetch)
 };
 
 template <int EPI>
@@ -77,9 +79,16 @@ __device__ __forceinline__ void load_resid_slab(const GemmParams& p, int row0, i
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         const int grow = row0 + it * 4 + (lane >> 3), gcol = col0 + (lane & 7) * 4;
-        rr4[it] = (p.resid && grow < p.M && gcol + 4 <= p.N)
-                      ? *reinterpret_cast<const float4*>(p.resid + (size_t)grow * p.ldr + gcol)
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool ok = grow < p.M && gcol + 4 <= p.N;
+        if (p.resid16) {
+            uint2 h = make_uint2(0u, 0u);
+            if (ok) h = *reinterpret_cast<const uint2*>(p.resid16 + (size_t)grow * p.ldr + gcol);
+            rr4[it] = make_float4(__uint_as_float(h.x << 16), __uint_as_float(h.x & 0xffff0000u),
+                                  __uint_as_float(h.y << 16), __uint_as_float(h.y & 0xffff0000u));
+        } else {
+            rr4[it] = (p.resid && ok) ? *reinterpret_cast<const float4*>(p.resid + (size_t)grow * p.ldr + gcol)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
 }
 
@@ -116,61 +125,80 @@ struct RowStats {
 };
 
 template <int EPI>
-__device__ __forceinline__ void epilogue_store_slab(const GemmParams& p, uint8_t* stage, int row0, int col0, int n_out,
+__device__ __forceinline__ void epilogue_store_slab(const GemmParams& p, uint32_t stage, int row0, int col0, int n_out,
                                                     const float (&v)[32], int lane, const float4 (&rr4)[8],
                                                     RowStats& rs) {
+    // `stage` = shared-space address of the warp's 4 KB tile.  All reads of the transposed tile are issued as one batch
+    // (no branch in between), then the global stores follow.
     if constexpr (epi_is_bf16<EPI>()) {
-        uint4* st = reinterpret_cast<uint4*>(stage);                    // [32 rows][4 chunks of 16 B]
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint4 q;
-            q.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]); q.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
-            q.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]); q.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
-            st[lane * 4 + (j ^ ((lane >> 1) & 3))] = q;
-        }
+        for (int j = 0; j < 4; ++j)                                     // [32 rows][4 chunks of 16 B]
+            sts128(stage + (lane * 4 + (j ^ ((lane >> 1) & 3))) * 16, pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]),
+                   pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]), pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]),
+                   pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
         __syncwarp();
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out);
+        uint4 q[4];
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
             const int rr = it * 8 + (lane >> 2), jj = lane & 3;
-            const uint4 q = st[rr * 4 + (jj ^ ((rr >> 1) & 3))];
-            const int grow = row0 + rr, gcol = col0 + jj * 8;
-            if (grow < p.M && gcol + 8 <= n_out) *reinterpret_cast<uint4*>(o + (size_t)grow * p.ldo + gcol) = q;
+            q[it] = lds128(stage + (rr * 4 + (jj ^ ((rr >> 1) & 3))) * 16);
         }
         __syncwarp();
-    } else {
-        float4* st = reinterpret_cast<float4*>(stage);                  // [32 rows][8 chunks of 16 B]
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out);
+        const int gcol = col0 + (lane & 3) * 8;
+        if (gcol + 8 <= n_out) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            st[lane * 8 + (j ^ (lane & 7))] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+            for (int it = 0; it < 4; ++it) {
+                const int grow = row0 + it * 8 + (lane >> 2);
+                if (grow < p.M) *reinterpret_cast<uint4*>(o + (size_t)grow * p.ldo + gcol) = q[it];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)                                     // [32 rows][8 chunks of 16 B]
+            sts128(stage + (lane * 8 + (j ^ (lane & 7))) * 16, __float_as_uint(v[j * 4]), __float_as_uint(v[j * 4 + 1]),
+                   __float_as_uint(v[j * 4 + 2]), __float_as_uint(v[j * 4 + 3]));
         __syncwarp();
-        float* o = reinterpret_cast<float*>(p.out);
+        uint4 q[8];
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
             const int rr = it * 4 + (lane >> 3), jj = lane & 7;
-            float4 q = st[rr * 8 + (jj ^ (rr & 7))];
-            const int grow = row0 + rr, gcol = col0 + jj * 4;
-            if (grow < p.M && gcol + 4 <= n_out) {
-                if constexpr (EPI == VF_EPI_BIAS_RESID_F32) {
-                    q.x += rr4[it].x; q.y += rr4[it].y; q.z += rr4[it].z; q.w += rr4[it].w;
-                }
-                *reinterpret_cast<float4*>(o + (size_t)grow * p.ldo + gcol) = q;
-                if (p.out2) {
-                    uint2 h; h.x = pack_bf16x2(q.x, q.y); h.y = pack_bf16x2(q.z, q.w);
-                    *reinterpret_cast<uint2*>(p.out2 + (size_t)grow * p.ldo2 + gcol) = h;
-                }
-                rs.s1[it] += (q.x + q.y) + (q.z + q.w);
-                rs.s2[it] += fmaf(q.x, q.x, q.y * q.y) + fmaf(q.z, q.z, q.w * q.w);
-            }
+            q[it] = lds128(stage + (rr * 8 + (jj ^ (rr & 7))) * 16);
         }
         __syncwarp();
+        float* o = reinterpret_cast<float*>(p.out);
+        const int gcol = col0 + (lane & 7) * 4;
+        if (gcol + 4 <= n_out) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int grow = row0 + it * 4 + (lane >> 3);
+                float4 f = make_float4(__uint_as_float(q[it].x), __uint_as_float(q[it].y), __uint_as_float(q[it].z),
+                                       __uint_as_float(q[it].w));
+                if constexpr (EPI == VF_EPI_BIAS_RESID_F32) {
+                    f.x += rr4[it].x; f.y += rr4[it].y; f.z += rr4[it].z; f.w += rr4[it].w;
+                }
+                if (grow < p.M) {
+                    if (o) *reinterpret_cast<float4*>(o + (size_t)grow * p.ldo + gcol) = f;
+                    if (p.out2) {
+                        uint2 h; h.x = pack_bf16x2(f.x, f.y); h.y = pack_bf16x2(f.z, f.w);
+                        *reinterpret_cast<uint2*>(p.out2 + (size_t)grow * p.ldo2 + gcol) = h;
+                    }
+                    rs.s1[it] += (f.x + f.y) + (f.z + f.w);
+                    rs.s2[it] += fmaf(f.x, f.x, f.y * f.y) + fmaf(f.z, f.z, f.w * f.w);
+                }
+            }
+        }
     }
 }
 
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmR, const GemmParams p_in) {
+    // Local copy: the fields live in registers.  Read through the parameter itself they are re-fetched from the
+    // constant bank (LDCU, a scoreboard wait each) after every asm statement with a memory clobber — in the epilogue
+    // that is several times per slab.
+    const GemmParams p = p_in;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;                                  // kStages x 16 KB
@@ -215,7 +243,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
                     if constexpr (EPI == VF_EPI_BIAS_RESID_F32) {
                         // the epilogue of this tile runs one mainloop from now: pull its residual into L2 meanwhile
-                        if (p.resid) {
+                        if (p.resid && p.prefetch_resid) {   // (fp32 residual only)
 #pragma unroll
                             for (int c = 0; c < BN; c += 64)
                                 if (n0 + c < p.N) tma_prefetch_l2_2d(&tmR, n0 + c, m0);
@@ -268,12 +296,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int quad = warp & 3;
         const int half = (warp - kFirstEpiWarp) >> 2;
         const int lane = threadIdx.x & 31;
-        uint8_t* stage_out = smem_out + (warp - kFirstEpiWarp) * kStageOutBytes;
+        const uint32_t stage_out = smem_u32(smem_out + (warp - kFirstEpiWarp) * kStageOutBytes);
         constexpr int kSlabs = (EPI == VF_EPI_BIAS_GEGLU_BF16) ? 2 : 4;      // per warp per tile
         const int n_out = (EPI == VF_EPI_BIAS_GEGLU_BF16) ? p.N / 2 : p.N;
         const bool ln = epi_is_bf16<EPI>() && p.ln_stats != nullptr;
         const bool want_stats = !epi_is_bf16<EPI>() && p.stats_out != nullptr;
         RowStats rs;
+        float4 rr4[4][8];                                     // residual of slab i of a tile (RESID epilogue only)
+        if constexpr (EPI == VF_EPI_BIAS_RESID_F32) {
+            if ((int)blockIdx.x < num_tiles) {                // prime the slab stream: slabs 0 and 1 of the first tile
+                const int m0f = ((int)blockIdx.x / n_tiles) * BM, n0f = ((int)blockIdx.x % n_tiles) * BN;
+                load_resid_slab(p, m0f + quad * 32, n0f + half * 32, lane, rr4[0]);
+                load_resid_slab(p, m0f + quad * 32, n0f + (half + 2) * 32, lane, rr4[1]);
+            }
+        }
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
@@ -333,22 +369,47 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     float4 none[8];
                     epilogue_store_slab<EPI>(p, stage_out, row0, out0 + c * 32, n_out, v, lane, none, rs);
                 }
+            } else if constexpr (EPI == VF_EPI_BIAS_RESID_F32) {
+                // The fp32 residual is the long-latency input of this epilogue (one DRAM round trip per slab) and it
+                // does not depend on the MMA: the slab stream of this warp (4 per tile, tile after tile) keeps the
+                // residual of the NEXT TWO slabs in flight in registers — across the tile boundary too — while the
+                // current slab is converted and stored.  rr4[i] belongs to slab i of a tile; slabs 0 and 1 of the first
+                // tile were primed before the loop.
+                uint32_t r[32];
+#pragma unroll
+                for (int i = 0; i < kSlabs; ++i) {
+                    const int c = half + 2 * i;
+                    const int col0 = n0 + c * 32;
+                    {   // prefetch distance 2: slab i+2 of this tile, or slab i-2 of this warp's next tile
+                        const int tn = i + 2 < kSlabs ? t : t + (int)gridDim.x;
+                        const int cn = half + 2 * ((i + 2) & 3);
+                        const int m0n = (tn / n_tiles) * BM, n0n = (tn % n_tiles) * BN;
+                        if (tn < num_tiles) load_resid_slab(p, m0n + quad * 32, n0n + cn * 32, lane, rr4[(i + 2) & 3]);
+                    }
+                    if (col0 < p.N) {                                     // warp-uniform
+                        tmem_ld_32x32(t_row + c * 32, r);
+                        tmem_ld_wait();
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (p.bias && col0 + j + 4 <= p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                            v[j + 0] = __uint_as_float(r[j + 0]) + b.x; v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
+                            v[j + 2] = __uint_as_float(r[j + 2]) + b.z; v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
+                        }
+                        epilogue_store_slab<EPI>(p, stage_out, row0, col0, n_out, v, lane, rr4[i], rs);
+                    }
+                }
             } else {
                 uint32_t r[2][32];
-                float4 rr4[2][8];
+                float4 none[8];
                 const bool any = n0 + half * 32 < p.N;
                 if (any) tmem_ld_32x32(t_row + half * 32, r[0]);
-                if constexpr (EPI == VF_EPI_BIAS_RESID_F32) {
-                    if (any) load_resid_slab(p, row0, n0 + half * 32, lane, rr4[0]);
-                }
 #pragma unroll
                 for (int i = 0; i < kSlabs; ++i) {
                     const int c = half + 2 * i;
                     const int col0 = n0 + c * 32;
                     if (col0 >= p.N) break;                               // warp-uniform
-                    if constexpr (EPI == VF_EPI_BIAS_RESID_F32) {        // next slab's residual: one slab ahead
-                        if (i + 1 < kSlabs && col0 + 64 < p.N) load_resid_slab(p, row0, col0 + 64, lane, rr4[(i + 1) & 1]);
-                    }
                     tmem_ld_wait();
                     if (i + 1 < kSlabs && col0 + 64 < p.N) tmem_ld_32x32(t_row + (c + 2) * 32, r[(i + 1) & 1]);
                     float v[32];
@@ -372,7 +433,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
                     }
-                    epilogue_store_slab<EPI>(p, stage_out, row0, col0, n_out, v, lane, rr4[i & 1], rs);
+                    epilogue_store_slab<EPI>(p, stage_out, row0, col0, n_out, v, lane, none, rs);
                 }
             }
             // all TMEM reads of this accumulator are complete (wait::ld above) -> hand it back to the MMA warp
@@ -445,12 +506,13 @@ __global__ void gemm_simt_epilogue_kernel(const float* __restrict__ C, const Gem
             if (p.ln_stats && EPI != VF_EPI_BIAS_RESID_F32 && EPI != VF_EPI_BIAS_F32) v = ln_a * v + ln_c * p.ln_colsum[col];
             if (p.bias) v += p.bias[col];
             if (EPI == VF_EPI_BIAS_RESID_F32 && p.resid) v += p.resid[(size_t)row * p.ldr + col];
+            if (EPI == VF_EPI_BIAS_RESID_F32 && p.resid16) v += __bfloat162float(p.resid16[(size_t)row * p.ldr + col]);
             if (EPI == VF_EPI_BIAS_GELU_BF16) v = gelu_erf(v);
         }
         if constexpr (EPI == VF_EPI_BIAS_BF16 || EPI == VF_EPI_BIAS_GEGLU_BF16 || EPI == VF_EPI_BIAS_GELU_BF16) {
             reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)row * p.ldo + col] = __float2bfloat16_rn(v);
         } else {
-            reinterpret_cast<float*>(p.out)[(size_t)row * p.ldo + col] = v;
+            if (p.out) reinterpret_cast<float*>(p.out)[(size_t)row * p.ldo + col] = v;
             if (p.out2) p.out2[(size_t)row * p.ldo2 + col] = __float2bfloat16_rn(v);
             if (p.stats_out) {      // debug path: everything lands in part 0 (the buffer was zeroed by the launcher)
                 const int parts = 2 * ((p.N + BN - 1) / BN);
@@ -517,6 +579,7 @@ static int make_tmap_resid(CUtensorMap* tm, const float* base, int rows, int col
 
 static int g_num_sms = 0;
 static bool g_debug_simt = false;
+static int g_resid_prefetch = 0;
 static bool g_inited = false;
 
 template <int EPI>
@@ -550,7 +613,7 @@ static int launch_simt(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, 
 }
 
 int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int epi, const float* bias,
-              const float* resid, int ldr, void* out, int ldo, void* out2, int ldo2, const float* ln_stats,
+              const void* resid, int resid_bf16, int ldr, void* out, int ldo, void* out2, int ldo2, const float* ln_stats,
               int ln_parts, const float* ln_colsum, int ln_dim, float ln_eps, float* stats_out, cudaStream_t stream) {
     if (!g_inited) {
         int dev = 0;
@@ -558,6 +621,8 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
         VF_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
         const char* e = getenv("VF_GEMM_DEBUG_SIMT");
         g_debug_simt = e && e[0] == '1';
+        const char* e2 = getenv("VF_GEMM_RESID_PREFETCH");
+        g_resid_prefetch = e2 && e2[0] == '1';
         g_inited = true;
     }
     VF_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
@@ -566,9 +631,14 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
     VF_REQUIRE(epi >= 0 && epi < VF_EPI_COUNT, "gemm: unknown epilogue %d", epi);
     if (epi == VF_EPI_BIAS_GEGLU_BF16) VF_REQUIRE(N % 256 == 0, "gemm: GeGLU epilogue needs N %% 256 == 0 (N=%d)", N);
     const int n_out = epi == VF_EPI_BIAS_GEGLU_BF16 ? N / 2 : N;
-    VF_REQUIRE(ldo >= n_out && (ldo % 8) == 0, "gemm: bad output stride %d", ldo);
+    const bool out_f32 = epi == VF_EPI_BIAS_RESID_F32 || epi == VF_EPI_BIAS_F32;
+    VF_REQUIRE(out || (out_f32 && out2), "gemm: no output buffer (only the fp32 epilogues may write their bf16 mirror alone)");
+    VF_REQUIRE(!out || (ldo >= n_out && (ldo % 8) == 0), "gemm: bad output stride %d", ldo);
+    VF_REQUIRE(!resid_bf16 || epi == VF_EPI_BIAS_RESID_F32, "gemm: a bf16 residual needs the residual epilogue");
     GemmParams p;
-    p.M = M; p.N = N; p.K = K; p.bias = bias; p.resid = resid; p.ldr = ldr; p.out = out; p.ldo = ldo;
+    p.M = M; p.N = N; p.K = K; p.bias = bias; p.ldr = ldr; p.out = out; p.ldo = ldo;
+    p.resid = resid_bf16 ? nullptr : reinterpret_cast<const float*>(resid);
+    p.resid16 = resid_bf16 ? reinterpret_cast<const __nv_bfloat16*>(resid) : nullptr;
     p.out2 = reinterpret_cast<__nv_bfloat16*>(out2); p.ldo2 = ldo2;
     const bool out_bf16 = epi == VF_EPI_BIAS_BF16 || epi == VF_EPI_BIAS_GEGLU_BF16 || epi == VF_EPI_BIAS_GELU_BF16;
     VF_REQUIRE(!ln_stats || (out_bf16 && ln_colsum && ln_dim > 0 && ln_parts > 0),
@@ -592,8 +662,8 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
     CUtensorMap ta, tb, tr;
     if (make_tmap_kmajor(&ta, A, M, K, lda, BM)) return -1;
     if (make_tmap_kmajor(&tb, W, N, K, ldw, BN)) return -1;
-    if (epi == VF_EPI_BIAS_RESID_F32 && resid) {
-        if (make_tmap_resid(&tr, resid, M, N, ldr)) return -1;
+    if (epi == VF_EPI_BIAS_RESID_F32 && resid && !resid_bf16 && g_resid_prefetch) {
+        if (make_tmap_resid(&tr, reinterpret_cast<const float*>(resid), M, N, ldr)) return -1;
     } else {
         tr = ta;                                                       // never dereferenced
     }

@@ -225,14 +225,15 @@ class Engine:
         s1 = ws.get("r_s1", (n_tok, P, 2), torch.float32)                # ... of x1
         qkv = ws.get("r_qkv", (n_tok, 3 * d), torch.bfloat16)
         a = ws.get("r_a", (n_tok, d), torch.bfloat16)
-        x1 = ws.get("r_x1", (n_tok, d), torch.float32)
         f = ws.get("r_f", (n_tok, W.layers[0]["g2"].w.shape[1]), torch.bfloat16)
         ops.rowstats(x, xs0, xb)
         for li, L in enumerate(W.layers):
             ops.gemm(xb, L["qkv"].w, EPI_BIAS_BF16, bias=L["qkv"].b, out=qkv,
                      ln=L["qkv"].ln(xs0 if li == 0 else xs))                                           # Wqkv(norm1(x))
             plan.run(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], H, hd, W.slopes, a)
-            ops.gemm(a, L["out"].w, EPI_BIAS_RESID_F32, bias=L["out"].b, resid=x, out=x1, out2=xb, stats_out=s1)
+            # x1 = x + MHA(..) is consumed only through norm2 -> linear_geglu_1 (the layer's residual is its INPUT,
+            # modules.py:189): it exists as a bf16 mirror + row statistics only
+            ops.gemm(a, L["out"].w, EPI_BIAS_RESID_F32, bias=L["out"].b, resid=x, out2=xb, stats_out=s1, mirror_only=True)
             ops.gemm(xb, L["g1"].w, EPI_BIAS_GEGLU_BF16, bias=L["g1"].b, out=f, ln=L["g1"].ln(s1))      # GeGLU(norm2(x1))
             ops.gemm(f, L["g2"].w, EPI_BIAS_RESID_F32, bias=L["g2"].b, resid=x, out=x, out2=xb, stats_out=xs)  # + layer input
         return ops.masked_meanpool(x, cu, n_win)
@@ -247,15 +248,16 @@ class Engine:
         xs_out = ws.get(tag + "_xs", (M, ops.stats_parts(D), 2), torch.float32)  # ... of the layer output
         qkv = ws.get(tag + "_qkv", (M, 3 * D), torch.bfloat16)
         a = ws.get(tag + "_a", (M, D), torch.bfloat16)
-        x1 = ws.get(tag + "_x1", (M, D), torch.float32)
         f = ws.get(tag + "_f", (M, L["g2"].w.shape[1]), torch.bfloat16)
         ops.gemm(xb, L["qkv"].w, EPI_BIAS_BF16, bias=L["qkv"].b, out=qkv, ln=L["qkv"].ln(xs))          # Wqkv(norm1(x))
         self_attn(qkv, a)
-        ops.gemm(a, L["out"].w, EPI_BIAS_RESID_F32, bias=L["out"].b, resid=x, out=x1, out2=hb, stats_out=s1)
+        # x1 = x + selfMHA(..) and x1' = x1 + crossMHA(..) are consumed only through norm2 / norm3 -> bf16 GEMM and as
+        # each other's residual (the layer's own residual is its INPUT, layers.py:163): bf16 mirror + statistics only
+        ops.gemm(a, L["out"].w, EPI_BIAS_RESID_F32, bias=L["out"].b, resid=x, out2=hb, stats_out=s1, mirror_only=True)
         q = qkv[:, :D]                                                  # reuse the qkv buffer for the cross query
         ops.gemm(hb, L["q"].w, EPI_BIAS_BF16, bias=L["q"].b, out=q, ln=L["q"].ln(s1))                  # Wq(norm2(x1))
         cross_attn(q, a)
-        ops.gemm(a, L["out2"].w, EPI_BIAS_RESID_F32, bias=L["out2"].b, resid=x1, out=x1, out2=hb, stats_out=s1)
+        ops.gemm(a, L["out2"].w, EPI_BIAS_RESID_F32, bias=L["out2"].b, resid=hb, out2=hb, stats_out=s1, mirror_only=True)
         ops.gemm(hb, L["g1"].w, EPI_BIAS_GEGLU_BF16, bias=L["g1"].b, out=f, ln=L["g1"].ln(s1))         # GeGLU(norm3(x1))
         ops.gemm(f, L["g2"].w, EPI_BIAS_RESID_F32, bias=L["g2"].b, resid=x, out=x, out2=xb, stats_out=xs_out)
         return xs_out

@@ -66,21 +66,25 @@ def _chk_bf16(t):
     assert t.is_cuda and t.dtype == torch.bfloat16 and t.stride(-1) == 1, "expected a row-major CUDA bf16 tensor"
 
 
-def gemm(a, w, epilogue, bias=None, resid=None, out=None, out2=None, ln=None, stats_out=None):
+def gemm(a, w, epilogue, bias=None, resid=None, out=None, out2=None, ln=None, stats_out=None, mirror_only=False):
     """out = epilogue(a[M,K] @ w[N,K]^T).  a, w bf16; bias fp32 [N]; resid fp32 [M,N].
     ln = (stats fp32 [M,P,2], colsum fp32 [N], width, eps): LayerNorm of the rows `a` mirrors, folded into the epilogue
     (w, bias must be the gamma/beta-folded ones); stats_out fp32 [M, stats_parts(N), 2]: partial row (sum, sum of
-    squares) of an fp32 output."""
+    squares) of an fp32 output.  resid may be bf16 (residual epilogue); mirror_only: an fp32 epilogue writes only its
+    bf16 mirror out2 (and the statistics), no fp32 output."""
     _chk_bf16(a); _chk_bf16(w)
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K
     n_out = N // 2 if epilogue == EPI_BIAS_GEGLU_BF16 else N
-    if out is None:
-        out = torch.empty((M, n_out), dtype=_OUT_DTYPE[epilogue], device=a.device)
-    assert out.dtype == _OUT_DTYPE[epilogue] and out.shape == (M, n_out) and out.stride(1) == 1
+    if mirror_only:
+        assert out is None and out2 is not None and _OUT_DTYPE[epilogue] == torch.float32
+    else:
+        if out is None:
+            out = torch.empty((M, n_out), dtype=_OUT_DTYPE[epilogue], device=a.device)
+        assert out.dtype == _OUT_DTYPE[epilogue] and out.shape == (M, n_out) and out.stride(1) == 1
     if resid is not None:
-        assert resid.dtype == torch.float32 and resid.shape == (M, N) and resid.stride(1) == 1
+        assert resid.dtype in (torch.float32, torch.bfloat16) and resid.shape == (M, N) and resid.stride(1) == 1
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
     if out2 is not None:
@@ -97,11 +101,13 @@ def gemm(a, w, epilogue, bias=None, resid=None, out=None, out2=None, ln=None, st
         assert stats_out.dtype == torch.float32 and stats_out.shape == (M, stats_parts(N), 2) and stats_out.is_contiguous()
     with _timed("gemm", 2.0 * M * N * K):
         check(_lib.lib().vf_gemm_bf16_ln(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, epilogue, ptr(bias),
-                                         ptr(resid), resid.stride(0) if resid is not None else 0, ptr(out),
-                                         out.stride(0), ptr(out2), out2.stride(0) if out2 is not None else 0,
+                                         ptr(resid), int(resid is not None and resid.dtype == torch.bfloat16),
+                                         resid.stride(0) if resid is not None else 0, ptr(out),
+                                         out.stride(0) if out is not None else 0, ptr(out2),
+                                         out2.stride(0) if out2 is not None else 0,
                                          ptr(ln_stats), ln_parts, ptr(ln_colsum), int(ln_dim), float(ln_eps),
                                          ptr(stats_out), stream()))
-    return out
+    return out2 if mirror_only else out
 
 
 def stats_parts(n):
