@@ -91,11 +91,30 @@ class SlotMap:
     def __init__(self, q_lens, device, k_lens=None):
         self.q_lens = np.asarray(q_lens)
         self.k_lens = self.q_lens if k_lens is None else np.asarray(k_lens)
+        self.units = None
+
+    @classmethod
+    def from_units(cls, units, device):
+        self = cls.__new__(cls)
+        self.units = np.asarray(units, np.int64).reshape(-1, 5)
+        return self
 
 
 def attention_mc(q, k, v, slots, heads, head_dim, slopes=None, out=None):
-    return attention(q, k, v, cu_seqlens(slots.q_lens, None), cu_seqlens(slots.k_lens, None),
-                     TileMap(slots.q_lens, 128, None), heads, head_dim, slopes, out)
+    if slots.units is None:
+        return attention(q, k, v, cu_seqlens(slots.q_lens, None), cu_seqlens(slots.k_lens, None),
+                         TileMap(slots.q_lens, 128, None), heads, head_dim, slopes, out)
+    res = torch.zeros(q.shape[0], heads * head_dim)
+    for qrow, nrows, krow, Sk, qpos0 in slots.units.tolist():        # explicit slot records (include/vf_b200.h)
+        qq = q[qrow:qrow + nrows].float().reshape(-1, heads, head_dim)
+        kk = k[krow:krow + Sk].float().reshape(-1, heads, head_dim)
+        vv = v[krow:krow + Sk].float().reshape(-1, heads, head_dim)
+        sc = torch.einsum("thd,shd->hts", qq, kk) / math.sqrt(head_dim)
+        if slopes is not None:
+            i = qpos0 + torch.arange(nrows)[:, None]; j = torch.arange(Sk)[None, :]
+            sc = sc - slopes[:, None, None] * (i - j).abs()[None]
+        res[qrow:qrow + nrows] = torch.einsum("hts,shd->thd", sc.softmax(-1), vv).reshape(-1, heads * head_dim)
+    return _store(out, res) if out is not None else res.bfloat16()
 
 
 TC_BLOCK_M = 512

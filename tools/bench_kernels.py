@@ -9,6 +9,10 @@ import numpy as np
 import torch
 
 sys.path.insert(0, ".")
+import os  # noqa: E402
+from variantformer_b200 import _lib  # noqa: E402
+if os.environ.get("VF_BENCH_LIB"):                  # A/B experiments: a differently compiled build of the same library
+    _lib.LIB_PATH = os.path.abspath(os.environ["VF_BENCH_LIB"])
 from variantformer_b200 import ops  # noqa: E402
 from variantformer_b200._lib import EPI_BIAS_BF16, EPI_BIAS_GEGLU_BF16, EPI_BIAS_RESID_F32  # noqa: E402
 

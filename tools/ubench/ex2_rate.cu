@@ -26,6 +26,42 @@ __global__ void k(float* out, int iters, float seed) {
                 p = fmaf(p, f, 1.0f);
                 a[i] = __int_as_float(__float_as_int(p) + ((int)fl << 23)) * 1e-3f;
             }
+            if (MODE == 5) {   // one ex2 and four dependent-free FFMA per element: the softmax mix
+                asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+                float t = __uint_as_float(h[i]);
+                t = fmaf(t, 1.0001f, 0.5f); t = fmaf(t, 0.9999f, -0.5f); t = fmaf(t, 1.0001f, 0.25f); t = fmaf(t, 0.9999f, -0.25f);
+                h[i] = __float_as_uint(t);
+            }
+            if (MODE == 6) {   // FFMA only, 4 per element
+                float t = __uint_as_float(h[i]);
+                t = fmaf(t, 1.0001f, 0.5f); t = fmaf(t, 0.9999f, -0.5f); t = fmaf(t, 1.0001f, 0.25f); t = fmaf(t, 0.9999f, -0.25f);
+                h[i] = __float_as_uint(t);
+            }
+            if (MODE == 7) {   // ex2 + 2 FFMA + 2 FMNMX (fma pipe + alu pipe)
+                asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+                float t = __uint_as_float(h[i]);
+                t = fmaf(t, 1.0001f, 0.5f); t = fmaxf(t, a[(i + 1) & 7]); t = fmaf(t, 0.9999f, -0.5f); t = fminf(t, 3.0f);
+                h[i] = __float_as_uint(t);
+            }
+            if (MODE == 8) {   // ex2 + 1 FFMA + 1 FADD + half F2FP: the minimal softmax mix
+                asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+                float t = __uint_as_float(h[i]);
+                t = fmaf(t, 1.0001f, 0.5f); t = t + a[(i + 3) & 7];
+                h[i] = __float_as_uint(t);
+            }
+            if (MODE == 9) {   // ex2 + half a cvt.rn.bf16x2.f32 per element (the P pack)
+                asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+                if (i & 1) { uint32_t pk; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(a[i]), "f"(a[i - 1])); h[i] ^= pk; }
+            }
+            if (MODE == 10) {  // cvt.rn.bf16x2.f32 only
+                uint32_t pk; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(a[i]), "f"(a[(i + 1) & 7])); h[i] ^= pk;
+            }
+            if (MODE == 11) {  // full softmax mix: FFMA, ex2, FADD, half cvt, half FMNMX3-like
+                float x = fmaf(__uint_as_float(h[i]), 1.0001f, a[(i + 1) & 7]);
+                float p; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(x));
+                a[i] += p;
+                if (i & 1) { uint32_t pk; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(p), "f"(x)); h[i] ^= pk; }
+            }
             if (MODE == 4) {   // cvt pair + packed ex2 (the softmax inner step)
                 uint32_t pk;
                 asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(a[i]), "f"(a[(i + 1) & 7]));
@@ -42,24 +78,35 @@ __global__ void k(float* out, int iters, float seed) {
 }
 
 template <int MODE>
-void run(const char* name, int elems_per_instr) {
+void run(const char* name, int elems_per_instr, int threads = 1024) {
     float* d; cudaMalloc(&d, 148 * 1024 * sizeof(float));
     const int iters = 4096;
-    k<MODE><<<148, 1024>>>(d, 16, 1.0f);
+    k<MODE><<<148, threads>>>(d, 16, 1.0f);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    k<MODE><<<148, 1024>>>(d, iters, 1.0f);
+    k<MODE><<<148, threads>>>(d, iters, 1.0f);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     float cyc; cudaMemcpy(&cyc, d, 4, cudaMemcpyDeviceToHost);
-    double el = 1024.0 * iters * 8 * elems_per_instr;
-    printf("%-28s %8.3f ms  %7.2f elements/clk/SM (clock64)  %.2f T elem/s chip\n", name, ms, el / cyc,
+    double el = (double)threads * iters * 8 * elems_per_instr;
+    printf("[%4d thr] %-28s %8.3f ms  %7.2f elements/clk/SM (clock64)  %.2f T elem/s chip\n", threads, name, ms, el / cyc,
            el * 148 / ms / 1e9);
     cudaFree(d);
 }
 
 int main() {
     run<0>("ex2.approx.ftz.f32", 1);
+    run<0>("ex2.approx.ftz.f32", 1, 512);
+    run<0>("ex2.approx.ftz.f32", 1, 256);
+    run<0>("ex2.approx.ftz.f32", 1, 128);
+    run<5>("ex2 + 4 FFMA interleaved", 1, 512);
+    run<5>("ex2 + 4 FFMA interleaved", 1, 1024);
+    run<6>("4 FFMA (no ex2)", 1, 512);
+    run<9>("ex2 + 0.5 cvt.bf16x2", 1, 512);
+    run<10>("cvt.bf16x2 only (per instr)", 1, 512);
+    run<11>("FFMA+ex2+FADD+0.5cvt", 1, 512);
+    run<7>("ex2 + 2 FFMA + 2 FMNMX", 1, 512);
+    run<8>("ex2 + FFMA + FADD", 1, 512);
     run<1>("ex2.approx.f16x2", 2);
     run<2>("ex2.approx.ftz.bf16x2", 2);
     run<3>("poly3 exp2 (FMA pipe)", 1);

@@ -91,6 +91,15 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // K=512 GEMMs 5-15 % slower), so the default stays.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
+#ifdef VF_MBAR_HINT_NS
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)VF_MBAR_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
@@ -98,6 +107,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+#endif
     return ok != 0;
 }
 // Non-blocking test of a phase.
@@ -118,6 +128,10 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
     return t;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef VF_MBAR_SIMPLE
+    while (!mbar_try_wait(bar, parity)) {}
+    return;
+#endif
     if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
     uint64_t t0 = 0;

@@ -198,7 +198,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // Local copy: the fields live in registers.  Read through the parameter itself they are re-fetched from the
     // constant bank (LDCU, a scoreboard wait each) after every asm statement with a memory clobber — in the epilogue
     // that is several times per slab.
+#ifndef VF_GEMM_NO_PARAM_COPY
     const GemmParams p = p_in;
+#else
+    const GemmParams& p = p_in;
+#endif
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;                                  // kStages x 16 KB

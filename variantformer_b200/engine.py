@@ -39,9 +39,12 @@ class AttnPlan:
     """Host-built work decomposition of one attention problem (all sequences of a slab, one launch).  The kernel is
     chosen per ROLE and head size, never per batch content, so results do not depend on how genes are batched."""
 
-    def __init__(self, q_lens, device, head_dim, k_lens=None):
+    def __init__(self, q_lens, device, head_dim, k_lens=None, units=None):
         self.mc = ATTENTION_IMPL == "mc" and head_dim in (48, 64)
-        if self.mc:
+        if units is not None:                                  # explicit slot records (mc kernel only)
+            assert self.mc
+            self.slots = ops.SlotMap.from_units(units, device)
+        elif self.mc:
             self.slots = ops.SlotMap(q_lens, device, k_lens=k_lens)
         else:
             kl = q_lens if k_lens is None else k_lens
@@ -262,6 +265,35 @@ class Engine:
         ops.gemm(f, L["g2"].w, EPI_BIAS_RESID_F32, bias=L["g2"].b, resid=x, out=x, out2=xb, stats_out=xs_out)
         return xs_out
 
+    # ---------------------------------------------------------------- last gene layer, needed rows only
+    def _gene_layer_last(self, L, s, x, xb, xs, cre_bf, kv):
+        """The last ContextFlashAttentionEncoderLayer of the gene stream restricted to the rows whose output is read
+        (registry rows + VEP token rows): K/V of the self-attention still come from every row, all the rest runs on
+        `need` rows.  Same arithmetic as _layer on those rows.  -> fp32 [n_need, D]."""
+        ws, w = self.ws, self.w
+        D, H, hd = w.D, w.H, w.hd
+        M, R = x.shape[0], s["n_need"]
+        rows = s["last_rows"]
+        qkvw = L["qkv"]
+        kvs = ws.get("g_qkv", (M, 3 * D), torch.bfloat16)[:, D:]            # K | V of every row (Q columns unused)
+        ops.gemm(xb, qkvw.w[D:], EPI_BIAS_BF16, bias=qkvw.b[D:], out=kvs, ln=(xs, qkvw.cs[D:], qkvw.dim, qkvw.eps))
+        xR, xbR = ops.gather_rows(x, None, rows, want_f32=True, want_bf16=True)
+        P = xs.shape[1]
+        stR, _ = ops.gather_rows(xs.view(M, 2 * P), None, rows)
+        stR = stR.view(R, P, 2)
+        q = ops.gemm(xbR, qkvw.w[:D], EPI_BIAS_BF16, bias=qkvw.b[:D], ln=(stR, qkvw.cs[:D], qkvw.dim, qkvw.eps))
+        a = torch.empty((R, D), dtype=torch.bfloat16, device=x.device)
+        s["plan_last_self"].run(q, kvs[:, :D], kvs[:, D:], H, hd, w.slopes, a)
+        hb = torch.empty((R, D), dtype=torch.bfloat16, device=x.device)
+        s1 = torch.empty((R, ops.stats_parts(D), 2), dtype=torch.float32, device=x.device)
+        ops.gemm(a, L["out"].w, EPI_BIAS_RESID_F32, bias=L["out"].b, resid=xR, out2=hb, stats_out=s1, mirror_only=True)
+        ops.gemm(hb, L["q"].w, EPI_BIAS_BF16, bias=L["q"].b, out=q, ln=L["q"].ln(s1))
+        ops.gemm(cre_bf, L["kv"].w, EPI_BIAS_BF16, bias=L["kv"].b, out=kv)
+        s["plan_last_cross"].run(q, kv[:, :D], kv[:, D:], H, hd, None, a)
+        ops.gemm(a, L["out2"].w, EPI_BIAS_RESID_F32, bias=L["out2"].b, resid=hb, out2=hb, stats_out=s1, mirror_only=True)
+        f = ops.gemm(hb, L["g1"].w, EPI_BIAS_GEGLU_BF16, bias=L["g1"].b, ln=L["g1"].ln(s1))
+        return ops.gemm(f, L["g2"].w, EPI_BIAS_RESID_F32, bias=L["g2"].b, resid=xR, out=xR)
+
     # ---------------------------------------------------------------- slab preparation (host bookkeeping + H2D)
     def prepare(self, cre_tokens, cre_masks, gene_tokens, gene_masks, tissues, ref_labels,
                 cre_token_position=None, gene_token_position=None, lens=None):
@@ -314,9 +346,33 @@ class Engine:
             s["logc"] = up(np.log(counts), np.float32)
         reg_rows = np.cumsum(seq_lens) - seq_lens
         s["reg_idx"] = up(reg_rows, np.int32)
+        # Last gene layer: only the registry rows (and the VEP token rows) of its output are ever read, so everything
+        # after the K/V projection of its self-attention runs on those rows alone (exact).  `need` lists them; each is a
+        # one-row query tile against its own sequence (ALiBi position = its offset), and the rows of one gene form
+        # query tiles of the stacked cross-attention.
+        n_seq = len(seq_lens)
+        need_seq = np.arange(n_seq); need_off = np.zeros(n_seq, np.int64)
         if gene_token_position is not None:
-            gp = np.repeat(np.asarray([int(p) for p in gene_token_position]) + 1, T)   # +1: registry token (:665-666)
-            s["gene_pos_idx"] = up(reg_rows + gp, np.int32)
+            gp = np.repeat(np.asarray([int(p) for p in gene_token_position]) + 1, T)      # +1: registry token
+            need_seq = np.concatenate([need_seq, np.arange(n_seq)]); need_off = np.concatenate([need_off, gp])
+        s["last_rows"] = up(reg_rows[need_seq] + need_off, np.int32)
+        s["n_need"] = int(len(need_seq))
+        if ATTENTION_IMPL == "mc" and self.w.hd in (48, 64):
+            k = np.arange(len(need_seq))
+            s["plan_last_self"] = AttnPlan(None, dev, self.w.hd, units=np.stack(
+                [k, np.ones_like(k), reg_rows[need_seq], seq_lens[need_seq], need_off], 1))
+            gene_of = np.repeat(np.arange(B), T)[need_seq]                                  # gene of every needed row
+            cu_cre_np = np.concatenate([[0], np.cumsum(C)])
+            units = []
+            start = 0
+            for i in range(1, len(k) + 1):                                                 # runs of one gene, <= 128 rows
+                if i == len(k) or gene_of[i] != gene_of[start] or i - start == 128:
+                    g = gene_of[start]
+                    units.append([start, i - start, cu_cre_np[g], C[g], 0])
+                    start = i
+            s["plan_last_cross"] = AttnPlan(None, dev, self.w.hd, units=np.asarray(units))
+        if gene_token_position is not None:
+            s["gene_pos_idx"] = up(reg_rows + gp, np.int32)                                 # (:665-666)
         if cre_token_position is not None:
             c_off = np.concatenate([[0], np.cumsum(C)])[:-1]
             s["cre_pos_idx"] = up(np.repeat(c_off + np.asarray([int(p) for p in cre_token_position]), T), np.int32)
@@ -364,20 +420,32 @@ class Engine:
                 ops.label_attention(q, L["kv9"], s["logc"], s["row_seq"], H, hd, out=out)
             st["c"] = self._layer(L, cx, cre_bf, st["c"], nC, cre_self, cross, "c")
 
+        prune_last = "plan_last_self" in s and w.NL > 1
         gene_layer(w.gene_layers[0])
         for i in range(w.NL - 1):
             cre_layer(w.cre_layers[i])
-            gene_layer(w.gene_layers[i + 1])
+            if i + 1 < w.NL - 1 or not prune_last:
+                gene_layer(w.gene_layers[i + 1])
+        n_reg = s["reg_idx"].numel()
+        if prune_last:
+            last = self._gene_layer_last(w.gene_layers[w.NL - 1], s, gx, gxb, st["g"], cre_bf, kv)
+            emb = last[:n_reg]
+            emb_bf = ops.cast_bf16(emb.contiguous())
+        else:
+            last = None
+            emb, emb_bf = ops.gather_rows(gx, None, s["reg_idx"], want_f32=True, want_bf16=True)
 
         # ---- registry rows -> embeddings -> head ----
-        emb, emb_bf = ops.gather_rows(gx, None, s["reg_idx"], want_f32=True, want_bf16=True)
         h1 = ops.gemm(emb_bf, w.h0.w, EPI_BIAS_F32, bias=w.h0.b)
         h1n = ops.layernorm(h1, w.hn.g, w.hn.b, gelu=True)
         h2 = ops.gemm(h1n, w.h4.w, EPI_BIAS_GELU_BF16, bias=w.h4.b)
         pred = ops.head_out(h2, w.h6_w, w.h6_b, softplus=True)
         out = {"pred": pred, "emb": emb, "T": s["T"].tolist()}
         if "gene_pos_idx" in s:
-            out["gene_token_embedding"], _ = ops.gather_rows(gx, None, s["gene_pos_idx"])
+            if last is not None:
+                out["gene_token_embedding"] = last[n_reg:]
+            else:
+                out["gene_token_embedding"], _ = ops.gather_rows(gx, None, s["gene_pos_idx"])
         if "cre_pos_idx" in s:
             out["cre_token_embedding"], _ = ops.gather_rows(cx, None, s["cre_pos_idx"])
         return out

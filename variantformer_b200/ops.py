@@ -218,6 +218,19 @@ class SlotMap:
         self.n_items = int(items.shape[0])
         self.table = torch.from_numpy(np.ascontiguousarray(items)).to(device, non_blocking=True)
 
+    @classmethod
+    def from_units(cls, units, device):
+        """units: int array [n, 5] of explicit slot records {q row, valid rows, first key row, keys, ALiBi position of
+        row 0}; consecutive units are paired into items (units with the same key range share their K/V stream)."""
+        self = cls.__new__(cls)
+        units = np.asarray(units, np.int64).reshape(-1, 5)
+        self.qk_pairs = float((units[:, 1] * units[:, 3]).sum())
+        rec = np.zeros((len(units) + (len(units) & 1), 8), np.int32)
+        rec[:len(units), :5] = units
+        self.n_items = rec.shape[0] // 2
+        self.table = torch.from_numpy(np.ascontiguousarray(rec.reshape(-1, 2, 8))).to(device, non_blocking=True)
+        return self
+
 
 def attention_mc(q, k, v, slots: SlotMap, heads, head_dim, slopes=None, out=None):
     """Varlen attention on the two-CTAs-per-SM tcgen05 kernel (vf_attention_mc_varlen)."""
