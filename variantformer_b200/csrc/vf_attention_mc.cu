@@ -129,34 +129,42 @@ __device__ __forceinline__ void softmax_tile(uint32_t (&r)[64], uint32_t o_addr,
     } else {
         exponents<0>(r, scale, -base, 0.f, 0.f, d0, nvalid, mx);
     }
-    // P buffer free <=> the PV that read it (this slot's previous step) has retired; that PV is also the last writer
-    // of O_s, so O_s may be rescaled below
-    mbar_wait(p_empty_bar, p_empty_parity);
-    tc_fence_after();
+    // The PV of this slot's previous step is the last reader of the P buffer and the last writer of O_s.  It was issued
+    // at the end of the previous tile, so waiting for it HERE (before the exponentials) can stall every softmax warp
+    // of the slot; only a raise of the reference maximum needs it this early (it rescales O_s).  The common path
+    // takes the exponentials first, packed into the registers the scores occupied, and waits right before the stores.
+    bool waited = false;
     if (first || __any_sync(0xffffffffu, mx > kLazyThreshold)) {
         // first tile: the exact row maximum becomes the reference (may be negative).  later: raise by max(mx, 0).
         const float delta = first ? mx : fmaxf(mx, 0.f);
         const float corr = first ? 0.f : ex2_approx(-delta);
         l *= corr;
-        if (!first) rescale_o<HD>(o_addr, corr);
+        if (!first) {
+            mbar_wait(p_empty_bar, p_empty_parity);
+            tc_fence_after();
+            waited = true;
+            rescale_o<HD>(o_addr, corr);
+        }
         m_ref = base + delta;
 #pragma unroll
         for (int e = 0; e < 64; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) - delta);
     }
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int q8 = 0; q8 < 8; ++q8) {                          // 8 scores -> one 16-byte chunk of the P row
-        uint32_t pk[4];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            const float p0 = ex2_approx(__uint_as_float(r[q8 * 8 + 2 * h]));
-            const float p1 = ex2_approx(__uint_as_float(r[q8 * 8 + 2 * h + 1]));
-            acc[h] += p0 + p1;
-            pk[h] = pack_bf16x2(p0, p1);
-        }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + ((q8 ^ (row & 7)) * 16)), "r"(pk[0]),
-                     "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+    for (int i = 0; i < 32; ++i) {                            // r[i] <- bf16x2(p[2i], p[2i+1]); i <= 2i: in place
+        const float p0 = ex2_approx(__uint_as_float(r[2 * i]));
+        const float p1 = ex2_approx(__uint_as_float(r[2 * i + 1]));
+        acc[i & 3] += p0 + p1;
+        r[i] = pack_bf16x2(p0, p1);
     }
+    if (!waited) {
+        mbar_wait(p_empty_bar, p_empty_parity);
+        tc_fence_after();
+    }
+#pragma unroll
+    for (int q8 = 0; q8 < 8; ++q8)                            // 8 probabilities -> one 16-byte chunk of the P row
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + ((q8 ^ (row & 7)) * 16)), "r"(r[q8 * 4]),
+                     "r"(r[q8 * 4 + 1]), "r"(r[q8 * 4 + 2]), "r"(r[q8 * 4 + 3]) : "memory");
     l += (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
 

@@ -365,10 +365,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             bg.x = fmaf(ln_c, sg.x, bg.x); bg.y = fmaf(ln_c, sg.y, bg.y);
                             bg.z = fmaf(ln_c, sg.z, bg.z); bg.w = fmaf(ln_c, sg.w, bg.w);
                         }
-                        v[j + 0] = fmaf(__uint_as_float(ru[i & 1][j + 0]), ln_a, bu.x) * gelu_erf(fmaf(__uint_as_float(rg[i & 1][j + 0]), ln_a, bg.x));
-                        v[j + 1] = fmaf(__uint_as_float(ru[i & 1][j + 1]), ln_a, bu.y) * gelu_erf(fmaf(__uint_as_float(rg[i & 1][j + 1]), ln_a, bg.y));
-                        v[j + 2] = fmaf(__uint_as_float(ru[i & 1][j + 2]), ln_a, bu.z) * gelu_erf(fmaf(__uint_as_float(rg[i & 1][j + 2]), ln_a, bg.z));
-                        v[j + 3] = fmaf(__uint_as_float(ru[i & 1][j + 3]), ln_a, bu.w) * gelu_erf(fmaf(__uint_as_float(rg[i & 1][j + 3]), ln_a, bg.w));
+                        v[j + 0] = fmaf(__uint_as_float(ru[i & 1][j + 0]), ln_a, bu.x) * gelu_erf_fast(fmaf(__uint_as_float(rg[i & 1][j + 0]), ln_a, bg.x));
+                        v[j + 1] = fmaf(__uint_as_float(ru[i & 1][j + 1]), ln_a, bu.y) * gelu_erf_fast(fmaf(__uint_as_float(rg[i & 1][j + 1]), ln_a, bg.y));
+                        v[j + 2] = fmaf(__uint_as_float(ru[i & 1][j + 2]), ln_a, bu.z) * gelu_erf_fast(fmaf(__uint_as_float(rg[i & 1][j + 2]), ln_a, bg.z));
+                        v[j + 3] = fmaf(__uint_as_float(ru[i & 1][j + 3]), ln_a, bu.w) * gelu_erf_fast(fmaf(__uint_as_float(rg[i & 1][j + 3]), ln_a, bg.w));
                     }
                     float4 none[8];
                     epilogue_store_slab<EPI>(p, stage_out, row0, out0 + c * 32, n_out, v, lane, none, rs);
