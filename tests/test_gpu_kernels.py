@@ -54,7 +54,7 @@ def test_gemm(M, N, K, epi):
         assert torch.allclose(out2.float(), want, atol=2e-2, rtol=2e-2), _describe_mismatch(out2.float(), want, 2e-2)
 
 
-@pytest.mark.parametrize("M,K", [(128, 512), (1000, 1536), (333, 192)])
+@pytest.mark.parametrize("M,K", [(128, 512), (1000, 1536), (333, 192), (2500, 1536), (1300, 1024)])
 def test_gemm_geglu(M, K):
     N = 2048
     g = torch.Generator(device="cpu").manual_seed(M + K)

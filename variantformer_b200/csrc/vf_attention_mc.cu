@@ -149,6 +149,8 @@ __device__ __forceinline__ void softmax_tile(uint32_t (&r)[64], uint32_t o_addr,
 #pragma unroll
         for (int e = 0; e < 64; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) - delta);
     }
+    // (Serialising this section per scheduler with a lock — to break up convoys on the MUFU pipe — was measured 1.6x
+    // SLOWER: one warp alone does not keep the pipe busy.)
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 32; ++i) {                            // r[i] <- bf16x2(p[2i], p[2i+1]); i <= 2i: in place

@@ -33,6 +33,7 @@
 namespace vf {
 
 constexpr int BM = 128, BN = 256, BK = 64, kStages = 4;
+constexpr int kStagesPair = 6;                        // CTA-pair kernel: 6 x 32 KB stages in the same shared memory
 constexpr int kEpiWarps = 8;                          // two warps per TMEM lane quadrant
 constexpr int kFirstEpiWarp = 4;                      // warpgroup 0 = TMA + MMA (+2 idle warps), warpgroups 1-2 = epilogue
 constexpr int kGemmThreads = (kFirstEpiWarp + kEpiWarps) * 32;
@@ -191,8 +192,12 @@ __device__ __forceinline__ void epilogue_store_slab(const GemmParams& p, uint32_
     }
 }
 
-template <int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// CTAS = 1: one CTA per 128 x 256 tile.  CTAS = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256 x 256
+// tile: each CTA stages its own 128 A rows and HALF of the W rows (32 KB per stage instead of 48: a third less
+// L2 -> SM operand traffic and room for more stages), the pair leader issues M=256 MMAs that read both CTAs' shared
+// memory and write each CTA's 128 accumulator rows into its own TMEM; every CTA runs its own epilogue.
+template <int EPI, int CTAS>
+__global__ void __cluster_dims__(CTAS, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmR, const GemmParams p_in) {
     // Local copy: the fields live in registers.  Read through the parameter itself they are re-fetched from the
@@ -205,18 +210,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #endif
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* smem_a = smem;                                  // kStages x 16 KB
-    uint8_t* smem_b = smem + kStages * kABytes;              // kStages x 32 KB
-    uint8_t* smem_out = smem + kStages * kStageBytes;        // kEpiWarps x 4 KB staging tiles
+    constexpr int kStg = CTAS == 2 ? kStagesPair : kStages;
+    constexpr uint32_t kBBytesC = kBBytes / CTAS, kStageBytesC = kABytes + kBBytesC;
+    uint8_t* smem_a = smem;                                  // kStg x 16 KB
+    uint8_t* smem_b = smem + kStg * kABytes;                 // kStg x 32 KB (16 KB per CTA of a pair)
+    uint8_t* smem_out = smem + kStg * kStageBytesC;          // kEpiWarps x 4 KB staging tiles
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + kEpiWarps * kStageOutBytes);
-    uint64_t* full = bars;                 // [kStages]
-    uint64_t* empty = bars + kStages;      // [kStages]
-    uint64_t* tmem_full = bars + 2 * kStages;       // [2]
-    uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    uint64_t* full = bars;                 // [kStg]
+    uint64_t* empty = bars + kStg;         // [kStg]
+    uint64_t* tmem_full = bars + 2 * kStg;          // [2]
+    uint64_t* tmem_empty = bars + 2 * kStg + 2;     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStg + 4);
 
     const int warp = threadIdx.x >> 5;
-    const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+    // work unit = CTA (CTAS 1) or CTA pair (CTAS 2); `rank` = this CTA's half of the pair's 256 rows / 256 W rows
+    const int unit = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_units = CTAS == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;
+    const int m_tiles = (p.M + BM * CTAS - 1) / (BM * CTAS), n_tiles = (p.N + BN - 1) / BN;
     const int num_tiles = m_tiles * n_tiles;
     const int k_blocks = (p.K + BK - 1) / BK;
 
@@ -224,13 +235,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if constexpr (EPI == VF_EPI_BIAS_RESID_F32) tma_prefetch_desc(&tmR);
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kEpiWarps); }
+        for (int s = 0; s < kStg; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        // the leader's tmem_empty collects the epilogue warps of BOTH CTAs of a pair
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kEpiWarps * CTAS); }
         fence_barrier_init();
     }
+    if constexpr (CTAS == 2) cluster_sync_all();             // both CTAs' barriers exist before anyone signals the peer's
     if (warp == 1) {
-        tmem_alloc(tmem_slot, kTmemCols);
-        tmem_relinquish();
+        if constexpr (CTAS == 2) { tmem_alloc_pair(tmem_slot, kTmemCols); tmem_relinquish_pair(); }
+        else { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
     }
     tc_fence_before();
     __syncthreads();
@@ -243,8 +256,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // ================= TMA producer =================
             if (elect_one()) {
                 int stage = 0; uint32_t phase = 0;
-                for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                    const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+                for (int t = unit; t < num_tiles; t += n_units) {
+                    const int m0 = (t / n_tiles) * BM * CTAS + rank * BM, n0 = (t % n_tiles) * BN;
                     if constexpr (EPI == VF_EPI_BIAS_RESID_F32) {
                         // the epilogue of this tile runs one mainloop from now: pull its residual into L2 meanwhile
                         if (p.resid && p.prefetch_resid) {   // (fp32 residual only)
@@ -255,20 +268,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                     for (int kb = 0; kb < k_blocks; ++kb) {
                         mbar_wait(&empty[stage], phase ^ 1);
-                        mbar_arrive_expect_tx(&full[stage], kStageBytes);
-                        tma_load_2d(smem_a + stage * kABytes, &tmA, &full[stage], kb * BK, m0);
-                        tma_load_2d(smem_b + stage * kBBytes, &tmB, &full[stage], kb * BK, n0);
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        if constexpr (CTAS == 2) {
+                            // all four loads of the pair complete on the LEADER's barrier, which expects their total
+                            if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * kStageBytesC);
+                            tma_load_2d_pair(smem_a + stage * kABytes, &tmA, &full[stage], kb * BK, m0);
+                            tma_load_2d_pair(smem_b + stage * kBBytesC, &tmB, &full[stage], kb * BK, n0 + rank * (BN / 2));
+                        } else {
+                            mbar_arrive_expect_tx(&full[stage], kStageBytes);
+                            tma_load_2d(smem_a + stage * kABytes, &tmA, &full[stage], kb * BK, m0);
+                            tma_load_2d(smem_b + stage * kBBytes, &tmB, &full[stage], kb * BK, n0);
+                        }
+                        if (++stage == kStg) { stage = 0; phase ^= 1; }
                     }
                 }
             }
             __syncwarp();
         } else if (warp == 1) {
             // ================= MMA issuer =================
-            if (elect_one()) {
-                constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            if (rank == 0 && elect_one()) {                  // the pair's leader issues for both CTAs
+                constexpr uint32_t idesc = umma_idesc_bf16(BM * CTAS, BN);
                 int stage = 0; uint32_t phase = 0; int it = 0;
-                for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+                for (int t = unit; t < num_tiles; t += n_units, ++it) {
                     const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
                     mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
@@ -277,15 +297,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
                         const uint64_t da = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * kABytes));
-                        const uint64_t db = umma_desc_kmajor_sw128(smem_u32(smem_b + stage * kBBytes));
+                        const uint64_t db = umma_desc_kmajor_sw128(smem_u32(smem_b + stage * kBBytesC));
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             // +32 bytes per UMMA_K step inside the 128-byte swizzle row (start address is in 16 B units)
-                            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                            if constexpr (CTAS == 2) umma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                            else umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                         }
-                        umma_commit(&empty[stage]);                      // frees the smem slot when these MMAs retire
-                        if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        if constexpr (CTAS == 2) {                       // (multicast: the barrier of BOTH CTAs)
+                            umma_commit_pair(&empty[stage]);
+                            if (kb == k_blocks - 1) umma_commit_pair(&tmem_full[acc]);
+                        } else {
+                            umma_commit(&empty[stage]);                  // frees the smem slot when these MMAs retire
+                            if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
+                        }
+                        if (++stage == kStg) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -308,16 +334,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         RowStats rs;
         float4 rr4[4][8];                                     // residual of slab i of a tile (RESID epilogue only)
         if constexpr (EPI == VF_EPI_BIAS_RESID_F32) {
-            if ((int)blockIdx.x < num_tiles) {                // prime the slab stream: slabs 0 and 1 of the first tile
-                const int m0f = ((int)blockIdx.x / n_tiles) * BM, n0f = ((int)blockIdx.x % n_tiles) * BN;
+            if (unit < num_tiles) {                           // prime the slab stream: slabs 0 and 1 of the first tile
+                const int m0f = (unit / n_tiles) * BM * CTAS + rank * BM, n0f = (unit % n_tiles) * BN;
                 load_resid_slab(p, m0f + quad * 32, n0f + half * 32, lane, rr4[0]);
                 load_resid_slab(p, m0f + quad * 32, n0f + (half + 2) * 32, lane, rr4[1]);
             }
         }
         int it = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        for (int t = unit; t < num_tiles; t += n_units, ++it) {
             const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
-            const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+            const int m0 = (t / n_tiles) * BM * CTAS + rank * BM, n0 = (t % n_tiles) * BN;
             const int row0 = m0 + quad * 32;
             // LayerNorm fold: this thread's row is normalised as  ln_a * acc + ln_c * colsum[n] + bias'[n]
             float ln_a = 1.f, ln_c = 0.f;
@@ -385,9 +411,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const int c = half + 2 * i;
                     const int col0 = n0 + c * 32;
                     {   // prefetch distance 2: slab i+2 of this tile, or slab i-2 of this warp's next tile
-                        const int tn = i + 2 < kSlabs ? t : t + (int)gridDim.x;
+                        const int tn = i + 2 < kSlabs ? t : t + n_units;
                         const int cn = half + 2 * ((i + 2) & 3);
-                        const int m0n = (tn / n_tiles) * BM, n0n = (tn % n_tiles) * BN;
+                        const int m0n = (tn / n_tiles) * BM * CTAS + rank * BM, n0n = (tn % n_tiles) * BN;
                         if (tn < num_tiles) load_resid_slab(p, m0n + quad * 32, n0n + cn * 32, lane, rr4[(i + 2) & 3]);
                     }
                     if (col0 < p.N) {                                     // warp-uniform
@@ -444,7 +470,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                if constexpr (CTAS == 2) mbar_arrive_leader(&tmem_empty[acc]);
+                else mbar_arrive(&tmem_empty[acc]);
+            }
             if constexpr (!epi_is_bf16<EPI>()) {
                 if (want_stats) rs.flush(p.stats_out, row0, p.M, (t % n_tiles) * 2 + half, 2 * n_tiles, lane);
             }
@@ -453,9 +482,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (CTAS == 2) cluster_sync_all();             // the leader's MMAs read the peer's shared memory until the end
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if constexpr (CTAS == 2) tmem_dealloc_pair(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -584,6 +615,10 @@ static int make_tmap_resid(CUtensorMap* tm, const float* base, int rows, int col
 static int g_num_sms = 0;
 static bool g_debug_simt = false;
 static int g_resid_prefetch = 0;
+// CTA-pair kernel for M >= g_pair_min_rows (VF_GEMM_PAIR_MIN_ROWS; 0 = never) and K >= g_pair_min_k: measured 6-12 %
+// faster than the single-CTA kernel at K = 1024 / 1536 (Wqkv 101k x 4608 x 1536: 1.03 -> 0.90 ms = 1590 TFLOP/s, cuBLAS
+// 0.91), not at K = 512 where the epilogue, not the operand traffic, is the limit.
+static int g_pair_min_rows = 1024, g_pair_min_k = 1024;
 static bool g_inited = false;
 
 template <int EPI>
@@ -591,14 +626,44 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
                      cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        VF_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        VF_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)kGemmSmem));
         attr_set = true;
     }
     const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    gemm_tcgen05_kernel<EPI><<<grid, kGemmThreads, kGemmSmem, s>>>(ta, tb, tr, p);
+    gemm_tcgen05_kernel<EPI, 1><<<grid, kGemmThreads, kGemmSmem, s>>>(ta, tb, tr, p);
     VF_LAUNCH_OK("gemm_tcgen05_kernel launch");
+    return 0;
+}
+
+// CTA-pair variant: grid = 2 x (number of pairs that can be co-scheduled, asked from the driver once)
+static int g_max_pairs = 0;
+template <int EPI>
+static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const GemmParams& p,
+                          cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        VF_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)kGemmSmem));
+        attr_set = true;
+    }
+    if (g_max_pairs == 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(g_num_sms & ~1); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = kGemmSmem;
+        cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 2;
+        at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        int n = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<EPI, 2>, &cfg);
+        g_max_pairs = (e == cudaSuccess && n > 0) ? n : g_num_sms / 2;
+        if (g_max_pairs > g_num_sms / 2) g_max_pairs = g_num_sms / 2;
+        (void)cudaGetLastError();
+    }
+    const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN - 1) / BN);
+    const int pairs = tiles < g_max_pairs ? tiles : g_max_pairs;
+    gemm_tcgen05_kernel<EPI, 2><<<2 * pairs, kGemmThreads, kGemmSmem, s>>>(ta, tb, tr, p);
+    VF_LAUNCH_OK("gemm_tcgen05_kernel (CTA pair) launch");
     return 0;
 }
 
@@ -627,6 +692,10 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
         g_debug_simt = e && e[0] == '1';
         const char* e2 = getenv("VF_GEMM_RESID_PREFETCH");
         g_resid_prefetch = e2 && e2[0] == '1';
+        const char* e3 = getenv("VF_GEMM_PAIR_MIN_ROWS");
+        if (e3) g_pair_min_rows = atoi(e3);
+        const char* e4 = getenv("VF_GEMM_PAIR_MIN_K");
+        if (e4) g_pair_min_k = atoi(e4);
         g_inited = true;
     }
     VF_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
@@ -663,13 +732,23 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
             default: return launch_simt<VF_EPI_BIAS_F32>(a, lda, w, ldw, p, stream);
         }
     }
+    const bool pair = g_pair_min_rows > 0 && M >= g_pair_min_rows && K >= g_pair_min_k;
     CUtensorMap ta, tb, tr;
     if (make_tmap_kmajor(&ta, A, M, K, lda, BM)) return -1;
-    if (make_tmap_kmajor(&tb, W, N, K, ldw, BN)) return -1;
+    if (make_tmap_kmajor(&tb, W, N, K, ldw, pair ? BN / 2 : BN)) return -1;
     if (epi == VF_EPI_BIAS_RESID_F32 && resid && !resid_bf16 && g_resid_prefetch) {
         if (make_tmap_resid(&tr, reinterpret_cast<const float*>(resid), M, N, ldr)) return -1;
     } else {
         tr = ta;                                                       // never dereferenced
+    }
+    if (pair) {
+        switch (epi) {
+            case VF_EPI_BIAS_BF16: return launch_tc_pair<VF_EPI_BIAS_BF16>(ta, tb, tr, p, stream);
+            case VF_EPI_BIAS_GEGLU_BF16: return launch_tc_pair<VF_EPI_BIAS_GEGLU_BF16>(ta, tb, tr, p, stream);
+            case VF_EPI_BIAS_RESID_F32: return launch_tc_pair<VF_EPI_BIAS_RESID_F32>(ta, tb, tr, p, stream);
+            case VF_EPI_BIAS_GELU_BF16: return launch_tc_pair<VF_EPI_BIAS_GELU_BF16>(ta, tb, tr, p, stream);
+            default: return launch_tc_pair<VF_EPI_BIAS_F32>(ta, tb, tr, p, stream);
+        }
     }
     switch (epi) {
         case VF_EPI_BIAS_BF16: return launch_tc<VF_EPI_BIAS_BF16>(ta, tb, tr, p, stream);
