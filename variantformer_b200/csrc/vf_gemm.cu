@@ -349,8 +349,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             float ln_a = 1.f, ln_c = 0.f;
             if (ln && row0 + lane < p.M) {
                 const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + (size_t)(row0 + lane) * p.ln_parts;
-                float2 st = __ldg(sp);
-                for (int i = 1; i < p.ln_parts; ++i) { const float2 t2 = __ldg(sp + i); st.x += t2.x; st.y += t2.y; }
+                float2 st = make_float2(0.f, 0.f);
+                if (p.ln_parts > 1 && p.ln_parts <= 16 && (p.ln_parts & 1) == 0) {
+                    // the row's partials as ONE batch of 16-byte loads (a dependent loop pays a memory round trip per
+                    // partial: 12 per tile for a 1536-wide stream), summed in index order.  (Requesting them a whole
+                    // tile ahead was measured: no gain, 32 more live registers.)
+                    float4 q[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        q[i] = 2 * i < p.ln_parts ? __ldg(reinterpret_cast<const float4*>(sp) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { st.x += q[i].x; st.y += q[i].y; st.x += q[i].z; st.y += q[i].w; }
+                } else {
+                    st = __ldg(sp);
+                    for (int i = 1; i < p.ln_parts; ++i) { const float2 t2 = __ldg(sp + i); st.x += t2.x; st.y += t2.y; }
+                }
                 const float mean = st.x * p.ln_inv_d;
                 const float var = fmaxf(fmaf(st.y, p.ln_inv_d, -mean * mean), 0.f);
                 ln_a = rsqrtf(var + p.ln_eps);
@@ -370,6 +383,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                 for (int i = 0; i < kSlabs; ++i) {
                     const int c = half + 2 * i;                           // 32-column slab of the 128 outputs
+                    // bias (and LayerNorm column sums) of the slab: 16-32 broadcast loads issued as ONE batch before
+                    // the TMEM wait.  Loaded next to their use they cost one L1 round trip each (8 per slab, exposed).
+                    float4 bu[8], bg[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        bu[j] = bg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.bias) {
+                            bu[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c * 32) + j);
+                            bg[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 128 + c * 32) + j);
+                        }
+                    }
+                    if (ln) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 su = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + c * 32) + j);
+                            const float4 sg = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + 128 + c * 32) + j);
+                            bu[j].x = fmaf(ln_c, su.x, bu[j].x); bu[j].y = fmaf(ln_c, su.y, bu[j].y);
+                            bu[j].z = fmaf(ln_c, su.z, bu[j].z); bu[j].w = fmaf(ln_c, su.w, bu[j].w);
+                            bg[j].x = fmaf(ln_c, sg.x, bg[j].x); bg[j].y = fmaf(ln_c, sg.y, bg[j].y);
+                            bg[j].z = fmaf(ln_c, sg.z, bg[j].z); bg[j].w = fmaf(ln_c, sg.w, bg[j].w);
+                        }
+                    }
                     tmem_ld_wait();
                     if (i + 1 < kSlabs) {
                         tmem_ld_32x32(t_row + (c + 2) * 32, ru[(i + 1) & 1]);
@@ -378,23 +413,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        float4 bu = make_float4(0.f, 0.f, 0.f, 0.f), bg = bu;
-                        if (p.bias) {
-                            bu = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c * 32 + j));
-                            bg = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 128 + c * 32 + j));
-                        }
-                        if (ln) {
-                            const float4 su = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + c * 32 + j));
-                            const float4 sg = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + 128 + c * 32 + j));
-                            bu.x = fmaf(ln_c, su.x, bu.x); bu.y = fmaf(ln_c, su.y, bu.y);
-                            bu.z = fmaf(ln_c, su.z, bu.z); bu.w = fmaf(ln_c, su.w, bu.w);
-                            bg.x = fmaf(ln_c, sg.x, bg.x); bg.y = fmaf(ln_c, sg.y, bg.y);
-                            bg.z = fmaf(ln_c, sg.z, bg.z); bg.w = fmaf(ln_c, sg.w, bg.w);
-                        }
-                        v[j + 0] = fmaf(__uint_as_float(ru[i & 1][j + 0]), ln_a, bu.x) * gelu_erf_fast(fmaf(__uint_as_float(rg[i & 1][j + 0]), ln_a, bg.x));
-                        v[j + 1] = fmaf(__uint_as_float(ru[i & 1][j + 1]), ln_a, bu.y) * gelu_erf_fast(fmaf(__uint_as_float(rg[i & 1][j + 1]), ln_a, bg.y));
-                        v[j + 2] = fmaf(__uint_as_float(ru[i & 1][j + 2]), ln_a, bu.z) * gelu_erf_fast(fmaf(__uint_as_float(rg[i & 1][j + 2]), ln_a, bg.z));
-                        v[j + 3] = fmaf(__uint_as_float(ru[i & 1][j + 3]), ln_a, bu.w) * gelu_erf_fast(fmaf(__uint_as_float(rg[i & 1][j + 3]), ln_a, bg.w));
+                        const float4 b0 = bu[j >> 2], b1 = bg[j >> 2];
+                        v[j + 0] = fmaf(__uint_as_float(ru[i & 1][j + 0]), ln_a, b0.x) * gelu_erf_fast(fmaf(__uint_as_float(rg[i & 1][j + 0]), ln_a, b1.x));
+                        v[j + 1] = fmaf(__uint_as_float(ru[i & 1][j + 1]), ln_a, b0.y) * gelu_erf_fast(fmaf(__uint_as_float(rg[i & 1][j + 1]), ln_a, b1.y));
+                        v[j + 2] = fmaf(__uint_as_float(ru[i & 1][j + 2]), ln_a, b0.z) * gelu_erf_fast(fmaf(__uint_as_float(rg[i & 1][j + 2]), ln_a, b1.z));
+                        v[j + 3] = fmaf(__uint_as_float(ru[i & 1][j + 3]), ln_a, b0.w) * gelu_erf_fast(fmaf(__uint_as_float(rg[i & 1][j + 3]), ln_a, b1.w));
                     }
                     float4 none[8];
                     epilogue_store_slab<EPI>(p, stage_out, row0, out0 + c * 32, n_out, v, lane, none, rs);
@@ -418,12 +441,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                     if (col0 < p.N) {                                     // warp-uniform
                         tmem_ld_32x32(t_row + c * 32, r);
+                        float4 bb[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            bb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (p.bias && col0 + 4 * j + 4 <= p.N) bb[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+                        }
                         tmem_ld_wait();
                         float v[32];
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (p.bias && col0 + j + 4 <= p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                            const float4 b = bb[j >> 2];
                             v[j + 0] = __uint_as_float(r[j + 0]) + b.x; v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
                             v[j + 2] = __uint_as_float(r[j + 2]) + b.z; v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
                         }
@@ -440,20 +468,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const int c = half + 2 * i;
                     const int col0 = n0 + c * 32;
                     if (col0 >= p.N) break;                               // warp-uniform
+                    float4 bb[8];                                         // bias (+ LayerNorm term) of the slab: one batch of
+#pragma unroll                                                            // broadcast loads issued before the TMEM wait
+                    for (int j = 0; j < 8; ++j) {
+                        bb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.bias && col0 + 4 * j + 4 <= p.N) bb[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+                    }
+                    if constexpr (epi_is_bf16<EPI>()) {
+                        if (ln) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                if (col0 + 4 * j + 4 <= p.N) {
+                                    const float4 sc = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0) + j);
+                                    bb[j].x = fmaf(ln_c, sc.x, bb[j].x); bb[j].y = fmaf(ln_c, sc.y, bb[j].y);
+                                    bb[j].z = fmaf(ln_c, sc.z, bb[j].z); bb[j].w = fmaf(ln_c, sc.w, bb[j].w);
+                                }
+                            }
+                        }
+                    }
                     tmem_ld_wait();
                     if (i + 1 < kSlabs && col0 + 64 < p.N) tmem_ld_32x32(t_row + (c + 2) * 32, r[(i + 1) & 1]);
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p.bias && col0 + j + 4 <= p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                        if constexpr (epi_is_bf16<EPI>()) {
-                            if (ln && col0 + j + 4 <= p.N) {
-                                const float4 sc = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0 + j));
-                                b.x = fmaf(ln_c, sc.x, b.x); b.y = fmaf(ln_c, sc.y, b.y);
-                                b.z = fmaf(ln_c, sc.z, b.z); b.w = fmaf(ln_c, sc.w, b.w);
-                            }
-                        }
+                        const float4 b = bb[j >> 2];
                         v[j + 0] = fmaf(__uint_as_float(r[i & 1][j + 0]), ln_a, b.x);
                         v[j + 1] = fmaf(__uint_as_float(r[i & 1][j + 1]), ln_a, b.y);
                         v[j + 2] = fmaf(__uint_as_float(r[i & 1][j + 2]), ln_a, b.z);
