@@ -33,6 +33,8 @@ NUM_REF_CRES = 9
 # "mc" = tcgen05/TMEM attention, two CTAs per SM, for every attention of the path (default);
 # "legacy" = the round-1 mma.sync kernel everywhere (debug cross-check only)
 ATTENTION_IMPL = os.environ.get("VF_ATTENTION", "mc")
+# run the CRE stack on its own CUDA stream, concurrently with the gene stack ("0": one stream, for A/B and debugging)
+CRE_STREAM = os.environ.get("VF_CRE_STREAM", "1") != "0"
 
 
 class AttnPlan:
@@ -242,9 +244,9 @@ class Engine:
         return ops.masked_meanpool(x, cu, n_win)
 
     # ---------------------------------------------------------------- one encoder layer of seq2gene
-    def _layer(self, L, x, xb, xs, M, self_attn, cross_attn, tag):
+    def _layer(self, L, x, xb, xs, M, self_attn, cross_attn, tag, xb_out=None):
         """ContextFlashAttentionEncoderLayer on an unpadded fp32 stream x [M, D] with its bf16 mirror xb and row
-        statistics xs (all three updated in place)."""
+        statistics xs (x updated in place; the mirror of the output goes to xb_out, by default xb itself)."""
         ws, D = self.ws, self.w.D
         hb = ws.get(tag + "_hb", (M, D), torch.bfloat16)                 # bf16 mirror of x1
         s1 = ws.get(tag + "_s1", (M, ops.stats_parts(D), 2), torch.float32)     # row statistics of x1
@@ -262,7 +264,8 @@ class Engine:
         cross_attn(q, a)
         ops.gemm(a, L["out2"].w, EPI_BIAS_RESID_F32, bias=L["out2"].b, resid=hb, out2=hb, stats_out=s1, mirror_only=True)
         ops.gemm(hb, L["g1"].w, EPI_BIAS_GEGLU_BF16, bias=L["g1"].b, out=f, ln=L["g1"].ln(s1))         # GeGLU(norm3(x1))
-        ops.gemm(f, L["g2"].w, EPI_BIAS_RESID_F32, bias=L["g2"].b, resid=x, out=x, out2=xb, stats_out=xs_out)
+        ops.gemm(f, L["g2"].w, EPI_BIAS_RESID_F32, bias=L["g2"].b, resid=x, out=x,
+                 out2=xb if xb_out is None else xb_out, stats_out=xs_out)
         return xs_out
 
     # ---------------------------------------------------------------- last gene layer, needed rows only
@@ -389,12 +392,15 @@ class Engine:
         # ---- stage 2: window encoders ----
         cre_pooled = self.seq2reg(self.cre_tok, s["ctok"], s["cmsk"], s["clens"], s["c_cu_tok"], s["c_plan_tok"])
         gene_pooled = self.seq2reg(self.gene_tok, s["gtok"], s["gmsk"], s["glens"], s["g_cu_tok"], s["g_plan_tok"])
-        cre_bf = ws.get("cre_bf", (nC, D), torch.bfloat16)                           # bf16 mirror = cross-attn context
+        # bf16 mirrors of the CRE stream = cross-attention context of the gene stream: mirror[0] after cre_map,
+        # mirror[i+1] after CRE layer i.  One buffer per layer (25 MB each) so that the CRE stack can run ahead of the
+        # gene stack on its own CUDA stream.
+        mirror = [ws.get(f"cre_bf{i}", (nC, D), torch.bfloat16) for i in range(w.NL)]
         if w.cre_map is None:
             raise NotImplementedError("token_dim == emb_dim (no cre_map) is not wired on the B200 path")
         cxs = ws.get("cxs", (nC, ops.stats_parts(D), 2), torch.float32)
         cx = ops.gemm(cre_pooled, w.cre_map.w, EPI_BIAS_F32, bias=w.cre_map.b, out=ws.get("cx", (nC, D), torch.float32),
-                      out2=cre_bf, stats_out=cxs)
+                      out2=mirror[0], stats_out=cxs)
         gene_emb = ops.gemm(gene_pooled, w.gene_map.w, EPI_BIAS_F32, bias=w.gene_map.b)
         gx, _ = ops.gather_rows(gene_emb, w.registry, s["gene_idx"])
         gxb = ws.get("gxb", (Mg, D), torch.bfloat16)
@@ -408,24 +414,48 @@ class Engine:
         def cre_self(qkv, out):
             s["plan_cself"].run(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], H, hd, w.slopes, out)
 
-        def gene_layer(L):
-            ops.gemm(cre_bf, L["kv"].w, EPI_BIAS_BF16, bias=L["kv"].b, out=kv)      # shared by every tissue copy
+        def gene_layer(L, ctx):
+            ops.gemm(ctx, L["kv"].w, EPI_BIAS_BF16, bias=L["kv"].b, out=kv)         # shared by every tissue copy
 
             def cross(q, out):
                 s["plan_gcross"].run(q, kv[:, :D], kv[:, D:], H, hd, None, out)
             st["g"] = self._layer(L, gx, gxb, st["g"], Mg, gene_self, cross, "g")
 
-        def cre_layer(L):
+        def cre_layer(i):
+            L = w.cre_layers[i]
+
             def cross(q, out):
                 ops.label_attention(q, L["kv9"], s["logc"], s["row_seq"], H, hd, out=out)
-            st["c"] = self._layer(L, cx, cre_bf, st["c"], nC, cre_self, cross, "c")
+            st["c"] = self._layer(L, cx, mirror[i], st["c"], nC, cre_self, cross, "c", xb_out=mirror[i + 1])
 
+        # The CRE stack does not depend on the gene stack (gene layer i+1 reads the output of CRE layer i, never the
+        # other way round): it runs on a second CUDA stream and its short kernels (8 192 rows) fill the tails of the
+        # gene stack's persistent kernels.  Gene layer i+1 waits for the event recorded after CRE layer i.
         prune_last = "plan_last_self" in s and w.NL > 1
-        gene_layer(w.gene_layers[0])
+        two_streams = self.device.type == "cuda" and CRE_STREAM and w.NL > 1
+        done = []
+        if two_streams:
+            main = torch.cuda.current_stream(self.device)
+            if getattr(self, "_cre_stream", None) is None:
+                self._cre_stream = torch.cuda.Stream(self.device)
+            side = self._cre_stream
+            for t in (s["logc"], s["row_seq"], *s["plan_cself"].device_tensors()):
+                t.record_stream(side)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                for i in range(w.NL - 1):
+                    cre_layer(i)
+                    ev = torch.cuda.Event(); ev.record(side)
+                    done.append(ev)
+        gene_layer(w.gene_layers[0], mirror[0])
         for i in range(w.NL - 1):
-            cre_layer(w.cre_layers[i])
+            if two_streams:
+                main.wait_event(done[i])
+            else:
+                cre_layer(i)
             if i + 1 < w.NL - 1 or not prune_last:
-                gene_layer(w.gene_layers[i + 1])
+                gene_layer(w.gene_layers[i + 1], mirror[i + 1])
+        cre_bf = mirror[w.NL - 1]
         n_reg = s["reg_idx"].numel()
         if prune_last:
             last = self._gene_layer_last(w.gene_layers[w.NL - 1], s, gx, gxb, st["g"], cre_bf, kv)
