@@ -269,7 +269,7 @@ class Engine:
         return xs_out
 
     # ---------------------------------------------------------------- last gene layer, needed rows only
-    def _gene_layer_last(self, L, s, x, xb, xs, cre_bf, kv):
+    def _gene_layer_last(self, L, s, x, xb, xs, kv):
         """The last ContextFlashAttentionEncoderLayer of the gene stream restricted to the rows whose output is read
         (registry rows + VEP token rows): K/V of the self-attention still come from every row, all the rest runs on
         `need` rows.  Same arithmetic as _layer on those rows.  -> fp32 [n_need, D]."""
@@ -291,7 +291,6 @@ class Engine:
         s1 = torch.empty((R, ops.stats_parts(D), 2), dtype=torch.float32, device=x.device)
         ops.gemm(a, L["out"].w, EPI_BIAS_RESID_F32, bias=L["out"].b, resid=xR, out2=hb, stats_out=s1, mirror_only=True)
         ops.gemm(hb, L["q"].w, EPI_BIAS_BF16, bias=L["q"].b, out=q, ln=L["q"].ln(s1))
-        ops.gemm(cre_bf, L["kv"].w, EPI_BIAS_BF16, bias=L["kv"].b, out=kv)
         s["plan_last_cross"].run(q, kv[:, :D], kv[:, D:], H, hd, None, a)
         ops.gemm(a, L["out2"].w, EPI_BIAS_RESID_F32, bias=L["out2"].b, resid=hb, out2=hb, stats_out=s1, mirror_only=True)
         f = ops.gemm(hb, L["g1"].w, EPI_BIAS_GEGLU_BF16, bias=L["g1"].b, ln=L["g1"].ln(s1))
@@ -406,7 +405,9 @@ class Engine:
         gxb = ws.get("gxb", (Mg, D), torch.bfloat16)
         gxs = ops.rowstats(gx, ws.get("gxs0", (Mg, 1, 2), torch.float32), gxb)
         st = {"g": gxs, "c": cxs}                                      # current row statistics of each stream
-        kv = ws.get("g_kv", (nC, 2 * D), torch.bfloat16)
+        # K/V of the gene stack's cross-attention, one buffer per gene layer: they depend on the CRE stack only, so the
+        # projection of layer i+1 is issued on the CRE stream right behind CRE layer i
+        kvs = [ws.get(f"g_kv{i}", (nC, 2 * D), torch.bfloat16) for i in range(w.NL)]
 
         def gene_self(qkv, out):
             s["plan_gself"].run(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], H, hd, w.slopes, out)
@@ -414,8 +415,12 @@ class Engine:
         def cre_self(qkv, out):
             s["plan_cself"].run(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], H, hd, w.slopes, out)
 
-        def gene_layer(L, ctx):
-            ops.gemm(ctx, L["kv"].w, EPI_BIAS_BF16, bias=L["kv"].b, out=kv)         # shared by every tissue copy
+        def project_kv(i):
+            L = w.gene_layers[i]
+            ops.gemm(mirror[i], L["kv"].w, EPI_BIAS_BF16, bias=L["kv"].b, out=kvs[i])    # shared by every tissue copy
+
+        def gene_layer(i):
+            L, kv = w.gene_layers[i], kvs[i]
 
             def cross(q, out):
                 s["plan_gcross"].run(q, kv[:, :D], kv[:, D:], H, hd, None, out)
@@ -443,22 +448,26 @@ class Engine:
                 t.record_stream(side)
             side.wait_stream(main)
             with torch.cuda.stream(side):
+                project_kv(0)
+                ev = torch.cuda.Event(); ev.record(side)
+                done.append(ev)
                 for i in range(w.NL - 1):
                     cre_layer(i)
+                    project_kv(i + 1)
                     ev = torch.cuda.Event(); ev.record(side)
                     done.append(ev)
-        gene_layer(w.gene_layers[0], mirror[0])
-        for i in range(w.NL - 1):
+        for i in range(w.NL):                                  # done[i]: context and K/V of gene layer i are ready
             if two_streams:
                 main.wait_event(done[i])
             else:
-                cre_layer(i)
-            if i + 1 < w.NL - 1 or not prune_last:
-                gene_layer(w.gene_layers[i + 1], mirror[i + 1])
-        cre_bf = mirror[w.NL - 1]
+                if i > 0:
+                    cre_layer(i - 1)
+                project_kv(i)
+            if i < w.NL - 1 or not prune_last:
+                gene_layer(i)
         n_reg = s["reg_idx"].numel()
         if prune_last:
-            last = self._gene_layer_last(w.gene_layers[w.NL - 1], s, gx, gxb, st["g"], cre_bf, kv)
+            last = self._gene_layer_last(w.gene_layers[w.NL - 1], s, gx, gxb, st["g"], kvs[w.NL - 1])
             emb = last[:n_reg]
             emb_bf = ops.cast_bf16(emb.contiguous())
         else:
