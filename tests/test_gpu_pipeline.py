@@ -83,6 +83,24 @@ def test_hotpath_tokens_bit_exact_and_outputs_within_tolerance():
     assert rel_err(emb, w_emb) <= 1e-2 and pearson(emb, w_emb) >= 0.9999 and rel_err(pred, w_pred) <= 1e-2
 
 
+def test_pipelined_api_and_stream_overlap_are_invisible(monkeypatch):
+    """predict_pipelined (stage 1 of slab i+1 on a side stream, CRE stack on its own stream) returns bit-identical
+    results to one-slab-at-a-time, single-stream execution."""
+    from variantformer_b200 import engine as engine_mod
+    chroms, var, genes = _world()
+    sd = random_init.make_state_dict(CFG, HP, seed=5)
+    hot = HotPath(Engine(sd, CFG, HP), Genome.from_arrays(chroms, "cuda"))
+    sv = SampleVariants(var, "cuda")
+    slabs = [genes, genes[::-1], genes[:1], genes]
+    monkeypatch.setattr(engine_mod, "CRE_STREAM", False)
+    want = [hot.predict(g, sv) for g in slabs]
+    monkeypatch.setattr(engine_mod, "CRE_STREAM", True)
+    got = list(hot.predict_pipelined(iter(slabs), sv, to_host=True))
+    assert len(got) == len(want)
+    for (p0, e0), (p1, e1) in zip(want, got):
+        assert np.array_equal(p0, p1) and np.array_equal(e0, e1)
+
+
 def _write_artifacts(tmp_path, chroms, var, genes):
     art = tmp_path / "_artifacts"; (art / "gene_cre_manifests").mkdir(parents=True)
     with open(art / "GRCh38_no_alt_analysis_set_GCA_000001405.15.fasta.gz", "wb") as f:     # plain text is accepted too

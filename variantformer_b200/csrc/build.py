@@ -10,6 +10,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["vf_api.cu", "vf_gemm.cu", "vf_attention.cu", "vf_attention_tc.cu", "vf_attention_tc128.cu", "vf_attention_mc.cu", "vf_elementwise.cu", "vf_encode.cu"]
 HEADERS = ["vf_common.cuh", "vf_internal.h", os.path.join("..", "..", "include", "vf_b200.h")]
 LIB = os.path.join(HERE, "libvf_b200.so")
+INGEST_SRC = os.path.join(HERE, "vf_ingest.cpp")
+INGEST_LIB = os.path.join(HERE, "libvf_ingest.so")
+CXX = os.environ.get("CXX", "g++")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
@@ -44,7 +47,17 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed")
     if force or procs or _stale(LIB, objs):
         subprocess.run([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"], check=True)
+    build_ingest(force)
     return LIB
+
+
+def build_ingest(force=False):
+    """libvf_ingest.so: host-side FASTA / VCF ingest (C++17, zlib, threads; no CUDA)."""
+    hdr = os.path.join(HERE, "..", "..", "include", "vf_ingest.h")
+    if force or _stale(INGEST_LIB, [INGEST_SRC, hdr]):
+        subprocess.run([CXX, "-O3", "-std=c++17", "-shared", "-fPIC", "-Wall", INGEST_SRC, "-o", INGEST_LIB, "-lz",
+                        "-lpthread"], check=True)
+    return INGEST_LIB
 
 
 if __name__ == "__main__":

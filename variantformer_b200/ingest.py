@@ -1,88 +1,104 @@
-"""Host ingest for stage 1: FASTA -> byte arrays, one sample of a VCF -> sorted variant arrays.
+"""Host ingest for stage 1: FASTA -> byte arrays, one sample of a VCF -> sorted variant arrays (SURVEY §8f rank 1).
 
-Replaces what `samtools faidx` / `bcftools consensus` read from disk per window
-(utils/data_process.py:27,40-59) with one pass per genome / per sample.  Pure Python + numpy for now
-(SURVEY §8f rank 1 lists the C++/BGZF loader as the next row); the parsed arrays are what
-stage1.Genome / stage1.SampleVariants upload to HBM.
+Replaces what `samtools faidx` / `bcftools consensus` (htslib) read from disk per window
+(utils/data_process.py:27,40-59,404,416-435) with ONE pass per genome / per sample through libvf_ingest.so
+(csrc/vf_ingest.cpp: C++17, zlib, parallel BGZF inflation and line parsing; C ABI in include/vf_ingest.h).  The parsed
+arrays are what stage1.Genome / stage1.SampleVariants upload to HBM.  There is no Python fallback: the pure-Python
+restatement of the same semantics lives in oracle/ingest_py.py and is test infrastructure.
 """
-import gzip
+import ctypes as C
+import os
 
 import numpy as np
 
-_IUPAC2 = {frozenset("AC"): "M", frozenset("AG"): "R", frozenset("AT"): "W", frozenset("CG"): "S",
-           frozenset("CT"): "Y", frozenset("GT"): "K"}
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libvf_ingest.so")
+_vp, _i32, _i64 = C.c_void_p, C.c_int, C.c_int64
+
+# name -> (argtypes, restype): every symbol include/vf_ingest.h declares
+SIGNATURES = {
+    "vf_ingest_last_error": ([], C.c_char_p),
+    "vf_fasta_open": ([C.c_char_p, _i32], _vp),
+    "vf_fasta_num_seqs": ([_vp], _i32),
+    "vf_fasta_name": ([_vp, _i32], C.c_char_p),
+    "vf_fasta_length": ([_vp, _i32], _i64),
+    "vf_fasta_copy": ([_vp, _i32, _vp, _i64], _i64),
+    "vf_fasta_close": ([_vp], None),
+    "vf_vcf_open": ([C.c_char_p, C.c_char_p, _i32], _vp),
+    "vf_vcf_num_chroms": ([_vp], _i32),
+    "vf_vcf_chrom": ([_vp, _i32], C.c_char_p),
+    "vf_vcf_num_records": ([_vp, _i32], _i64),
+    "vf_vcf_alt_bytes": ([_vp, _i32], _i64),
+    "vf_vcf_copy": ([_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp], _i32),
+    "vf_vcf_close": ([_vp], None),
+}
+_lib = None
 
 
-def _open(path):
-    with open(path, "rb") as f:
-        magic = f.read(2)
-    return gzip.open(path, "rb") if magic == b"\x1f\x8b" else open(path, "rb")
+class IngestError(RuntimeError):
+    pass
 
 
-def load_fasta(path, chroms=None):
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise IngestError(f"{LIB_PATH} not found: build it with `python -m variantformer_b200.csrc.build`")
+        l = C.CDLL(LIB_PATH)
+        for name, (args, res) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = args
+            fn.restype = res
+        _lib = l
+    return _lib
+
+
+def _fail(what):
+    raise IngestError(f"{what}: {lib().vf_ingest_last_error().decode()}")
+
+
+def load_fasta(path, chroms=None, threads=0):
     """-> {name: uint8 array} with the FASTA's own case (soft-masking) preserved."""
-    out, name, parts = {}, None, []
+    l = lib()
+    h = l.vf_fasta_open(os.fsencode(path), threads)
+    if not h:
+        _fail("vf_fasta_open")
+    try:
+        out = {}
+        for i in range(l.vf_fasta_num_seqs(h)):
+            name = l.vf_fasta_name(h, i).decode()
+            if chroms is not None and name not in chroms:
+                continue
+            a = np.empty(l.vf_fasta_length(h, i), np.uint8)
+            if l.vf_fasta_copy(h, i, a.ctypes.data, a.size) != a.size:
+                _fail("vf_fasta_copy")
+            out[name] = a
+        return out
+    finally:
+        l.vf_fasta_close(h)
 
-    def flush():
-        if name is not None and (chroms is None or name in chroms):
-            out[name] = np.frombuffer(b"".join(parts), np.uint8).copy()
-    with _open(path) as f:
-        for line in f:
-            if line.startswith(b">"):
-                flush()
-                name = line[1:].split()[0].decode(); parts = []
-            elif chroms is None or name in chroms:
-                parts.append(line.rstrip(b"\r\n"))
-    flush()
-    return out
 
-
-def load_vcf_sample(path, sample=None, chroms=None):
-    """One sample's genotypes -> {chrom: dict(pos int64 0-based, ref_len, alt [bytes], gt uint8)}.
-    Records with symbolic ALT (<...>) or '*' are dropped (the reference's `-e 'ALT~"<.*>"'`); hom-ref and missing
-    genotypes are dropped; a het between two different ALT SNPs (1/2) is resolved here to its IUPAC code."""
-    per = {}
-    col = 9
-    with _open(path) as f:
-        for raw in f:
-            if raw.startswith(b"##"):
+def load_vcf_sample(path, sample=None, chroms=None, threads=0):
+    """One sample's genotypes -> {chrom: dict(pos int64 0-based, ref_len int32, alt [bytes], gt uint8)}, sorted by
+    position (semantics: include/vf_ingest.h)."""
+    l = lib()
+    h = l.vf_vcf_open(os.fsencode(path), None if sample is None else sample.encode(), threads)
+    if not h:
+        _fail("vf_vcf_open")
+    try:
+        per = {}
+        for c in range(l.vf_vcf_num_chroms(h)):
+            name = l.vf_vcf_chrom(h, c).decode()
+            if chroms is not None and name not in chroms:
                 continue
-            fields = raw.rstrip(b"\r\n").split(b"\t")
-            if raw.startswith(b"#CHROM"):
-                names = [x.decode() for x in fields[9:]]
-                if sample is not None:
-                    col = 9 + names.index(sample)
-                continue
-            chrom = fields[0].decode()
-            if chroms is not None and chrom not in chroms:
-                continue
-            ref = fields[3]; alts = fields[4].split(b",")
-            gt_field = fields[col].split(b":")[0] if len(fields) > col else b"./."
-            als = gt_field.replace(b"|", b"/").split(b"/")
-            if any(a in (b".", b"") for a in als):
-                continue
-            als = [int(a) for a in als]
-            if len(als) == 1:
-                als = als * 2
-            nz = [a for a in als if a > 0]
-            if not nz:
-                continue
-            a0 = alts[nz[0] - 1]
-            if a0.startswith(b"<") or a0 == b"*":
-                continue
-            d = per.setdefault(chrom, dict(pos=[], ref_len=[], alt=[], gt=[]))
-            if len(set(als)) == 1:
-                gt, alt = 2, a0
-            elif len(nz) == 2 and len(ref) == 1 and all(len(alts[a - 1]) == 1 for a in nz):
-                code = _IUPAC2.get(frozenset((alts[nz[0] - 1] + alts[nz[1] - 1]).decode().upper()))
-                gt, alt = 2, (code or "N").encode()
-            else:
-                gt, alt = 1, a0
-            d["pos"].append(int(fields[1]) - 1); d["ref_len"].append(len(ref)); d["alt"].append(alt); d["gt"].append(gt)
-    for chrom, d in per.items():
-        order = np.argsort(np.asarray(d["pos"], np.int64), kind="stable")
-        d["pos"] = np.asarray(d["pos"], np.int64)[order]
-        d["ref_len"] = np.asarray(d["ref_len"], np.int32)[order]
-        d["gt"] = np.asarray(d["gt"], np.uint8)[order]
-        d["alt"] = [d["alt"][i] for i in order]
-    return per
+            n, nb = l.vf_vcf_num_records(h, c), l.vf_vcf_alt_bytes(h, c)
+            pos = np.empty(n, np.int64); ref_len = np.empty(n, np.int32); off = np.empty(n, np.int32)
+            ln = np.empty(n, np.int32); gt = np.empty(n, np.uint8); pool = np.empty(nb, np.uint8)
+            if l.vf_vcf_copy(h, c, pos.ctypes.data, ref_len.ctypes.data, off.ctypes.data, ln.ctypes.data, gt.ctypes.data,
+                             pool.ctypes.data) != 0:
+                _fail("vf_vcf_copy")
+            pb = pool.tobytes()
+            per[name] = dict(pos=pos, ref_len=ref_len, gt=gt, alt=[pb[o:o + k] for o, k in zip(off.tolist(), ln.tolist())])
+        return per
+    finally:
+        l.vf_vcf_close(h)
