@@ -62,10 +62,17 @@ struct Params {
     float scale_log2;
 };
 
+#ifndef VF_ATTN_ABLATE
+#define VF_ATTN_ABLATE 0          // timing experiments only (results are wrong): 1 no MUFU, 2 no P stores, 3 no TMEM loads
+#endif
 __device__ __forceinline__ float ex2_approx(float x) {
+#if VF_ATTN_ABLATE == 1
+    return x * 0.001f;
+#else
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+#endif
 }
 
 // O_s row *= corr, in tensor memory, 8 columns at a time (few live registers: the caller holds a whole score row).
@@ -163,6 +170,9 @@ __device__ __forceinline__ void softmax_tile(uint32_t (&r)[64], uint32_t o_addr,
         mbar_wait(p_empty_bar, p_empty_parity);
         tc_fence_after();
     }
+#if VF_ATTN_ABLATE == 2
+    if (row == 1000)
+#endif
 #pragma unroll
     for (int q8 = 0; q8 < 8; ++q8)                            // 8 probabilities -> one 16-byte chunk of the P row
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + ((q8 ^ (row & 7)) * 16)), "r"(r[q8 * 4]),
@@ -392,9 +402,14 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 tc_fence_after();
                 // ---- scores of this row -> registers; then the score buffer is free for the next Q K^T ----
                 uint32_t r[64];
+#if VF_ATTN_ABLATE == 3
+#pragma unroll
+                for (int e = 0; e < 64; ++e) r[e] = __float_as_uint(0.01f * (float)(e + row + j));
+#else
                 tmem_ld_32x32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
                 tmem_ld_32x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
                 tmem_ld_wait();
+#endif
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s_empty[s]);

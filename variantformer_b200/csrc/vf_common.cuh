@@ -143,24 +143,27 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// Wait for a phase.  Pure spin on the NON-blocking test: `mbarrier.try_wait` lets the hardware suspend the thread, and
+// the wake-up after the phase completes costs on the order of a microsecond — measured on the attention kernels, whose
+// softmax <-> MMA hand-shakes happen every ~2 us: 31 % (201-token items) to 5 % (1024-key items) slower than spinning.
+// Every 2^20 spins the loop looks at %globaltimer: a wait longer than VF_WATCHDOG_NS kills the kernel (`trap`), so a
+// pipeline bug cannot hang the GPU.  The loop must not contain a call: a printf here (even on the cold path) gives
+// every kernel that waits on a barrier an ABI stack frame and cost the attention kernels the whole 31 % again; build
+// with -DVF_WATCHDOG_VERBOSE to get the message (block, thread, barrier, parity) when chasing a deadlock.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-#ifdef VF_MBAR_SIMPLE
-    while (!mbar_try_wait(bar, parity)) {}
-    return;
-#endif
-    if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
     uint64_t t0 = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 255u) == 0) {                         // look at the clock only now and then
+    while (!mbar_test_wait(bar, parity)) {
+        if ((++spins & 0xFFFFFu) == 0) {
             const uint64_t now = global_timer_ns();
             if (t0 == 0) t0 = now;
             if (now - t0 > VF_WATCHDOG_NS) {
-                // report, leave the other stuck threads of the grid a moment to report too, then kill the kernel
+#ifdef VF_WATCHDOG_VERBOSE
                 printf("vf: mbarrier watchdog: block %d thread %d barrier smem+0x%x parity %u\n", blockIdx.x, threadIdx.x,
                        smem_u32(bar), parity);
 #pragma unroll 1
                 for (int i = 0; i < 1000; ++i) __nanosleep(1000000);
+#endif
                 __trap();
             }
         }
