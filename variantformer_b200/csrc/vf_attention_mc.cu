@@ -62,6 +62,13 @@ struct Params {
     float scale_log2;
 };
 
+#ifndef VF_ATTN_REGS_LO
+#define VF_ATTN_REGS_LO 32        // producer / MMA issuer warpgroup; 128 * LO + 256 * HI <= 384 * 80
+#define VF_ATTN_REGS_HI 104       // softmax warpgroups
+#endif
+#ifndef VF_ATTN_NARROW
+#define VF_ATTN_NARROW 1          // tail block: softmax on whole 16-key groups up to the last key only (0: all 64 keys)
+#endif
 #ifndef VF_ATTN_ABLATE
 #define VF_ATTN_ABLATE 0          // timing experiments only (results are wrong): 1 no MUFU, 2 no P stores, 3 no TMEM loads
 #endif
@@ -91,59 +98,126 @@ __device__ __forceinline__ void rescale_o(uint32_t o_addr, float corr) {
     tmem_st_wait();
 }
 
-// exponent of one score: x = raw * scale + (bias - m_ref), written back in place; returns nothing.
-// MODE 0: no positional term.  MODE 1: ALiBi, the whole 64-key block on one side of the diagonal for every row of the
-// warp: bias = c + sl * e (sl = +-slope, c folded by the caller).  MODE 2: general (diagonal block and / or tail mask).
-template <int MODE>
-__device__ __forceinline__ void exponents(uint32_t (&r)[64], float scale, float c, float sl, float slope, float d0,
-                                          int nvalid, float& mx_out) {
-    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-    for (int e = 0; e < 64; ++e) {
-        float x;
-        if constexpr (MODE == 0) {
-            x = fmaf(__uint_as_float(r[e]), scale, c);
-        } else if constexpr (MODE == 1) {
-            x = fmaf(__uint_as_float(r[e]), scale, fmaf(sl, (float)e, c));
-        } else {
-            x = fmaf(__uint_as_float(r[e]), scale, fmaf(-slope, fabsf(d0 - (float)e), c));
-            if (e >= nvalid) x = -INFINITY;
-        }
-        r[e] = __float_as_uint(x);
-        mx[e & 3] = fmaxf(mx[e & 3], x);
-    }
-    mx_out = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2: one issue slot for two lanes of arithmetic) and the 3-input maximum.  The
+// softmax warps are bound by the instructions they issue, not by any single pipe, so the per-score count is what
+// matters: 3.0 (no positional term), 3.5 (ALiBi off the diagonal), 4.5 (diagonal block) instead of 4.5 / 5.5 / 7.5.
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+    uint64_t v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+    return v;
+}
+__device__ __forceinline__ uint64_t f2_pack(uint32_t lo, uint32_t hi) {
+    uint64_t v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(lo), "r"(hi));
+    return v;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, uint32_t& lo, uint32_t& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
 }
 
-// One 128 x 64 score tile for this thread's row (r = the 64 raw scores): -> P (shared memory, bf16, K-major
-// SWIZZLE_128B: 16-byte chunk index XOR (row & 7)), running m_ref / l, O_s rescaled in TMEM when the reference
-// maximum is raised.
-template <int HD, bool ALIBI>
-__device__ __forceinline__ void softmax_tile(uint32_t (&r)[64], uint32_t o_addr, bool first, uint64_t* p_empty_bar,
-                                             uint32_t p_empty_parity, float scale, float slope, float qpos, int key0,
-                                             int Sk, float& m_ref, float& l, uint32_t p_row, int row, int lane) {
-    const float base = first ? 0.f : m_ref;                  // exponents are first taken against `base`
-    const float d0 = qpos - (float)key0;                     // query position minus the block's first key
-    const int nvalid = Sk - key0;
-    float mx;
-    bool general = nvalid < kKB;
-    if constexpr (ALIBI) general = general || !(__all_sync(0xffffffffu, d0 >= 63.f) || __all_sync(0xffffffffu, d0 <= 0.f));
-    if (general) {
-        exponents<2>(r, scale, -base, 0.f, ALIBI ? slope : 0.f, d0, nvalid, mx);
-    } else if constexpr (ALIBI) {
-        const float sl = d0 > 0.f ? slope : -slope;          // |d0 - e| = +-(d0 - e) for the whole block
-        exponents<1>(r, scale, -slope * fabsf(d0) - base, sl, slope, d0, nvalid, mx);
+// {2i, 2i+1} and its negative as packed fp32 pairs (little-endian: low word = first key)
+#define VF_KP(i) (((uint64_t)__builtin_bit_cast(uint32_t, (float)(2 * (i) + 1)) << 32) | __builtin_bit_cast(uint32_t, (float)(2 * (i))))
+#define VF_NKP(i) (((uint64_t)__builtin_bit_cast(uint32_t, -(float)(2 * (i) + 1)) << 32) | __builtin_bit_cast(uint32_t, -(float)(2 * (i))))
+#define VF_ROW8(M, b) M(b), M(b + 1), M(b + 2), M(b + 3), M(b + 4), M(b + 5), M(b + 6), M(b + 7)
+__constant__ uint64_t kKeyPair[32] = {VF_ROW8(VF_KP, 0), VF_ROW8(VF_KP, 8), VF_ROW8(VF_KP, 16), VF_ROW8(VF_KP, 24)};
+__constant__ uint64_t kNegKeyPair[32] = {VF_ROW8(VF_NKP, 0), VF_ROW8(VF_NKP, 8), VF_ROW8(VF_NKP, 16), VF_ROW8(VF_NKP, 24)};
+
+// First pass over one row of a 128 x 64 score tile.  Exponent of a score (base 2, against the current reference
+// `base`): x = raw * scale + bias - base.  Returns the row maximum of x.
+// MODE 0: no positional term: the maximum is taken on the raw scores, r is left as it is and the affine map is applied
+//         in the exponential pass (where it overlaps the MUFU pipe).
+// MODE 1: ALiBi with the whole 64-key block on one side of the diagonal for every row of the warp: the bias is linear
+//         in the key index.
+// MODE 2: ALiBi across the diagonal.   MODE 3: MODE 2 + tail mask (keys >= nvalid -> -inf); slope may be 0; works on
+//         whole 16-key groups up to nvalid only.
+// Modes 1-3 write x back into r.  Key index pairs come from constant memory (operands of the packed instructions):
+// no running sums, the 32 pairs stay independent.
+template <int MODE>
+__device__ __forceinline__ float exponents(uint32_t (&r)[64], float scale, float slope, float d0, float base, int nvalid) {
+    float m0 = -INFINITY, m1 = -INFINITY;
+    if constexpr (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            m0 = max3(m0, __uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+            m1 = max3(m1, __uint_as_float(r[2 * i + 2]), __uint_as_float(r[2 * i + 3]));
+        }
+        return fmaf(fmaxf(m0, m1), scale, -base);               // scale > 0
     } else {
-        exponents<0>(r, scale, -base, 0.f, 0.f, d0, nvalid, mx);
+        const uint64_t scale2 = f2_pack(scale, scale);
+        uint64_t sl2 = 0, c2 = 0, d2 = 0;
+        if constexpr (MODE == 1) {
+            // |d0 - e| = +-(d0 - e) for the whole block: bias(e) = -slope |d0| - base + sl e
+            const float sl = d0 > 0.f ? slope : -slope;
+            const float c = fmaf(-slope, fabsf(d0), -base);
+            sl2 = f2_pack(sl, sl);
+            c2 = f2_pack(c, c);
+        } else {
+            d2 = f2_pack(d0, d0);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            if (VF_ATTN_NARROW && MODE == 3 && (i & 7) == 0 && 2 * i >= nvalid) break;   // whole groups past the end
+            uint64_t bias2;
+            if constexpr (MODE == 1) {
+                bias2 = f2_fma(kKeyPair[i], sl2, c2);
+            } else {
+                float t0, t1;
+                f2_unpack(f2_add(d2, kNegKeyPair[i]), t0, t1);                          // d0 - e
+                bias2 = f2_pack(fmaf(-slope, fabsf(t0), -base), fmaf(-slope, fabsf(t1), -base));
+            }
+            float x0, x1;
+            f2_unpack(f2_fma(f2_pack(r[2 * i], r[2 * i + 1]), scale2, bias2), x0, x1);
+            if constexpr (MODE == 3) {
+                if (2 * i >= nvalid) x0 = -INFINITY;
+                if (2 * i + 1 >= nvalid) x1 = -INFINITY;
+            }
+            r[2 * i] = __float_as_uint(x0);
+            r[2 * i + 1] = __float_as_uint(x1);
+            if (i & 1) m1 = max3(m1, x0, x1);
+            else m0 = max3(m0, x0, x1);
+        }
+        return fmaxf(m0, m1);
     }
+}
+
+// Everything after the first pass: lazy raise of the reference maximum (O_s rescaled in TMEM), exponentials, P -> shared
+// memory (bf16, K-major SWIZZLE_128B: 16-byte chunk index XOR (row & 7)), running row sum.
+// KIND 0: r holds raw scores (exponents<0>).  KIND 1: r holds x.  KIND 3: x, tail block (groups past nvalid: P = 0; the
+// issuer still runs all four P V steps).
+// The four warps of a slot meet different ALiBi block kinds in the same tile, so modes 1 and 2 share ONE copy of this
+// code (a copy per mode was measured 20 % slower on 201-token sequences: instruction fetch); tails and the no-bias
+// kind are uniform over the slot and get their own.
+template <int HD, int KIND>
+__device__ __forceinline__ void softmax_rest(uint32_t (&r)[64], float mx, float base, float scale, int nvalid,
+                                             uint32_t o_addr, bool first, uint64_t* p_empty_bar, uint32_t p_empty_parity,
+                                             float& m_ref, float& l, uint32_t p_row, int row) {
     // The PV of this slot's previous step is the last reader of the P buffer and the last writer of O_s.  It was issued
     // at the end of the previous tile, so waiting for it HERE (before the exponentials) can stall every softmax warp
     // of the slot; only a raise of the reference maximum needs it this early (it rescales O_s).  The common path
     // takes the exponentials first, packed into the registers the scores occupied, and waits right before the stores.
     bool waited = false;
+    float delta = 0.f;
     if (first || __any_sync(0xffffffffu, mx > kLazyThreshold)) {
         // first tile: the exact row maximum becomes the reference (may be negative).  later: raise by max(mx, 0).
-        const float delta = first ? mx : fmaxf(mx, 0.f);
+        delta = first ? mx : fmaxf(mx, 0.f);
         const float corr = first ? 0.f : ex2_approx(-delta);
         l *= corr;
         if (!first) {
@@ -153,17 +227,31 @@ __device__ __forceinline__ void softmax_tile(uint32_t (&r)[64], uint32_t o_addr,
             rescale_o<HD>(o_addr, corr);
         }
         m_ref = base + delta;
+        if constexpr (KIND != 0) {
+            const uint64_t nd2 = f2_pack(-delta, -delta);
 #pragma unroll
-        for (int e = 0; e < 64; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) - delta);
+            for (int i = 0; i < 32; ++i) {
+                if (VF_ATTN_NARROW && KIND == 3 && (i & 7) == 0 && 2 * i >= nvalid) break;
+                f2_unpack(f2_add(f2_pack(r[2 * i], r[2 * i + 1]), nd2), r[2 * i], r[2 * i + 1]);
+            }
+        }
     }
     // (Serialising this section per scheduler with a lock — to break up convoys on the MUFU pipe — was measured 1.6x
     // SLOWER: one warp alone does not keep the pipe busy.)
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const uint64_t scale2 = f2_pack(scale, scale);
+    const float c0 = -(base + delta);
+    const uint64_t c2 = f2_pack(c0, c0);
+    uint64_t acc0 = f2_pack(0.f, 0.f), acc1 = acc0;
+    int ndone = 32;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {                            // r[i] <- bf16x2(p[2i], p[2i+1]); i <= 2i: in place
-        const float p0 = ex2_approx(__uint_as_float(r[2 * i]));
-        const float p1 = ex2_approx(__uint_as_float(r[2 * i + 1]));
-        acc[i & 3] += p0 + p1;
+        if (VF_ATTN_NARROW && KIND == 3 && (i & 7) == 0 && 2 * i >= nvalid) { ndone = i; break; }
+        float x0, x1;
+        if constexpr (KIND == 0) f2_unpack(f2_fma(f2_pack(r[2 * i], r[2 * i + 1]), scale2, c2), x0, x1);
+        else { x0 = __uint_as_float(r[2 * i]); x1 = __uint_as_float(r[2 * i + 1]); }
+        const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+        if (i & 1) acc1 = f2_add(acc1, f2_pack(p0, p1));
+        else acc0 = f2_add(acc0, f2_pack(p0, p1));
         r[i] = pack_bf16x2(p0, p1);
     }
     if (!waited) {
@@ -174,10 +262,40 @@ __device__ __forceinline__ void softmax_tile(uint32_t (&r)[64], uint32_t o_addr,
     if (row == 1000)
 #endif
 #pragma unroll
-    for (int q8 = 0; q8 < 8; ++q8)                            // 8 probabilities -> one 16-byte chunk of the P row
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + ((q8 ^ (row & 7)) * 16)), "r"(r[q8 * 4]),
-                     "r"(r[q8 * 4 + 1]), "r"(r[q8 * 4 + 2]), "r"(r[q8 * 4 + 3]) : "memory");
-    l += (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    for (int q8 = 0; q8 < 8; ++q8) {                          // 8 probabilities -> one 16-byte chunk of the P row
+        const uint32_t dst = p_row + ((q8 ^ (row & 7)) * 16);
+        if (KIND == 3 && 4 * q8 >= ndone)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+        else
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(r[q8 * 4]), "r"(r[q8 * 4 + 1]),
+                         "r"(r[q8 * 4 + 2]), "r"(r[q8 * 4 + 3]) : "memory");
+    }
+    float s0, s1;
+    f2_unpack(f2_add(acc0, acc1), s0, s1);
+    l += s0 + s1;
+}
+
+template <int HD, bool ALIBI>
+__device__ __forceinline__ void softmax_tile(uint32_t (&r)[64], uint32_t o_addr, bool first, uint64_t* p_empty_bar,
+                                             uint32_t p_empty_parity, float scale, float slope, float qpos, int key0,
+                                             int Sk, float& m_ref, float& l, uint32_t p_row, int row, int lane) {
+    const float base = first ? 0.f : m_ref;                  // exponents are first taken against `base`
+    const float d0 = qpos - (float)key0;                     // query position minus the block's first key
+    const int nvalid = Sk - key0;
+    if (nvalid < kKB) {
+        const float mx = exponents<3>(r, scale, ALIBI ? slope : 0.f, d0, base, nvalid);
+        softmax_rest<HD, 3>(r, mx, base, scale, nvalid, o_addr, first, p_empty_bar, p_empty_parity, m_ref, l, p_row, row);
+    } else if constexpr (ALIBI) {
+        float mx;
+        if (__all_sync(0xffffffffu, d0 >= 63.f) || __all_sync(0xffffffffu, d0 <= 0.f))
+            mx = exponents<1>(r, scale, slope, d0, base, nvalid);
+        else
+            mx = exponents<2>(r, scale, slope, d0, base, nvalid);
+        softmax_rest<HD, 1>(r, mx, base, scale, nvalid, o_addr, first, p_empty_bar, p_empty_parity, m_ref, l, p_row, row);
+    } else {
+        const float mx = exponents<0>(r, scale, 0.f, d0, base, nvalid);
+        softmax_rest<HD, 0>(r, mx, base, scale, nvalid, o_addr, first, p_empty_bar, p_empty_parity, m_ref, l, p_row, row);
+    }
 }
 
 // global position of K/V block (j, slot) of an item inside the CTA's K / V rings, relative to the item's first load.
@@ -235,7 +353,7 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int4* recs = reinterpret_cast<const int4*>(p.slots);         // 4 int4 per item: {s0.lo, s0.hi, s1.lo, s1.hi}
 
     if (warp < kFirstSoftmaxWarp) {
-        reg_dealloc<32>();
+        reg_dealloc<VF_ATTN_REGS_LO>();
         if (warp == 0 && elect_one()) {
             // ============================ TMA producer ============================
             uint32_t ring = 0;                               // K / V blocks loaded so far (same count for both rings)
@@ -361,7 +479,7 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t vb = smem_u32(sm_v + st * kKvBytes);
-#pragma unroll
+                        #pragma unroll
                         for (int kk = 0; kk < kKB / 16; ++kk)
                             umma_bf16(o_tmem, p_desc + 2 * kk, umma_desc_kmajor_sw128(vb + kk * 2048), idesc_pv, (j | kk) != 0);
                         umma_commit(&p_empty[s]);
@@ -379,7 +497,7 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
     } else {
         // ============================ softmax warps (fully independent of each other) ============================
-        reg_alloc<104>();
+        reg_alloc<VF_ATTN_REGS_HI>();
         const int s = (warp - kFirstSoftmaxWarp) >> 2;        // slot owned by this warpgroup
         const int quad = warp & 3;                            // TMEM lane quadrant of this warp
         const int row = quad * 32 + lane;                     // row inside the 128-row query tile
@@ -407,7 +525,7 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 for (int e = 0; e < 64; ++e) r[e] = __float_as_uint(0.01f * (float)(e + row + j));
 #else
                 tmem_ld_32x32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-                tmem_ld_32x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+                if (!VF_ATTN_NARROW || me.w - j * kKB > 32) tmem_ld_32x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
                 tmem_ld_wait();
 #endif
                 tc_fence_before();

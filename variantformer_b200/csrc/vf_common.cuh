@@ -150,11 +150,13 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 // pipeline bug cannot hang the GPU.  The loop must not contain a call: a printf here (even on the cold path) gives
 // every kernel that waits on a barrier an ABI stack frame and cost the attention kernels the whole 31 % again; build
 // with -DVF_WATCHDOG_VERBOSE to get the message (block, thread, barrier, parity) when chasing a deadlock.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+template <int SLEEP_NS>
+__device__ __forceinline__ void mbar_wait_impl(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     uint64_t t0 = 0;
     while (!mbar_test_wait(bar, parity)) {
-        if ((++spins & 0xFFFFFu) == 0) {
+        if constexpr (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+        if ((++spins & (SLEEP_NS > 0 ? 0x3FFFu : 0xFFFFFu)) == 0) {
             const uint64_t now = global_timer_ns();
             if (t0 == 0) t0 = now;
             if (now - t0 > VF_WATCHDOG_NS) {
@@ -169,6 +171,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         }
     }
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_impl<0>(bar, parity); }
+// The same wait for warps that share a scheduler with working warps (TMA producers, MMA issuers): a tight spin loop
+// is always ready to issue and takes up to a third of the scheduler's issue slots from the warps doing arithmetic
+// (in-kernel clock stamps: the 64-key softmax tile of the attention kernel is issue bound).  Sleeping ~30 ns between
+// polls costs far less than the microsecond wake-up of mbarrier.try_wait.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) { mbar_wait_impl<32>(bar, parity); }
 
 // ---- TMA (cp.async.bulk.tensor) -----------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
