@@ -319,6 +319,10 @@ def main():
                            "measured_in": "single-stream instrumented pass after the timed region "
                                           f"({prof_ms / args.steps:.1f} ms/step vs {elapsed_ms / args.steps:.1f} timed)"}
         out["kernel_breakdown_ms_per_step"] = {k: v["ms"] / args.steps for k, v in summ.items()}
+        det = prof.summarize_detail()
+        out["kernel_detail"] = {k: {"ms_per_step": round(v["ms"] / args.steps, 3), "launches_per_step": v["n"] / args.steps,
+                                    "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["ms"] > 0 else 0.0}
+                                for k, v in sorted(det.items(), key=lambda kv: -kv[1]["ms"])[:24]}
         total_flops = sum(v["flops"] for v in summ.values())
         out["config"]["algorithmic_tflop_per_step"] = total_flops / args.steps / 1e12
         out["achieved_tflops_all_kernels"] = total_flops / (elapsed_ms / 1e3) / 1e12

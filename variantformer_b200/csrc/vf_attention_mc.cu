@@ -207,7 +207,7 @@ __device__ __forceinline__ float exponents(uint32_t (&r)[64], float scale, float
 // kind are uniform over the slot and get their own.
 template <int HD, int KIND>
 __device__ __forceinline__ void softmax_rest(uint32_t (&r)[64], float mx, float base, float scale, int nvalid,
-                                             uint32_t o_addr, bool first, uint64_t* p_empty_bar, uint32_t p_empty_parity,
+                                             uint32_t o_addr, bool first, SmemBar p_empty_bar, uint32_t p_empty_parity,
                                              float& m_ref, float& l, uint32_t p_row, int row) {
     // The PV of this slot's previous step is the last reader of the P buffer and the last writer of O_s.  It was issued
     // at the end of the previous tile, so waiting for it HERE (before the exponentials) can stall every softmax warp
@@ -276,7 +276,7 @@ __device__ __forceinline__ void softmax_rest(uint32_t (&r)[64], float mx, float 
 }
 
 template <int HD, bool ALIBI>
-__device__ __forceinline__ void softmax_tile(uint32_t (&r)[64], uint32_t o_addr, bool first, uint64_t* p_empty_bar,
+__device__ __forceinline__ void softmax_tile(uint32_t (&r)[64], uint32_t o_addr, bool first, SmemBar p_empty_bar,
                                              uint32_t p_empty_parity, float scale, float slope, float qpos, int key0,
                                              int Sk, float& m_ref, float& l, uint32_t p_row, int row, int lane) {
     const float base = first ? 0.f : m_ref;                  // exponents are first taken against `base`
@@ -310,22 +310,27 @@ __global__ void __launch_bounds__(kThreads, 2)
 attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const Params p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sm_q = smem;                                         // 2 slots x 16 KB
-    uint8_t* sm_k = sm_q + 2 * kQBytes;                           // kKStages x 8 KB
-    uint8_t* sm_v = sm_k + kKStages * kKvBytes;                   // kVStages x 8 KB
-    uint8_t* sm_p = sm_v + kVStages * kKvBytes;                   // 2 slots x 16 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm_p + 2 * kQBytes);
-    uint64_t* q_full = bars + 0;   uint64_t* q_empty = bars + 2;                   // [slot]
-    uint64_t* s_full = bars + 4;   uint64_t* s_empty = bars + 6;                   // [slot]
-    uint64_t* p_full = bars + 8;   uint64_t* p_empty = bars + 10;                  // [slot]
-    uint64_t* o_full = bars + 12;  uint64_t* o_empty = bars + 14;                  // [slot]
+    // Everything in shared memory is named by its 32-bit shared-space address (see SmemBar): one base register, constant
+    // offsets.
+    uint32_t smem_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    // HD = 48: opaque, so the base stays in a register instead of being rebuilt (S2UR + ULEA) at every hand-shake
+    // (201-token self-attention 0.69 -> 0.63 ms).  HD = 64 has no register to spare in the softmax warps.
+    if constexpr (HD == 48) asm volatile("mov.b32 %0, %0;" : "+r"(smem_a));
+    const uint32_t sm_q = smem_a;                                 // 2 slots x 16 KB
+    const uint32_t sm_k = sm_q + 2 * kQBytes;                     // kKStages x 8 KB
+    const uint32_t sm_v = sm_k + kKStages * kKvBytes;             // kVStages x 8 KB
+    const uint32_t sm_p = sm_v + kVStages * kKvBytes;             // 2 slots x 16 KB
+    const SmemBar bars{sm_p + 2 * kQBytes};
+    const SmemBar q_full = bars[0], q_empty = bars[2];            // [slot]
+    const SmemBar s_full = bars[4], s_empty = bars[6];            // [slot]
+    const SmemBar p_full = bars[8], p_empty = bars[10];           // [slot]
+    const SmemBar o_full = bars[12], o_empty = bars[14];          // [slot]
     // a K / V stage has TWO release barriers, one per slot: both slots arrive (tcgen05.commit) when they share the
     // block, its only user arrives on both otherwise.  (Two commits on ONE barrier with count 2 are not reliable: when
     // both are pending on the same MMAs they can be merged into a single arrival.)
-    uint64_t* k_full = bars + 16;  uint64_t* k_empty = k_full + kKStages;          // k_empty[2 * stage + slot]
-    uint64_t* v_full = k_empty + 2 * kKStages;   uint64_t* v_empty = v_full + kVStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + 2 * kVStages);
+    const SmemBar k_full = bars[16], k_empty = k_full[kKStages];  // k_empty[2 * stage + slot]
+    const SmemBar v_full = k_empty[2 * kKStages], v_empty = v_full[kVStages];
+    const uint32_t tmem_slot = v_empty[2 * kVStages].addr;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_work = p.n_items * p.heads;
@@ -333,20 +338,24 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
-            mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);      // 4 softmax warps per slot
-            mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1);
-            mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4);
+            mbar_init(q_full[i], 1); mbar_init(q_empty[i], 1);
+            mbar_init(s_full[i], 1); mbar_init(s_empty[i], 4);      // 4 softmax warps per slot
+            mbar_init(p_full[i], 4); mbar_init(p_empty[i], 1);
+            mbar_init(o_full[i], 1); mbar_init(o_empty[i], 4);
         }
-        for (int i = 0; i < kKStages; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[2 * i], 1); mbar_init(&k_empty[2 * i + 1], 1); }
-        for (int i = 0; i < kVStages; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[2 * i], 1); mbar_init(&v_empty[2 * i + 1], 1); }
+        for (int i = 0; i < kKStages; ++i) { mbar_init(k_full[i], 1); mbar_init(k_empty[2 * i], 1); mbar_init(k_empty[2 * i + 1], 1); }
+        for (int i = 0; i < kVStages; ++i) { mbar_init(v_full[i], 1); mbar_init(v_empty[2 * i], 1); mbar_init(v_empty[2 * i + 1], 1); }
         fence_barrier_init();
     }
-    if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)kTmemCols) : "memory");
+        tmem_relinquish();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
     // work index w -> (head, item): head-major so concurrently running CTAs share one head's K/V in L2.  Every role
     // reads only the fields it needs from the item's two slot records.
@@ -369,9 +378,9 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 for (int s = 0; s < 2; ++s) {
                     if (nk[s] == 0) continue;
                     const uint32_t m = nq[s]++;
-                    mbar_wait(&q_empty[s], (m & 1) ^ 1);
-                    mbar_arrive_expect_tx(&q_full[s], kQBytes);
-                    tma_load_2d(sm_q + s * kQBytes, &tmQ, &q_full[s], col, qrow[s]);
+                    mbar_wait(q_empty[s], (m & 1) ^ 1);
+                    mbar_arrive_expect_tx(q_full[s], kQBytes);
+                    tma_load_2d(sm_q + s * kQBytes, &tmQ, q_full[s], col, qrow[s]);
                 }
                 // K / V blocks in exactly the order the MMA warps consume them: K of block j+1 before V of block j
                 const int nkmax = max(nk[0], nk[1]);
@@ -379,18 +388,18 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 auto load_k = [&](int j, int s) {
                     const uint32_t idx = base + ring_offset(j, s, same, nk[0], nk[1]);
                     const uint32_t st = idx % kKStages;
-                    mbar_wait(&k_empty[2 * st], ((idx / kKStages) & 1) ^ 1);
-                    mbar_wait(&k_empty[2 * st + 1], ((idx / kKStages) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&k_full[st], kKvBytes);
-                    tma_load_2d(sm_k + st * kKvBytes, &tmK, &k_full[st], col, krow[s] + j * kKB);
+                    mbar_wait(k_empty[2 * st], ((idx / kKStages) & 1) ^ 1);
+                    mbar_wait(k_empty[2 * st + 1], ((idx / kKStages) & 1) ^ 1);
+                    mbar_arrive_expect_tx(k_full[st], kKvBytes);
+                    tma_load_2d(sm_k + st * kKvBytes, &tmK, k_full[st], col, krow[s] + j * kKB);
                 };
                 auto load_v = [&](int j, int s) {
                     const uint32_t idx = base + ring_offset(j, s, same, nk[0], nk[1]);
                     const uint32_t st = idx % kVStages;
-                    mbar_wait(&v_empty[2 * st], ((idx / kVStages) & 1) ^ 1);
-                    mbar_wait(&v_empty[2 * st + 1], ((idx / kVStages) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&v_full[st], kKvBytes);
-                    tma_load_2d(sm_v + st * kKvBytes, &tmV, &v_full[st], col, krow[s] + j * kKB);
+                    mbar_wait(v_empty[2 * st], ((idx / kVStages) & 1) ^ 1);
+                    mbar_wait(v_empty[2 * st + 1], ((idx / kVStages) & 1) ^ 1);
+                    mbar_arrive_expect_tx(v_full[st], kKvBytes);
+                    tma_load_2d(sm_v + st * kKvBytes, &tmV, v_full[st], col, krow[s] + j * kKB);
                 };
 #pragma unroll
                 for (int s = 0; s < 2; ++s) if (nk[s] > 0 && !(s == 1 && same)) load_k(0, s);
@@ -411,8 +420,8 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             constexpr uint32_t idesc_qk = umma_idesc_bf16(128, kKB);                         // A, B K-major
             constexpr uint32_t idesc_pv = umma_idesc_bf16(128, HD) | (1u << 16);            // B (= V) MN-major
             const uint32_t s_tmem = tmem_base + s * kKB, o_tmem = tmem_base + 128 + s * 64;
-            const uint64_t q_desc = umma_desc_kmajor_sw128(smem_u32(sm_q + s * kQBytes));
-            const uint64_t p_desc = umma_desc_kmajor_sw128(smem_u32(sm_p + s * kQBytes));
+            const uint64_t q_desc = umma_desc_kmajor_sw128(sm_q + s * kQBytes);
+            const uint64_t p_desc = umma_desc_kmajor_sw128(sm_p + s * kQBytes);
             struct It { int nk0, nk1, my_nk; uint32_t base, tile0; bool same; };
             uint32_t ring = 0, n_tiles = 0, n_q = 0, n_done = 0;      // ring position, score tiles / items started / finished
             int w = blockIdx.x;
@@ -431,7 +440,7 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 }
                 return false;
             };
-            auto ready = [&](uint64_t* bar, uint32_t parity, bool blocking) -> bool {
+            auto ready = [&](SmemBar bar, uint32_t parity, bool blocking) -> bool {
                 if (blocking) { mbar_wait(bar, parity); return true; }
                 return mbar_test_wait(bar, parity);
             };
@@ -439,20 +448,20 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             auto issue_qk = [&](It& it, int j, bool blocking) -> bool {
                 const uint32_t idx = it.base + ring_offset(j, s, it.same, it.nk0, it.nk1);
                 const uint32_t st = idx % kKStages;
-                if (j == 0 && !ready(&q_full[s], n_q & 1, blocking)) return false;
-                if (!ready(&k_full[st], (idx / kKStages) & 1, blocking)) return false;
-                if (!ready(&s_empty[s], (n_tiles & 1) ^ 1, blocking)) return false;      // previous scores are in registers
+                if (j == 0 && !ready(q_full[s], n_q & 1, blocking)) return false;
+                if (!ready(k_full[st], (idx / kKStages) & 1, blocking)) return false;
+                if (!ready(s_empty[s], (n_tiles & 1) ^ 1, blocking)) return false;      // previous scores are in registers
                 if (j == 0) { ++n_q; it.tile0 = n_tiles; }
                 ++n_tiles;
                 tc_fence_after();
                 if (elect_one()) {                            // the whole warp keeps the (uniform) books, one lane issues
-                    const uint64_t db = umma_desc_kmajor_sw128(smem_u32(sm_k + st * kKvBytes));
+                    const uint64_t db = umma_desc_kmajor_sw128(sm_k + st * kKvBytes);
 #pragma unroll
                     for (int k = 0; k < HD / 16; ++k) umma_bf16(s_tmem, q_desc + 2 * k, db + 2 * k, idesc_qk, k != 0);
-                    umma_commit(&s_full[s]);
-                    umma_commit(&k_empty[2 * st + s]);
-                    if (!it.same) umma_commit(&k_empty[2 * st + (s ^ 1)]);    // sole user: the other slot's release too
-                    if (j + 1 == it.my_nk) umma_commit(&q_empty[s]);          // last Q K^T of the item: Q slot may be refilled
+                    umma_commit(s_full[s]);
+                    umma_commit(k_empty[2 * st + s]);
+                    if (!it.same) umma_commit(k_empty[2 * st + (s ^ 1)]);    // sole user: the other slot's release too
+                    if (j + 1 == it.my_nk) umma_commit(q_empty[s]);          // last Q K^T of the item: Q slot may be refilled
                 }
                 __syncwarp();
                 return true;
@@ -473,19 +482,19 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     // ---- O += P(j) V(j) ----
                     const uint32_t idx = cur.base + ring_offset(j, s, cur.same, cur.nk0, cur.nk1);
                     const uint32_t st = idx % kVStages;
-                    if (j == 0) mbar_wait(&o_empty[s], (n_done & 1) ^ 1);   // previous item's O has been read out
-                    mbar_wait(&v_full[st], (idx / kVStages) & 1);
-                    mbar_wait(&p_full[s], (cur.tile0 + j) & 1);
+                    if (j == 0) mbar_wait(o_empty[s], (n_done & 1) ^ 1);   // previous item's O has been read out
+                    mbar_wait(v_full[st], (idx / kVStages) & 1);
+                    mbar_wait(p_full[s], (cur.tile0 + j) & 1);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t vb = smem_u32(sm_v + st * kKvBytes);
+                        const uint32_t vb = sm_v + st * kKvBytes;
                         #pragma unroll
                         for (int kk = 0; kk < kKB / 16; ++kk)
                             umma_bf16(o_tmem, p_desc + 2 * kk, umma_desc_kmajor_sw128(vb + kk * 2048), idesc_pv, (j | kk) != 0);
-                        umma_commit(&p_empty[s]);
-                        umma_commit(&v_empty[2 * st + s]);
-                        if (!cur.same) umma_commit(&v_empty[2 * st + (s ^ 1)]);
-                        if (j + 1 == cur.my_nk) umma_commit(&o_full[s]);
+                        umma_commit(p_empty[s]);
+                        umma_commit(v_empty[2 * st + s]);
+                        if (!cur.same) umma_commit(v_empty[2 * st + (s ^ 1)]);
+                        if (j + 1 == cur.my_nk) umma_commit(o_full[s]);
                     }
                     __syncwarp();
                 }
@@ -503,7 +512,7 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int row = quad * 32 + lane;                     // row inside the 128-row query tile
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
         const uint32_t s_addr = t_lane + s * kKB, o_addr = t_lane + 128 + s * 64;
-        const uint32_t my_p = smem_u32(sm_p + s * kQBytes) + row * 128;    // this row of the P tile (shared-space address)
+        const uint32_t my_p = sm_p + s * kQBytes + row * 128;    // this row of the P tile (shared-space address)
         uint32_t n_tiles = 0, n_mine = 0;                     // score tiles / items this slot has processed so far
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
             const int head = w / p.n_items, item = w - head * p.n_items;
@@ -516,7 +525,7 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             float m_ref = 0.f, l_run = 0.f;
             for (int j = 0; j < my_nk; ++j) {
                 const uint32_t m = n_tiles++;
-                mbar_wait(&s_full[s], m & 1);
+                mbar_wait(s_full[s], m & 1);
                 tc_fence_after();
                 // ---- scores of this row -> registers; then the score buffer is free for the next Q K^T ----
                 uint32_t r[64];
@@ -530,16 +539,16 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #endif
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&s_empty[s]);
-                softmax_tile<HD, ALIBI>(r, o_addr, j == 0, &p_empty[s], (m & 1) ^ 1, p.scale_log2, slope, qpos, j * kKB,
+                if (lane == 0) mbar_arrive(s_empty[s]);
+                softmax_tile<HD, ALIBI>(r, o_addr, j == 0, p_empty[s], (m & 1) ^ 1, p.scale_log2, slope, qpos, j * kKB,
                                         me.w, m_ref, l_run, my_p, row, lane);
                 fence_proxy_async_smem();                     // generic-proxy P writes -> visible to the UMMA (async proxy)
                 tc_fence_before();                            // orders a possible tcgen05.st rescale before the PV
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&p_full[s]);
+                if (lane == 0) mbar_arrive(p_full[s]);
             }
             // ---- epilogue: O_s / l -> bf16 -> global ----
-            mbar_wait(&o_full[s], n_mine & 1);
+            mbar_wait(o_full[s], n_mine & 1);
             ++n_mine;
             tc_fence_after();
             uint32_t o0[32], o1[32];
@@ -549,7 +558,7 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&o_empty[s]);          // O_s may be overwritten by the next item's first P V
+            if (lane == 0) mbar_arrive(o_empty[s]);          // O_s may be overwritten by the next item's first P V
             if (row < me.y) {
                 const float inv = 1.0f / l_run;
                 __nv_bfloat16* dst = p.o + (size_t)(me.x + row) * p.ldo + head * HD;

@@ -86,21 +86,33 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 }
 
 // ---- mbarrier ----------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+// A barrier named by its 32-bit shared-space address.  Kernels whose warps hand-shake every few hundred cycles keep
+// ONE such base in a register and index it: going through a generic pointer makes the compiler rebuild the shared
+// window base (S2UR + ULEA, a short-scoreboard stall) at every use.
+struct SmemBar {
+    uint32_t addr;
+    __device__ __forceinline__ SmemBar operator[](int i) const { return SmemBar{addr + 8u * (uint32_t)i}; }
+};
+__device__ __forceinline__ SmemBar smem_bar(uint64_t* bar) { return SmemBar{smem_u32(bar)}; }
+__device__ __forceinline__ void mbar_init(SmemBar bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar.addr), "r"(count));
 }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { mbar_init(smem_bar(bar), count); }
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(SmemBar bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar.addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { mbar_arrive(smem_bar(bar)); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(SmemBar bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar.addr), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
+    mbar_arrive_expect_tx(smem_bar(bar), bytes);
 }
 // Potentially blocking test (the hardware may suspend the thread for a short, implementation-defined time).  An
 // explicit long suspend-time hint was measured: it saves issue slots but wakes the waiter late (attention and the
@@ -127,17 +139,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Non-blocking test of a phase.
-__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_test_wait(SmemBar bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
         "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
         "selp.b32 %0, 1, 0, P1;\n\t}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(bar.addr), "r"(parity)
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) { return mbar_test_wait(smem_bar(bar), parity); }
 __device__ __forceinline__ uint64_t global_timer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -151,7 +164,7 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 // every kernel that waits on a barrier an ABI stack frame and cost the attention kernels the whole 31 % again; build
 // with -DVF_WATCHDOG_VERBOSE to get the message (block, thread, barrier, parity) when chasing a deadlock.
 template <int SLEEP_NS>
-__device__ __forceinline__ void mbar_wait_impl(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_impl(SmemBar bar, uint32_t parity) {
     uint32_t spins = 0;
     uint64_t t0 = 0;
     while (!mbar_test_wait(bar, parity)) {
@@ -162,7 +175,7 @@ __device__ __forceinline__ void mbar_wait_impl(uint64_t* bar, uint32_t parity) {
             if (now - t0 > VF_WATCHDOG_NS) {
 #ifdef VF_WATCHDOG_VERBOSE
                 printf("vf: mbarrier watchdog: block %d thread %d barrier smem+0x%x parity %u\n", blockIdx.x, threadIdx.x,
-                       smem_u32(bar), parity);
+                       bar.addr, parity);
 #pragma unroll 1
                 for (int i = 0; i < 1000; ++i) __nanosleep(1000000);
 #endif
@@ -171,23 +184,28 @@ __device__ __forceinline__ void mbar_wait_impl(uint64_t* bar, uint32_t parity) {
         }
     }
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_impl<0>(bar, parity); }
+__device__ __forceinline__ void mbar_wait(SmemBar bar, uint32_t parity) { mbar_wait_impl<0>(bar, parity); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_impl<0>(smem_bar(bar), parity); }
 // The same wait for warps that share a scheduler with working warps (TMA producers, MMA issuers): a tight spin loop
 // is always ready to issue and takes up to a third of the scheduler's issue slots from the warps doing arithmetic
 // (in-kernel clock stamps: the 64-key softmax tile of the attention kernel is issue bound).  Sleeping ~30 ns between
 // polls costs far less than the microsecond wake-up of mbarrier.try_wait.
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) { mbar_wait_impl<32>(bar, parity); }
+__device__ __forceinline__ void mbar_wait_relaxed(SmemBar bar, uint32_t parity) { mbar_wait_impl<32>(bar, parity); }
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) { mbar_wait_impl<32>(smem_bar(bar), parity); }
 
 // ---- TMA (cp.async.bulk.tensor) -----------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
 // 2-D tile load: coordinates are (c0 = innermost element index, c1 = row index)
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap, SmemBar bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar.addr), "r"(c0), "r"(c1)
         : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1) {
+    tma_load_2d(smem_u32(smem_dst), tmap, smem_bar(bar), c0, c1);
 }
 
 // L2 prefetch of a 2-D tile (no shared-memory destination, no barrier): the tile is resident in L2 when ordinary
@@ -231,10 +249,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 }
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread retire
 // (implies tcgen05.fence::before_thread_sync).
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+__device__ __forceinline__ void umma_commit(SmemBar bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar.addr)
                  : "memory");
 }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) { umma_commit(smem_bar(bar)); }
 // ---- CTA pair (cta_group::2): two CTAs of a cluster cooperate on one 256-row UMMA tile.  The leader (even rank)
 // issues the MMA; each CTA loads its own A rows and its half of the B rows; barriers of the leader are addressed from
 // the peer by clearing the rank bit of the shared::cluster address (same offset in the even CTA of the pair). ----

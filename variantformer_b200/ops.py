@@ -26,25 +26,36 @@ class EventProfiler:
         e.record()
         return e
 
-    def end(self, e0, kind, flops=0.0):
+    def end(self, e0, kind, flops=0.0, detail=None):
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
-        self.items.append((kind, float(flops), e0, e1))
+        self.items.append((kind, float(flops), e0, e1, detail))
 
     def summarize(self):
         torch.cuda.synchronize()
         out = {}
-        for kind, flops, e0, e1 in self.items:
+        for kind, flops, e0, e1, _ in self.items:
             d = out.setdefault(kind, {"ms": 0.0, "flops": 0.0, "n": 0})
+            d["ms"] += e0.elapsed_time(e1); d["flops"] += flops; d["n"] += 1
+        return out
+
+    def summarize_detail(self):
+        """Same, keyed by the launch's shape string (GEMM: "N x K epilogue flags"; attention: heads x head_dim, bias)."""
+        torch.cuda.synchronize()
+        out = {}
+        for kind, flops, e0, e1, detail in self.items:
+            if detail is None:
+                continue
+            d = out.setdefault(f"{kind} {detail}", {"ms": 0.0, "flops": 0.0, "n": 0})
             d["ms"] += e0.elapsed_time(e1); d["flops"] += flops; d["n"] += 1
         return out
 
 
 class _timed:
-    __slots__ = ("kind", "flops", "e0")
+    __slots__ = ("kind", "flops", "e0", "detail")
 
-    def __init__(self, kind, flops=0.0):
-        self.kind, self.flops, self.e0 = kind, flops, None
+    def __init__(self, kind, flops=0.0, detail=None):
+        self.kind, self.flops, self.e0, self.detail = kind, flops, None, detail
 
     def __enter__(self):
         if PROFILER is not None:
@@ -54,10 +65,12 @@ class _timed:
         global LAUNCHES
         LAUNCHES += 1
         if self.e0 is not None and PROFILER is not None:
-            PROFILER.end(self.e0, self.kind, self.flops)
+            PROFILER.end(self.e0, self.kind, self.flops, self.detail() if callable(self.detail) else self.detail)
         return False
 
 
+_EPI_NAME = {EPI_BIAS_BF16: "bias", EPI_BIAS_GEGLU_BF16: "geglu", EPI_BIAS_GELU_BF16: "gelu", EPI_BIAS_RESID_F32: "resid",
+             EPI_BIAS_F32: "f32"}
 _OUT_DTYPE = {EPI_BIAS_BF16: torch.bfloat16, EPI_BIAS_GEGLU_BF16: torch.bfloat16, EPI_BIAS_GELU_BF16: torch.bfloat16,
               EPI_BIAS_RESID_F32: torch.float32, EPI_BIAS_F32: torch.float32}
 
@@ -99,7 +112,11 @@ def gemm(a, w, epilogue, bias=None, resid=None, out=None, out2=None, ln=None, st
         assert ln_colsum.dtype == torch.float32 and ln_colsum.numel() == N and ln_colsum.is_contiguous()
     if stats_out is not None:
         assert stats_out.dtype == torch.float32 and stats_out.shape == (M, stats_parts(N), 2) and stats_out.is_contiguous()
-    with _timed("gemm", 2.0 * M * N * K):
+    with _timed("gemm", 2.0 * M * N * K, lambda: (
+            f"N={N} K={K} {_EPI_NAME[epilogue]}" + (" ln" if ln is not None else "") +
+            ("" if resid is None else " resid16" if resid.dtype == torch.bfloat16 else " resid32") +
+            (" out32" if out is not None and out.dtype == torch.float32 else "") + (" mirror" if out2 is not None else "") +
+            (" stats" if stats_out is not None else "") + (" M>=64k" if M >= 65536 else " M<64k"))):
         check(_lib.lib().vf_gemm_bf16_ln(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, epilogue, ptr(bias),
                                          ptr(resid), int(resid is not None and resid.dtype == torch.bfloat16),
                                          resid.stride(0) if resid is not None else 0, ptr(out),
@@ -238,7 +255,8 @@ def attention_mc(q, k, v, slots: SlotMap, heads, head_dim, slopes=None, out=None
         assert t.is_cuda and t.dtype == torch.bfloat16 and t.stride(1) == 1
     if out is None:
         out = torch.empty((q.shape[0], heads * head_dim), dtype=torch.bfloat16, device=q.device)
-    with _timed("attention", 4.0 * slots.qk_pairs * heads * head_dim):
+    with _timed("attention", 4.0 * slots.qk_pairs * heads * head_dim,
+                lambda: f"h={heads} hd={head_dim}{' alibi' if slopes is not None else ''} rows={q.shape[0]} keys={k.shape[0]}"):
         check(_lib.lib().vf_attention_mc_varlen(ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0),
                                                 ptr(out), out.stride(0), q.shape[0], k.shape[0], ptr(slots.table),
                                                 slots.n_items, heads, head_dim, ptr(slopes), stream()))
