@@ -263,7 +263,7 @@ __device__ __forceinline__ void softmax_rest(uint32_t (&r)[64], float mx, float 
 #endif
 #pragma unroll
     for (int q8 = 0; q8 < 8; ++q8) {                          // 8 probabilities -> one 16-byte chunk of the P row
-        const uint32_t dst = p_row + ((q8 ^ (row & 7)) * 16);
+        const uint32_t dst = p_row ^ (q8 * 16);              // p_row carries the row's swizzle term (see the caller)
         if (KIND == 3 && 4 * q8 >= ndone)
             asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
         else
@@ -512,7 +512,15 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int row = quad * 32 + lane;                     // row inside the 128-row query tile
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
         const uint32_t s_addr = t_lane + s * kKB, o_addr = t_lane + 128 + s * 64;
-        const uint32_t my_p = sm_p + s * kQBytes + row * 128;    // this row of the P tile (shared-space address)
+        // this row of the P tile (shared-space address, 128-byte aligned) with the row's SWIZZLE_128B term folded in:
+        // chunk q8 of the row lives at my_p ^ (q8 * 16)
+        const uint32_t my_p = (sm_p + s * kQBytes + row * 128) ^ ((row & 7) * 16);
+        // this slot's barriers, relative to ONE register (index = the [slot] arrays' offsets from `bars`)
+        uint32_t sb_a = bars[s].addr;
+        if constexpr (HD == 48) asm volatile("mov.b32 %0, %0;" : "+r"(sb_a));
+        const SmemBar sb{sb_a};
+        const SmemBar my_s_full = sb[4], my_s_empty = sb[6], my_p_full = sb[8], my_p_empty = sb[10], my_o_full = sb[12],
+                      my_o_empty = sb[14];
         uint32_t n_tiles = 0, n_mine = 0;                     // score tiles / items this slot has processed so far
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
             const int head = w / p.n_items, item = w - head * p.n_items;
@@ -525,7 +533,7 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             float m_ref = 0.f, l_run = 0.f;
             for (int j = 0; j < my_nk; ++j) {
                 const uint32_t m = n_tiles++;
-                mbar_wait(s_full[s], m & 1);
+                mbar_wait(my_s_full, m & 1);
                 tc_fence_after();
                 // ---- scores of this row -> registers; then the score buffer is free for the next Q K^T ----
                 uint32_t r[64];
@@ -539,16 +547,16 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #endif
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(s_empty[s]);
-                softmax_tile<HD, ALIBI>(r, o_addr, j == 0, p_empty[s], (m & 1) ^ 1, p.scale_log2, slope, qpos, j * kKB,
+                if (lane == 0) mbar_arrive(my_s_empty);
+                softmax_tile<HD, ALIBI>(r, o_addr, j == 0, my_p_empty, (m & 1) ^ 1, p.scale_log2, slope, qpos, j * kKB,
                                         me.w, m_ref, l_run, my_p, row, lane);
                 fence_proxy_async_smem();                     // generic-proxy P writes -> visible to the UMMA (async proxy)
                 tc_fence_before();                            // orders a possible tcgen05.st rescale before the PV
                 __syncwarp();
-                if (lane == 0) mbar_arrive(p_full[s]);
+                if (lane == 0) mbar_arrive(my_p_full);
             }
             // ---- epilogue: O_s / l -> bf16 -> global ----
-            mbar_wait(o_full[s], n_mine & 1);
+            mbar_wait(my_o_full, n_mine & 1);
             ++n_mine;
             tc_fence_after();
             uint32_t o0[32], o1[32];
@@ -558,7 +566,7 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(o_empty[s]);          // O_s may be overwritten by the next item's first P V
+            if (lane == 0) mbar_arrive(my_o_empty);          // O_s may be overwritten by the next item's first P V
             if (row < me.y) {
                 const float inv = 1.0f / l_run;
                 __nv_bfloat16* dst = p.o + (size_t)(me.x + row) * p.ldo + head * HD;

@@ -58,6 +58,7 @@ struct GemmParams {
     const float* ln_colsum;  //                 fp32 [N] column sums of the gamma-folded weight (layout of `bias`)
     float ln_inv_d, ln_eps;  //                 1 / normalised width, eps
     float* stats_out;        // fp32 outputs: partial (sum, sum of squares) of every output row -> [M, 2*n_tiles, 2], or nullptr
+    int tile_chunked;        // tile schedule: 1 = each unit walks a contiguous run of tiles (n fastest), 0 = round-robin
     int prefetch_resid;      // producer warp bulk-prefetches the residual tile into L2 (VF_GEMM_RESID_PREFETCH=1; off by
                              // default: measured 5-10 % slower than the epilogue's own one-slab-ahead register prefetch)
 };
@@ -236,6 +237,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;
     const int m_tiles = (p.M + BM * CTAS - 1) / (BM * CTAS), n_tiles = (p.N + BN - 1) / BN;
     const int num_tiles = m_tiles * n_tiles;
+    // Tile schedule of this unit: t = t_first + i * t_step, i < t_count.  Tiles are numbered n-fastest.  "chunked": a unit
+    // owns a contiguous run, i.e. it walks the n-tiles of one row block one after the other, so the LayerNorm row
+    // statistics are reduced once per row block instead of once per tile (their load was the top stall of the K = 512
+    // epilogues) and the A tile is re-read while it is hot.  "strided": round-robin over the units.
+    int t_first, t_step, t_count;
+    if (p.tile_chunked) {
+        const int per = (num_tiles + n_units - 1) / n_units;
+        t_first = unit * per; t_step = 1; t_count = max(0, min(per, num_tiles - t_first));
+    } else {
+        t_first = unit; t_step = n_units; t_count = unit < num_tiles ? (num_tiles - unit + n_units - 1) / n_units : 0;
+    }
     const int k_blocks = (p.K + BK - 1) / BK;
 
     if (warp == 0 && elect_one()) {
@@ -263,7 +275,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // ================= TMA producer =================
             if (elect_one()) {
                 int stage = 0; uint32_t phase = 0;
-                for (int t = unit; t < num_tiles; t += n_units) {
+                for (int ti = 0; ti < t_count; ++ti) {
+                    const int t = t_first + ti * t_step;
                     const int m0 = (t / n_tiles) * BM * CTAS + rank * BM, n0 = (t % n_tiles) * BN;
                     if constexpr (EPI == VF_EPI_BIAS_RESID_F32) {
                         // the epilogue of this tile runs one mainloop from now: pull its residual into L2 meanwhile
@@ -295,7 +308,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (rank == 0 && elect_one()) {                  // the pair's leader issues for both CTAs
                 constexpr uint32_t idesc = umma_idesc_bf16(BM * CTAS, BN);
                 int stage = 0; uint32_t phase = 0; int it = 0;
-                for (int t = unit; t < num_tiles; t += n_units, ++it) {
+                for (; it < t_count; ++it) {
                     const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
                     mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
@@ -341,20 +354,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         RowStats rs;
         float4 rr4[4][8];                                     // residual of slab i of a tile (RESID epilogue only)
         if constexpr (EPI == VF_EPI_BIAS_RESID_F32) {
-            if (unit < num_tiles) {                           // prime the slab stream: slabs 0 and 1 of the first tile
-                const int m0f = (unit / n_tiles) * BM * CTAS + rank * BM, n0f = (unit % n_tiles) * BN;
+            if (t_count > 0) {                                // prime the slab stream: slabs 0 and 1 of the first tile
+                const int m0f = (t_first / n_tiles) * BM * CTAS + rank * BM, n0f = (t_first % n_tiles) * BN;
                 load_resid_slab(p, m0f + quad * 32, n0f + half * 32, lane, rr4[0]);
                 load_resid_slab(p, m0f + quad * 32, n0f + (half + 2) * 32, lane, rr4[1]);
             }
         }
-        int it = 0;
-        for (int t = unit; t < num_tiles; t += n_units, ++it) {
+        int last_m0 = -1;
+        float ln_a = 1.f, ln_c = 0.f;
+        for (int it = 0; it < t_count; ++it) {
+            const int t = t_first + it * t_step;
             const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
             const int m0 = (t / n_tiles) * BM * CTAS + rank * BM, n0 = (t % n_tiles) * BN;
             const int row0 = m0 + quad * 32;
-            // LayerNorm fold: this thread's row is normalised as  ln_a * acc + ln_c * colsum[n] + bias'[n]
-            float ln_a = 1.f, ln_c = 0.f;
-            if (ln && row0 + lane < p.M) {
+            // LayerNorm fold: this thread's row is normalised as  ln_a * acc + ln_c * colsum[n] + bias'[n]; the pair is
+            // kept while the unit stays on the same row block
+            if (ln && m0 != last_m0) { ln_a = 1.f; ln_c = 0.f; }
+            if (ln && m0 != last_m0 && row0 + lane < p.M) {
                 const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + (size_t)(row0 + lane) * p.ln_parts;
                 float2 st = make_float2(0.f, 0.f);
                 if (p.ln_parts > 1 && p.ln_parts <= 16 && (p.ln_parts & 1) == 0) {
@@ -376,6 +392,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 ln_a = rsqrtf(var + p.ln_eps);
                 ln_c = -ln_a * mean;
             }
+            last_m0 = m0;
             rs.clear();
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
@@ -441,7 +458,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const int c = half + 2 * i;
                     const int col0 = n0 + c * 32;
                     {   // prefetch distance 2: slab i+2 of this tile, or slab i-2 of this warp's next tile
-                        const int tn = i + 2 < kSlabs ? t : t + n_units;
+                        const int tn = i + 2 < kSlabs ? t : (it + 1 < t_count ? t + t_step : num_tiles);
                         const int cn = half + 2 * ((i + 2) & 3);
                         const int m0n = (tn / n_tiles) * BM * CTAS + rank * BM, n0n = (tn % n_tiles) * BN;
                         if (tn < num_tiles) load_resid_slab(p, m0n + quad * 32, n0n + cn * 32, lane, rr4[(i + 2) & 3]);
@@ -660,6 +677,10 @@ static int make_tmap_resid(CUtensorMap* tm, const float* base, int rows, int col
 static int g_num_sms = 0;
 static bool g_debug_simt = false;
 static int g_resid_prefetch = 0;
+// Tile schedule: -1 = by shape (chunked for LayerNorm-folded epilogues with K <= 512, whose epilogue is the critical
+// path: +5-10 % there; round-robin otherwise: concurrently running CTAs then share A tiles in L2, worth 15 % at
+// K = 1536).  VF_GEMM_TILE_ORDER=strided|chunked forces one (A/B timing).
+static int g_tile_chunked = -1;
 // CTA-pair kernel for M >= g_pair_min_rows (VF_GEMM_PAIR_MIN_ROWS; 0 = never) and K >= g_pair_min_k: measured 6-12 %
 // faster than the single-CTA kernel at K = 1024 / 1536 (Wqkv 101k x 4608 x 1536: 1.03 -> 0.90 ms = 1590 TFLOP/s, cuBLAS
 // 0.91), not at K = 512 where the epilogue, not the operand traffic, is the limit.
@@ -737,6 +758,8 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
         g_debug_simt = e && e[0] == '1';
         const char* e2 = getenv("VF_GEMM_RESID_PREFETCH");
         g_resid_prefetch = e2 && e2[0] == '1';
+        const char* e5 = getenv("VF_GEMM_TILE_ORDER");
+        if (e5) g_tile_chunked = e5[0] == 'c' ? 1 : e5[0] == 's' ? 0 : -1;
         const char* e3 = getenv("VF_GEMM_PAIR_MIN_ROWS");
         if (e3) g_pair_min_rows = atoi(e3);
         const char* e4 = getenv("VF_GEMM_PAIR_MIN_K");
@@ -753,7 +776,7 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
     VF_REQUIRE(out || (out_f32 && out2), "gemm: no output buffer (only the fp32 epilogues may write their bf16 mirror alone)");
     VF_REQUIRE(!out || (ldo >= n_out && (ldo % 8) == 0), "gemm: bad output stride %d", ldo);
     VF_REQUIRE(!resid_bf16 || epi == VF_EPI_BIAS_RESID_F32, "gemm: a bf16 residual needs the residual epilogue");
-    GemmParams p;
+    GemmParams p{};
     p.M = M; p.N = N; p.K = K; p.bias = bias; p.ldr = ldr; p.out = out; p.ldo = ldo;
     p.resid = resid_bf16 ? nullptr : reinterpret_cast<const float*>(resid);
     p.resid16 = resid_bf16 ? reinterpret_cast<const __nv_bfloat16*>(resid) : nullptr;
@@ -764,6 +787,8 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
     VF_REQUIRE(!stats_out || !out_bf16, "gemm: row statistics are produced by the fp32 epilogues only");
     p.ln_stats = ln_stats; p.ln_parts = ln_parts; p.ln_colsum = ln_colsum;
     p.ln_inv_d = ln_dim > 0 ? 1.0f / (float)ln_dim : 0.f; p.ln_eps = ln_eps; p.stats_out = stats_out;
+    p.tile_chunked = g_tile_chunked >= 0 ? g_tile_chunked : (ln_stats != nullptr && K <= 512);
+    p.prefetch_resid = g_resid_prefetch && epi == VF_EPI_BIAS_RESID_F32 && resid && !resid_bf16;
     if (g_debug_simt) {
         if (stats_out)
             VF_CUDA_OK(cudaMemsetAsync(stats_out, 0, (size_t)M * 2 * ((N + BN - 1) / BN) * 2 * sizeof(float), stream));
