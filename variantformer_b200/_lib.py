@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libvf_b200.so")
+# VF_LIB: a differently compiled build of the SAME library (A/B timing of kernel variants, tools/build_variant.py)
+LIB_PATH = os.path.abspath(os.environ["VF_LIB"]) if os.environ.get("VF_LIB") else os.path.join(_HERE, "csrc", "libvf_b200.so")
 
 EPI_BIAS_BF16, EPI_BIAS_GEGLU_BF16, EPI_BIAS_RESID_F32, EPI_BIAS_F32, EPI_BIAS_GELU_BF16 = range(5)
 

@@ -62,6 +62,15 @@ struct Params {
     float scale_log2;
 };
 
+// producer waits (a stage to be released): optionally polled with a short sleep, see vf_gemm.cu (measured: no gain)
+#ifndef VF_RELAXED_WAITS
+#define VF_RELAXED_WAITS 0
+#endif
+#if VF_RELAXED_WAITS
+#define VF_IDLE_WAIT mbar_wait_relaxed
+#else
+#define VF_IDLE_WAIT mbar_wait
+#endif
 #ifndef VF_ATTN_REGS_LO
 #define VF_ATTN_REGS_LO 32        // producer / MMA issuer warpgroup; 128 * LO + 256 * HI <= 384 * 80
 #define VF_ATTN_REGS_HI 104       // softmax warpgroups
@@ -378,7 +387,7 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 for (int s = 0; s < 2; ++s) {
                     if (nk[s] == 0) continue;
                     const uint32_t m = nq[s]++;
-                    mbar_wait(q_empty[s], (m & 1) ^ 1);
+                    VF_IDLE_WAIT(q_empty[s], (m & 1) ^ 1);
                     mbar_arrive_expect_tx(q_full[s], kQBytes);
                     tma_load_2d(sm_q + s * kQBytes, &tmQ, q_full[s], col, qrow[s]);
                 }
@@ -388,16 +397,16 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 auto load_k = [&](int j, int s) {
                     const uint32_t idx = base + ring_offset(j, s, same, nk[0], nk[1]);
                     const uint32_t st = idx % kKStages;
-                    mbar_wait(k_empty[2 * st], ((idx / kKStages) & 1) ^ 1);
-                    mbar_wait(k_empty[2 * st + 1], ((idx / kKStages) & 1) ^ 1);
+                    VF_IDLE_WAIT(k_empty[2 * st], ((idx / kKStages) & 1) ^ 1);
+                    VF_IDLE_WAIT(k_empty[2 * st + 1], ((idx / kKStages) & 1) ^ 1);
                     mbar_arrive_expect_tx(k_full[st], kKvBytes);
                     tma_load_2d(sm_k + st * kKvBytes, &tmK, k_full[st], col, krow[s] + j * kKB);
                 };
                 auto load_v = [&](int j, int s) {
                     const uint32_t idx = base + ring_offset(j, s, same, nk[0], nk[1]);
                     const uint32_t st = idx % kVStages;
-                    mbar_wait(v_empty[2 * st], ((idx / kVStages) & 1) ^ 1);
-                    mbar_wait(v_empty[2 * st + 1], ((idx / kVStages) & 1) ^ 1);
+                    VF_IDLE_WAIT(v_empty[2 * st], ((idx / kVStages) & 1) ^ 1);
+                    VF_IDLE_WAIT(v_empty[2 * st + 1], ((idx / kVStages) & 1) ^ 1);
                     mbar_arrive_expect_tx(v_full[st], kKvBytes);
                     tma_load_2d(sm_v + st * kKvBytes, &tmV, v_full[st], col, krow[s] + j * kKB);
                 };
@@ -517,7 +526,7 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const uint32_t my_p = (sm_p + s * kQBytes + row * 128) ^ ((row & 7) * 16);
         // this slot's barriers, relative to ONE register (index = the [slot] arrays' offsets from `bars`)
         uint32_t sb_a = bars[s].addr;
-        if constexpr (HD == 48) asm volatile("mov.b32 %0, %0;" : "+r"(sb_a));
+        if constexpr (HD == 48 && !ALIBI) asm volatile("mov.b32 %0, %0;" : "+r"(sb_a));   // (a register too many with ALiBi)
         const SmemBar sb{sb_a};
         const SmemBar my_s_full = sb[4], my_s_empty = sb[6], my_p_full = sb[8], my_p_empty = sb[10], my_o_full = sb[12],
                       my_o_empty = sb[14];

@@ -30,6 +30,19 @@
 #include "vf_common.cuh"
 #include "vf_internal.h"
 
+// Waits of warps that are idle most of the time (producer, MMA issuer, epilogue warps waiting for a whole mainloop) can
+// poll with a ~30 ns sleep instead of a tight spin (-DVF_RELAXED_WAITS=1).  The step runs power capped, so the idea was
+// to leave issue slots and power to the working warps; measured on the whole step (same box, alternating): 218.2 ms
+// relaxed vs 216.2 ms tight, clocks unchanged — the late wake-ups cost more than the spinning.  Default: tight.
+#ifndef VF_RELAXED_WAITS
+#define VF_RELAXED_WAITS 0
+#endif
+#if VF_RELAXED_WAITS
+#define VF_IDLE_WAIT mbar_wait_relaxed
+#else
+#define VF_IDLE_WAIT mbar_wait
+#endif
+
 namespace vf {
 
 constexpr int BM = 128, BN = 256, BK = 64, kStages = 4;
@@ -287,7 +300,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         }
                     }
                     for (int kb = 0; kb < k_blocks; ++kb) {
-                        mbar_wait(&empty[stage], phase ^ 1);
+                        VF_IDLE_WAIT(&empty[stage], phase ^ 1);
                         if constexpr (CTAS == 2) {
                             // all four loads of the pair complete on the LEADER's barrier, which expects their total
                             if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * kStageBytesC);
@@ -310,11 +323,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 int stage = 0; uint32_t phase = 0; int it = 0;
                 for (; it < t_count; ++it) {
                     const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
-                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                    VF_IDLE_WAIT(&tmem_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * BN;
                     for (int kb = 0; kb < k_blocks; ++kb) {
-                        mbar_wait(&full[stage], phase);
+                        VF_IDLE_WAIT(&full[stage], phase);
                         tc_fence_after();
                         const uint64_t da = umma_desc_kmajor_sw128(smem_u32(smem_a + stage * kABytes));
                         const uint64_t db = umma_desc_kmajor_sw128(smem_u32(smem_b + stage * kBBytesC));
@@ -358,6 +371,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int m0f = (t_first / n_tiles) * BM * CTAS + rank * BM, n0f = (t_first % n_tiles) * BN;
                 load_resid_slab(p, m0f + quad * 32, n0f + half * 32, lane, rr4[0]);
                 load_resid_slab(p, m0f + quad * 32, n0f + (half + 2) * 32, lane, rr4[1]);
+                load_resid_slab(p, m0f + quad * 32, n0f + (half + 4) * 32, lane, rr4[2]);
             }
         }
         int last_m0 = -1;
@@ -394,7 +408,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             last_m0 = m0;
             rs.clear();
-            mbar_wait(&tmem_full[acc], acc_phase);
+            VF_IDLE_WAIT(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
             if constexpr (EPI == VF_EPI_BIAS_GEGLU_BF16) {
@@ -449,19 +463,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             } else if constexpr (EPI == VF_EPI_BIAS_RESID_F32) {
                 // The fp32 residual is the long-latency input of this epilogue (one DRAM round trip per slab) and it
                 // does not depend on the MMA: the slab stream of this warp (4 per tile, tile after tile) keeps the
-                // residual of the NEXT TWO slabs in flight in registers — across the tile boundary too — while the
-                // current slab is converted and stored.  rr4[i] belongs to slab i of a tile; slabs 0 and 1 of the first
+                // residual of the NEXT THREE slabs in flight in registers — across the tile boundary too — while the
+                // current slab is converted and stored.  rr4[i] belongs to slab i of a tile; slabs 0-2 of the first
                 // tile were primed before the loop.
                 uint32_t r[32];
 #pragma unroll
                 for (int i = 0; i < kSlabs; ++i) {
                     const int c = half + 2 * i;
                     const int col0 = n0 + c * 32;
-                    {   // prefetch distance 2: slab i+2 of this tile, or slab i-2 of this warp's next tile
-                        const int tn = i + 2 < kSlabs ? t : (it + 1 < t_count ? t + t_step : num_tiles);
-                        const int cn = half + 2 * ((i + 2) & 3);
+                    {   // prefetch distance 3 (the buffer slab i-1 just left): slab i+3 of this tile, or slab i-1 of
+                        // this warp's next tile.  (Distance 2 left the residual add on the long scoreboard for ~12 % of
+                        // the kernel's samples.)
+                        const int tn = i + 3 < kSlabs ? t : (it + 1 < t_count ? t + t_step : num_tiles);
+                        const int cn = half + 2 * ((i + 3) & 3);
                         const int m0n = (tn / n_tiles) * BM * CTAS + rank * BM, n0n = (tn % n_tiles) * BN;
-                        if (tn < num_tiles) load_resid_slab(p, m0n + quad * 32, n0n + cn * 32, lane, rr4[(i + 2) & 3]);
+                        if (tn < num_tiles) load_resid_slab(p, m0n + quad * 32, n0n + cn * 32, lane, rr4[(i + 3) & 3]);
                     }
                     if (col0 < p.N) {                                     // warp-uniform
                         tmem_ld_32x32(t_row + c * 32, r);
