@@ -28,6 +28,16 @@ sys.path.insert(0, ROOT)
 
 METRIC = "gene_x_tissue_predictions_per_s"
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the first
+# communicator), so file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved descriptor.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _RESULT_OUT.write(json.dumps(obj) + "\n")
+    _RESULT_OUT.flush()
+
 
 def load_peaks():
     try:
@@ -173,7 +183,7 @@ def run_reference(args):
     v = float(np.mean([x["value"] for x in vals]))
     ms = 1e3 * float(np.mean([x["t_T1_s"] + x["t_T2_s"] for x in vals]))
     last = dict(vals[-1], value=v)
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "predictions/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -329,7 +339,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             sd_cpu = {k: v.float().cpu() for k, v in sd.items()}
             out["cpu_baseline"] = cpu_baseline(sd_cpu, cfg, hp, chroms, var, sets[0][0], C, T)
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
