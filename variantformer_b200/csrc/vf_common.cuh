@@ -85,6 +85,12 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     return v;
 }
 
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 // ---- mbarrier ----------------------------------------------------------------
 // A barrier named by its 32-bit shared-space address.  Kernels whose warps hand-shake every few hundred cycles keep
 // ONE such base in a register and index it: going through a generic pointer makes the compiler rebuild the shared

@@ -53,8 +53,10 @@ constexpr int kGemmThreads = (kFirstEpiWarp + kEpiWarps) * 32;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
 constexpr uint32_t kStageOutBytes = 32 * 32 * 4;      // per-epilogue-warp staging tile: 32 rows x 32 fp32 columns
-constexpr size_t kGemmSmem = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + kEpiWarps * kStageOutBytes +
-                             256 /*barriers*/;
+constexpr uint32_t kColVecBytes = 2 * BN * 4;         // bias and LayerNorm column sums of the tile's 256 columns
+// (no alignment slack: the dynamic shared memory of a kernel without static shared memory starts 1 KB aligned; the
+// kernel traps otherwise)
+constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + kEpiWarps * kStageOutBytes + 256 /*barriers*/ + kColVecBytes;
 
 struct GemmParams {
     int M, N, K;
@@ -230,7 +232,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const GemmParams& p = p_in;
 #endif
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw;
+    if (smem_u32(smem_raw) & 1023u) __trap();                // SWIZZLE_128B tiles need 1 KB alignment
     constexpr int kStg = CTAS == 2 ? kStagesPair : kStages;
     constexpr uint32_t kBBytesC = kBBytes / CTAS, kStageBytesC = kABytes + kBBytesC;
     uint8_t* smem_a = smem;                                  // kStg x 16 KB
@@ -242,6 +245,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* tmem_full = bars + 2 * kStg;          // [2]
     uint64_t* tmem_empty = bars + 2 * kStg + 2;     // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStg + 4);
+    const uint32_t colvec = smem_u32(bars) + 256;            // [256] bias | [256] LayerNorm column sums (shared-space address)
 
     const int warp = threadIdx.x >> 5;
     // work unit = CTA (CTAS 1) or CTA pair (CTAS 2); `rank` = this CTA's half of the pair's 256 rows / 256 W rows
@@ -376,11 +380,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         int last_m0 = -1;
         float ln_a = 1.f, ln_c = 0.f;
+        // Per-column epilogue vectors of a tile (bias, LayerNorm column sums) go through shared memory: one value per
+        // epilogue thread, requested a whole tile ahead, instead of 16-32 global loads per slab and warp whose L2 latency
+        // sat on the critical path of the K = 512 epilogues (39 % of their samples on the long scoreboard; only ~28 KB of
+        // L1 is left next to the operand ring).
+        const int etid = threadIdx.x - kFirstEpiWarp * 32;    // 0..255 = column of the tile
+        auto col_values = [&](int tile, float& b, float& cs) {
+            const int col = (tile % n_tiles) * BN + etid;
+            b = (p.bias && col < p.N) ? __ldg(p.bias + col) : 0.f;
+            cs = (ln && col < p.N) ? __ldg(p.ln_colsum + col) : 0.f;
+        };
+        float nb = 0.f, ncs = 0.f;
+        if (t_count > 0) col_values(t_first, nb, ncs);
         for (int it = 0; it < t_count; ++it) {
             const int t = t_first + it * t_step;
             const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
             const int m0 = (t / n_tiles) * BM * CTAS + rank * BM, n0 = (t % n_tiles) * BN;
             const int row0 = m0 + quad * 32;
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");      // previous tile's vectors are no longer read
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(colvec + etid * 4), "f"(nb) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(colvec + BN * 4 + etid * 4), "f"(ncs) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+            if (it + 1 < t_count) col_values(t + t_step, nb, ncs);
             // LayerNorm fold: this thread's row is normalised as  ln_a * acc + ln_c * colsum[n] + bias'[n]; the pair is
             // kept while the unit stays on the same row block
             if (ln && m0 != last_m0) { ln_a = 1.f; ln_c = 0.f; }
@@ -421,22 +442,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                 for (int i = 0; i < kSlabs; ++i) {
                     const int c = half + 2 * i;                           // 32-column slab of the 128 outputs
-                    // bias (and LayerNorm column sums) of the slab: 16-32 broadcast loads issued as ONE batch before
-                    // the TMEM wait.  Loaded next to their use they cost one L1 round trip each (8 per slab, exposed).
+                    // bias (and LayerNorm column sums) of the slab from the tile's shared-memory vectors: 16-32 broadcast
+                    // loads issued as ONE batch before the TMEM wait
                     float4 bu[8], bg[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        bu[j] = bg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p.bias) {
-                            bu[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c * 32) + j);
-                            bg[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 128 + c * 32) + j);
-                        }
+                        bu[j] = lds_f4(colvec + (c * 32 + 4 * j) * 4);
+                        bg[j] = lds_f4(colvec + (128 + c * 32 + 4 * j) * 4);
                     }
                     if (ln) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float4 su = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + c * 32) + j);
-                            const float4 sg = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + 128 + c * 32) + j);
+                            const float4 su = lds_f4(colvec + (BN + c * 32 + 4 * j) * 4);
+                            const float4 sg = lds_f4(colvec + (BN + 128 + c * 32 + 4 * j) * 4);
                             bu[j].x = fmaf(ln_c, su.x, bu[j].x); bu[j].y = fmaf(ln_c, su.y, bu[j].y);
                             bu[j].z = fmaf(ln_c, su.z, bu[j].z); bu[j].w = fmaf(ln_c, su.w, bu[j].w);
                             bg[j].x = fmaf(ln_c, sg.x, bg[j].x); bg[j].y = fmaf(ln_c, sg.y, bg[j].y);
@@ -484,8 +502,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         float4 bb[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            bb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (p.bias && col0 + 4 * j + 4 <= p.N) bb[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+                            bb[j] = lds_f4(colvec + (c * 32 + 4 * j) * 4);
                         }
                         tmem_ld_wait();
                         float v[32];
@@ -511,15 +528,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     float4 bb[8];                                         // bias (+ LayerNorm term) of the slab: one batch of
 #pragma unroll                                                            // broadcast loads issued before the TMEM wait
                     for (int j = 0; j < 8; ++j) {
-                        bb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p.bias && col0 + 4 * j + 4 <= p.N) bb[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+                        bb[j] = lds_f4(colvec + (c * 32 + 4 * j) * 4);
                     }
                     if constexpr (epi_is_bf16<EPI>()) {
                         if (ln) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                if (col0 + 4 * j + 4 <= p.N) {
-                                    const float4 sc = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0) + j);
+                                {
+                                    const float4 sc = lds_f4(colvec + (BN + c * 32 + 4 * j) * 4);
                                     bb[j].x = fmaf(ln_c, sc.x, bb[j].x); bb[j].y = fmaf(ln_c, sc.y, bb[j].y);
                                     bb[j].z = fmaf(ln_c, sc.z, bb[j].z); bb[j].w = fmaf(ln_c, sc.w, bb[j].w);
                                 }
