@@ -110,32 +110,6 @@ __device__ __forceinline__ void rescale_o(uint32_t o_addr, float corr) {
 // Packed fp32 pairs (sm_100 FFMA2 / FADD2: one issue slot for two lanes of arithmetic) and the 3-input maximum.  The
 // softmax warps are bound by the instructions they issue, not by any single pipe, so the per-score count is what
 // matters: 3.0 (no positional term), 3.5 (ALiBi off the diagonal), 4.5 (diagonal block) instead of 4.5 / 5.5 / 7.5.
-__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
-    uint64_t v;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
-    return v;
-}
-__device__ __forceinline__ uint64_t f2_pack(uint32_t lo, uint32_t hi) {
-    uint64_t v;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(lo), "r"(hi));
-    return v;
-}
-__device__ __forceinline__ void f2_unpack(uint64_t v, uint32_t& lo, uint32_t& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
-}
-__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
-    uint64_t d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
-    uint64_t d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
 __device__ __forceinline__ float max3(float a, float b, float c) {
     float d;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));

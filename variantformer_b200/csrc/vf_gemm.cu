@@ -442,25 +442,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                 for (int i = 0; i < kSlabs; ++i) {
                     const int c = half + 2 * i;                           // 32-column slab of the 128 outputs
-                    // bias (and LayerNorm column sums) of the slab from the tile's shared-memory vectors: 16-32 broadcast
-                    // loads issued as ONE batch before the TMEM wait
-                    float4 bu[8], bg[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        bu[j] = lds_f4(colvec + (c * 32 + 4 * j) * 4);
-                        bg[j] = lds_f4(colvec + (128 + c * 32 + 4 * j) * 4);
-                    }
-                    if (ln) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 su = lds_f4(colvec + (BN + c * 32 + 4 * j) * 4);
-                            const float4 sg = lds_f4(colvec + (BN + 128 + c * 32 + 4 * j) * 4);
-                            bu[j].x = fmaf(ln_c, su.x, bu[j].x); bu[j].y = fmaf(ln_c, su.y, bu[j].y);
-                            bu[j].z = fmaf(ln_c, su.z, bu[j].z); bu[j].w = fmaf(ln_c, su.w, bu[j].w);
-                            bg[j].x = fmaf(ln_c, sg.x, bg[j].x); bg[j].y = fmaf(ln_c, sg.y, bg[j].y);
-                            bg[j].z = fmaf(ln_c, sg.z, bg[j].z); bg[j].w = fmaf(ln_c, sg.w, bg[j].w);
-                        }
-                    }
                     tmem_ld_wait();
                     if (i + 1 < kSlabs) {
                         tmem_ld_32x32(t_row + (c + 2) * 32, ru[(i + 1) & 1]);
@@ -469,11 +450,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const float4 b0 = bu[j >> 2], b1 = bg[j >> 2];
-                        v[j + 0] = fmaf(__uint_as_float(ru[i & 1][j + 0]), ln_a, b0.x) * gelu_erf_fast(fmaf(__uint_as_float(rg[i & 1][j + 0]), ln_a, b1.x));
-                        v[j + 1] = fmaf(__uint_as_float(ru[i & 1][j + 1]), ln_a, b0.y) * gelu_erf_fast(fmaf(__uint_as_float(rg[i & 1][j + 1]), ln_a, b1.y));
-                        v[j + 2] = fmaf(__uint_as_float(ru[i & 1][j + 2]), ln_a, b0.z) * gelu_erf_fast(fmaf(__uint_as_float(rg[i & 1][j + 2]), ln_a, b1.z));
-                        v[j + 3] = fmaf(__uint_as_float(ru[i & 1][j + 3]), ln_a, b0.w) * gelu_erf_fast(fmaf(__uint_as_float(rg[i & 1][j + 3]), ln_a, b1.w));
+                        // bias (+ LayerNorm column-sum term) of these four columns, from the tile's shared-memory vectors
+                        // (read where they are used: as arrays they cost 64 registers the packed arithmetic needs)
+                        float4 b0 = lds_f4(colvec + (c * 32 + j) * 4), b1 = lds_f4(colvec + (128 + c * 32 + j) * 4);
+                        if (ln) {
+                            const float4 su = lds_f4(colvec + (BN + c * 32 + j) * 4), sg = lds_f4(colvec + (BN + 128 + c * 32 + j) * 4);
+                            b0.x = fmaf(ln_c, su.x, b0.x); b0.y = fmaf(ln_c, su.y, b0.y); b0.z = fmaf(ln_c, su.z, b0.z); b0.w = fmaf(ln_c, su.w, b0.w);
+                            b1.x = fmaf(ln_c, sg.x, b1.x); b1.y = fmaf(ln_c, sg.y, b1.y); b1.z = fmaf(ln_c, sg.z, b1.z); b1.w = fmaf(ln_c, sg.w, b1.w);
+                        }
+                        // u * gelu(gate) on packed pairs (FFMA2 / FMUL2)
+                        const uint64_t la2 = f2_bcast(ln_a);
+                        float g0, g1, g2, g3, y0, y1, y2, y3;
+                        f2_unpack(f2_fma(f2_pack(rg[i & 1][j + 0], rg[i & 1][j + 1]), la2, f2_pack(b1.x, b1.y)), g0, g1);
+                        f2_unpack(f2_fma(f2_pack(rg[i & 1][j + 2], rg[i & 1][j + 3]), la2, f2_pack(b1.z, b1.w)), g2, g3);
+                        gelu_erf_fast2(g0, g1, y0, y1);
+                        gelu_erf_fast2(g2, g3, y2, y3);
+                        const uint64_t u01 = f2_fma(f2_pack(ru[i & 1][j + 0], ru[i & 1][j + 1]), la2, f2_pack(b0.x, b0.y));
+                        const uint64_t u23 = f2_fma(f2_pack(ru[i & 1][j + 2], ru[i & 1][j + 3]), la2, f2_pack(b0.z, b0.w));
+                        f2_unpack(f2_mul(u01, f2_pack(y0, y1)), v[j + 0], v[j + 1]);
+                        f2_unpack(f2_mul(u23, f2_pack(y2, y3)), v[j + 2], v[j + 3]);
                     }
                     float4 none[8];
                     epilogue_store_slab<EPI>(p, stage_out, row0, out0 + c * 32, n_out, v, lane, none, rs);
