@@ -28,7 +28,7 @@ def main():
     objs = []
     for src in B.SOURCES:
         o = os.path.join(B.HERE, src.replace(".cu", ".o"))
-        if src in ("vf_attention_mc.cu", "vf_gemm.cu") and (flags or src in alt):
+        if src in ("vf_attention_mc.cu", "vf_gemm.cu", "vf_encode.cu") and (flags or src in alt):
             o = os.path.join(out, f"{name}_{src.replace('.cu', '.o')}")
             s = alt.get(src, os.path.join(B.HERE, src))
             r = subprocess.run([B.NVCC] + B.FLAGS + flags + ["-I", B.HERE, "-c", s, "-o", o], capture_output=True, text=True)
