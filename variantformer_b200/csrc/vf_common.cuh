@@ -234,8 +234,10 @@ __device__ __forceinline__ void mbar_wait_impl(SmemBar bar, uint32_t parity) {
             if (t0 == 0) t0 = now;
             if (now - t0 > VF_WATCHDOG_NS) {
 #ifdef VF_WATCHDOG_VERBOSE
-                printf("vf: mbarrier watchdog: block %d thread %d barrier smem+0x%x parity %u\n", blockIdx.x, threadIdx.x,
-                       bar.addr, parity);
+                unsigned long long raw;
+                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(raw) : "r"(bar.addr) : "memory");
+                printf("vf: mbarrier watchdog: block %d thread %d barrier smem+0x%x parity %u state 0x%016llx\n", blockIdx.x,
+                       threadIdx.x, bar.addr, parity, raw);
 #pragma unroll 1
                 for (int i = 0; i < 1000; ++i) __nanosleep(1000000);
 #endif
