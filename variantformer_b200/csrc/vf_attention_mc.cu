@@ -426,7 +426,9 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             };
             auto ready = [&](SmemBar bar, uint32_t parity, bool blocking) -> bool {
                 if (blocking) { mbar_wait(bar, parity); return true; }
-                return mbar_test_wait(bar, parity);
+                // one lane's answer for the whole warp: the lanes keep the (uniform) books of the pipeline, so they
+                // must never disagree on whether the early Q K^T went out
+                return __shfl_sync(0xffffffffu, (int)mbar_test_wait(bar, parity), 0) != 0;
             };
             // S(j) = Q K(j)^T of item `it`; non-blocking mode gives up (nothing issued) if an input has not landed yet
             auto issue_qk = [&](It& it, int j, bool blocking) -> bool {
