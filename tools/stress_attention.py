@@ -1,0 +1,45 @@
+"""Determinism stress of the attention kernel (seq_len <= 128: one-tile sequences — with ops.PAIR_UNRELATED_TILES two
+of them share a work item and stream their own keys; longer: tiles of one sequence share the K/V stream):
+the same launch N times, every output compared bit for bit with the first; a second stream keeps unrelated kernels
+running to perturb the timing.  GPU box only.   python tools/stress_attention.py [launches] [seq_len]
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from variantformer_b200 import _lib  # noqa: E402
+
+if os.environ.get("VF_BENCH_LIB"):
+    _lib.LIB_PATH = os.path.abspath(os.environ["VF_BENCH_LIB"])
+from variantformer_b200 import ops  # noqa: E402
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
+    L = int(sys.argv[2]) if len(sys.argv) > 2 else 97
+    H, hd = 8, 64
+    lens = [L] * (8192 if L <= 128 else 1600)
+    d = H * hd
+    tot = sum(lens)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    q, k, v = (torch.randn(tot, d, device="cuda", generator=g).bfloat16() for _ in range(3))
+    slots = ops.SlotMap(lens, "cuda")
+    ref = ops.attention_mc(q, k, v, slots, H, hd, None).clone()
+    out = torch.empty_like(ref)
+    bad = torch.zeros((), dtype=torch.int64, device="cuda")
+    side = torch.cuda.Stream()
+    a = torch.randn(4096, 4096, device="cuda"); b = torch.randn(1 << 26, device="cuda")
+    for i in range(n):
+        if i % 7 == 0:
+            with torch.cuda.stream(side):               # unrelated traffic: a GEMM and a streaming copy
+                (a @ a).sum(); b.add_(1.0)
+        ops.attention_mc(q, k, v, slots, H, hd, None, out=out)
+        bad += (out.view(torch.int16) != ref.view(torch.int16)).any().to(torch.int64)
+    torch.cuda.synchronize()
+    print(f"launches {n} seq_len {L}: {int(bad.item())} differ from the first")
+
+
+if __name__ == "__main__":
+    main()

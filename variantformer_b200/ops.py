@@ -203,12 +203,20 @@ def attention_tc(q, k, v, cu_q, cu_k, items: TileMap, heads, head_dim, slopes=No
     return out
 
 
+# Two query tiles that read DIFFERENT key ranges in one work item ("split" items: each slot streams its own K/V
+# through the shared rings) are disabled: a 12 000-launch determinism stress (tools/stress_attention.py) found one
+# launch in 12 000 whose output differed — an MMA issuer waits by parity on a ring stage whose previous use belonged to
+# the other slot, and bulk loads can complete far enough out of order to alias that parity.  Left-over tiles therefore
+# run alone (slot 1 empty: half of the softmax warps idle for those items) until the kernel counts uses per stage.
+PAIR_UNRELATED_TILES = False
+
+
 class SlotMap:
     """Work items of vf_attention_mc_varlen for a batch of variable-length sequences (host-built, device-resident).
 
     Every sequence is cut into 128-row query tiles; consecutive tiles of a sequence are paired into one item (they
-    share the sequence's K/V stream), and the odd tiles left over (all of them when sequences have <= 128 rows) are
-    paired with each other, each slot then streaming its own keys.  Record layout: include/vf_b200.h."""
+    share the sequence's K/V stream); the odd tiles left over (all of them when sequences have <= 128 rows) get an
+    item of their own (see PAIR_UNRELATED_TILES).  Record layout: include/vf_b200.h."""
 
     def __init__(self, q_lens, device, k_lens=None):
         q_lens = np.asarray(q_lens, np.int64)
@@ -229,9 +237,13 @@ class SlotMap:
         odd = (t == nt[seq] - 1) & (nt[seq] % 2 == 1)
         odd = odd[(k_lens[seq] > 0)]
         pairs, singles = rec[~odd], rec[odd]
-        if len(singles) % 2:
-            singles = np.concatenate([singles, np.zeros((1, 8), np.int32)])
-        items = np.concatenate([pairs.reshape(-1, 2, 8), singles.reshape(-1, 2, 8)])
+        if PAIR_UNRELATED_TILES:
+            if len(singles) % 2:
+                singles = np.concatenate([singles, np.zeros((1, 8), np.int32)])
+            singles = singles.reshape(-1, 2, 8)
+        else:                                                             # each left-over tile alone, slot 1 empty
+            singles = np.stack([singles, np.zeros_like(singles)], axis=1)
+        items = np.concatenate([pairs.reshape(-1, 2, 8), singles])
         self.n_items = int(items.shape[0])
         self.table = torch.from_numpy(np.ascontiguousarray(items)).to(device, non_blocking=True)
 
@@ -242,10 +254,24 @@ class SlotMap:
         self = cls.__new__(cls)
         units = np.asarray(units, np.int64).reshape(-1, 5)
         self.qk_pairs = float((units[:, 1] * units[:, 3]).sum())
-        rec = np.zeros((len(units) + (len(units) & 1), 8), np.int32)
-        rec[:len(units), :5] = units
-        self.n_items = rec.shape[0] // 2
-        self.table = torch.from_numpy(np.ascontiguousarray(rec.reshape(-1, 2, 8))).to(device, non_blocking=True)
+        n = len(units)
+        if PAIR_UNRELATED_TILES:
+            first = np.arange(0, n, 2)
+            paired = first + 1 < n
+        else:
+            # greedy left to right: unit i opens an item; unit i+1 joins it only if it reads the same key range
+            same_next = np.zeros(n, bool)
+            if n > 1:
+                same_next[:-1] = (units[:-1, 2] == units[1:, 2]) & (units[:-1, 3] == units[1:, 3])
+            first, paired, i = [], [], 0
+            while i < n:
+                first.append(i); paired.append(bool(same_next[i])); i += 2 if same_next[i] else 1
+            first = np.asarray(first, np.int64); paired = np.asarray(paired, bool)
+        rec = np.zeros((len(first), 2, 8), np.int32)
+        rec[:, 0, :5] = units[first]
+        rec[paired, 1, :5] = units[first[paired] + 1]
+        self.n_items = int(rec.shape[0])
+        self.table = torch.from_numpy(np.ascontiguousarray(rec)).to(device, non_blocking=True)
         return self
 
 
