@@ -112,8 +112,10 @@ int vf_attention_tc_varlen(const void* q, int ldq, const void* k, int ldk, const
  * attention of the hot path.  A work item has two SLOTS, each a query tile of up to 128 rows of one sequence.
  * slots: int32 [n_items][2][8], 16-byte aligned, per slot {first query row (absolute row of q/o), valid rows (0 = empty
  * slot), first key row (absolute row of k/v), number of keys, i + Sk - Sq of the tile's first row (ALiBi position),
- * 0, 0, 0}.  Two slots with the same key range share one K/V stream; slots of different sequences stream their own
- * keys, which keeps both softmax warpgroups busy on sequences of <= 128 rows.  head_dim in {48, 64}.
+ * 0, 0, 0}.  Two slots with the same key range share one K/V stream.  CALLERS MUST NOT put two slots with DIFFERENT
+ * key ranges into one item: the kernel has a path for it (each slot streaming its own keys) but that path is not
+ * reliable yet (a parity wait across slots can alias; 1 wrong launch in 12 000 under load): give a
+ * left-over tile an item of its own with an empty second slot, as ops.SlotMap does.  head_dim in {48, 64}.
  * Same reference call sites as above.
  */
 int vf_attention_mc_varlen(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
