@@ -294,6 +294,34 @@ def test_mc_many_items_per_cta(H, hd, alibi, n_seq, lo, hi):
     assert torch.allclose(got.float(), want, atol=2e-2, rtol=2e-2), _describe_mismatch(got.float(), want, 2e-2)
 
 
+@pytest.mark.parametrize("lens,H,hd,alibi", [([97] * 2048, 8, 64, False), ([201] * 300 + [97] * 301, 32, 48, True)])
+def test_mc_repeated_launches_are_bit_identical(lens, H, hd, alibi):
+    """The kernel is deterministic: the same launch repeated next to unrelated traffic on another stream must give the
+    same bits every time (this is the check that caught the cross-slot parity alias of split-key work items; the long
+    form is tools/stress_attention.py).  Also pins the host rule that replaced those items: no item mixes key ranges."""
+    n, d = sum(lens), H * hd
+    g = torch.Generator(device="cpu").manual_seed(11)
+    q, k, v = (torch.randn(n, d, generator=g).to(DEV).bfloat16() for _ in range(3))
+    slopes = torch.tensor([2 ** (-8 * (h + 1) / H) for h in range(H)], device=DEV) if alibi else None
+    slots = ops.SlotMap(lens, DEV)
+    tab = slots.table.cpu().numpy()
+    both = (tab[:, 0, 1] > 0) & (tab[:, 1, 1] > 0)
+    assert np.all(tab[both, 0, 2] == tab[both, 1, 2]) and np.all(tab[both, 0, 3] == tab[both, 1, 3])
+    ref = ops.attention_mc(q, k, v, slots, H, hd, slopes).clone()
+    out = torch.empty_like(ref)
+    bad = torch.zeros((), dtype=torch.int64, device=DEV)
+    side = torch.cuda.Stream()
+    a = torch.randn(2048, 2048, device=DEV)
+    for i in range(400):
+        if i % 5 == 0:
+            with torch.cuda.stream(side):
+                (a @ a).sum()
+        ops.attention_mc(q, k, v, slots, H, hd, slopes, out=out)
+        bad += (out.view(torch.int16) != ref.view(torch.int16)).any().to(torch.int64)
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0
+
+
 def test_mc_large_scores_raise_the_lazy_maximum():
     """Scores that grow along the key axis force the reference maximum to be raised (O rescaled in TMEM) many times."""
     H, hd, lens = 4, 48, [700, 130]
