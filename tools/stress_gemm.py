@@ -1,0 +1,52 @@
+"""Determinism stress of the GEMM epilogues (GPU box only): every configuration launched N times next to unrelated
+traffic, outputs compared bit for bit with the first launch.   python tools/stress_gemm.py [launches]
+"""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from variantformer_b200 import ops  # noqa: E402
+from variantformer_b200._lib import EPI_BIAS_BF16, EPI_BIAS_GEGLU_BF16, EPI_BIAS_RESID_F32  # noqa: E402
+
+DEV = "cuda"
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+    side = torch.cuda.Stream()
+    junk = torch.randn(4096, 4096, device=DEV)
+    for (M, N, K, epi, ln) in [(40000, 1536, 512, EPI_BIAS_BF16, True), (40000, 2048, 512, EPI_BIAS_GEGLU_BF16, True),
+                               (40000, 512, 512, EPI_BIAS_RESID_F32, False), (20000, 1536, 1536, EPI_BIAS_RESID_F32, False),
+                               (20000, 4608, 1536, EPI_BIAS_BF16, True)]:
+        g = torch.Generator(device=DEV).manual_seed(M + N)
+        a = torch.randn(M, K, device=DEV, generator=g).bfloat16(); w = torch.randn(N, K, device=DEV, generator=g).bfloat16()
+        bias = torch.randn(N, device=DEV, generator=g)
+        kw = {}
+        if ln:
+            st = torch.rand(M, 4, 2, device=DEV, generator=g) / 4 + 0.25
+            st[:, :, 1] += K / 4
+            kw["ln"] = (st, bias, K, 1e-5)
+        if epi == EPI_BIAS_RESID_F32:
+            kw["resid"] = torch.randn(M, N, device=DEV, generator=g)
+            kw["out2"] = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+            kw["stats_out"] = torch.empty(M, ops.stats_parts(N), 2, device=DEV)
+        ref = ops.gemm(a, w, epi, bias=bias, **kw).clone()
+        ref2 = kw["stats_out"].clone() if "stats_out" in kw else None
+        out = torch.empty_like(ref)
+        bad = torch.zeros((), dtype=torch.int64, device=DEV)
+        for i in range(n):
+            if i % 5 == 0:
+                with torch.cuda.stream(side):
+                    (junk @ junk).sum()
+            ops.gemm(a, w, epi, bias=bias, out=out, **kw)
+            bad += (out.view(torch.int32 if out.dtype == torch.float32 else torch.int16) !=
+                    ref.view(torch.int32 if ref.dtype == torch.float32 else torch.int16)).any().to(torch.int64)
+            if ref2 is not None:
+                bad += (kw["stats_out"] != ref2).any().to(torch.int64)
+        torch.cuda.synchronize()
+        print(f"M={M} N={N} K={K} epi={epi} ln={ln}: {n} launches, {int(bad.item())} differ")
+
+
+if __name__ == "__main__":
+    main()
