@@ -18,14 +18,17 @@ from variantformer_b200 import ops  # noqa: E402
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
-    L = int(sys.argv[2]) if len(sys.argv) > 2 else 97
-    H, hd = 8, 64
-    lens = [L] * (8192 if L <= 128 else 1600)
+    L = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2] != "cross" else 97
+    cross = len(sys.argv) > 2 and sys.argv[2] == "cross"     # stacked gene->CRE cross-attention: pairs + left-over tiles
+    H, hd = (32, 48) if cross else (8, 64)
+    lens = [12663] * 8 if cross else [L] * (8192 if L <= 128 else 1600)
+    k_lens = [1024] * 8 if cross else None
     d = H * hd
     tot = sum(lens)
     g = torch.Generator(device="cuda").manual_seed(1)
-    q, k, v = (torch.randn(tot, d, device="cuda", generator=g).bfloat16() for _ in range(3))
-    slots = ops.SlotMap(lens, "cuda")
+    q = torch.randn(tot, d, device="cuda", generator=g).bfloat16()
+    k, v = (torch.randn(sum(k_lens or lens), d, device="cuda", generator=g).bfloat16() for _ in range(2))
+    slots = ops.SlotMap(lens, "cuda", k_lens=k_lens)
     ref = ops.attention_mc(q, k, v, slots, H, hd, None).clone()
     out = torch.empty_like(ref)
     bad = torch.zeros((), dtype=torch.int64, device="cuda")
@@ -38,7 +41,7 @@ def main():
         ops.attention_mc(q, k, v, slots, H, hd, None, out=out)
         bad += (out.view(torch.int16) != ref.view(torch.int16)).any().to(torch.int64)
     torch.cuda.synchronize()
-    print(f"launches {n} seq_len {L}: {int(bad.item())} differ from the first")
+    print(f"launches {n} {'cross' if cross else 'seq_len ' + str(L)}: {int(bad.item())} differ from the first")
 
 
 if __name__ == "__main__":
