@@ -81,42 +81,23 @@ int vf_gemm_bf16_ln(const void* A, int lda, const void* W, int ldw, int M, int N
 int vf_rowstats(const float* x, int ldx, int M, int d, float* stats, void* out_bf16, int ldo, void* stream);
 
 /*
- * Variable-length non-causal attention, one launch for all sequences and heads.
- * q/k/v/o: bf16, head h at columns [h*head_dim, (h+1)*head_dim) of each row; packed QKV/KV buffers are
- * addressed by passing offset base pointers.  cu_q/cu_k: int32 [n_seq+1] row prefix sums.
- * tile_seq/tile_q0: int32 [n_tiles] query-tile map (sequence id, first query row) for block_m rows per tile.
- * slopes: fp32 [heads] ALiBi slopes (bias -slope*|i + Sk - Sq - j|) or NULL.  head_dim in {32,48,64}.
- * Replaces flash_attn_varlen_qkvpacked_func / flash_attn_varlen_kvpacked_func as called through
- * flash_attn.modules.mha.MHA at seq2reg/modules.py:159-171 and seq2gene/modules/layers.py:372-467.
- */
-int vf_attention_varlen(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
-                        const int32_t* cu_q, const int32_t* cu_k, const int32_t* tile_seq, const int32_t* tile_q0,
-                        int n_tiles, int block_m, int heads, int head_dim, const float* slopes, void* stream);
-
-/*
- * Same operation on the tcgen05 tensor cores (TMA-staged Q/K/V tiles, S and O accumulators in TMEM, one softmax
- * thread per query row, two-pass exact softmax).  Work items are blocks of up to 4 x 128 query rows of one sequence:
- * item_seq/item_q0 int32 [n_items] (a tile map built with 512 rows per item).  rows_q / rows_k = total rows of the
- * q and k/v tensors (TMA bounds).  head_dim in {48, 64}.  key_block: keys per softmax step, 64 (two S/P buffers per
- * softmax warpgroup; best for short sequences) or 128 (best for long key ranges).  short_items != 0 promises that
- * every work item has at most 2 query tiles (all query sequences <= 256 rows): the 64-key kernel then double-buffers
- * Q and O across consecutive items.  Same reference call sites as vf_attention_varlen.
- */
-int vf_attention_tc_varlen(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
-                           int64_t rows_q, int64_t rows_k, const int32_t* cu_q, const int32_t* cu_k,
-                           const int32_t* item_seq, const int32_t* item_q0, int n_items, int heads, int head_dim,
-                           const float* slopes, int key_block, int short_items, void* stream);
-
-/*
- * Same operation, two co-resident CTAs per SM (16 softmax warps per SM): the kernel the engine uses for every
- * attention of the hot path.  A work item has two SLOTS, each a query tile of up to 128 rows of one sequence.
+ * Variable-length non-causal attention, one launch for all sequences and heads:
+ *   o = softmax(q k^T / sqrt(head_dim) - slope_h * |i + Sk - Sq - j|) v      (fp32 statistics, bf16 operands)
+ * tcgen05 tensor cores (TMA-staged Q/K/V tiles, S and O accumulators in TMEM, one softmax thread per query row,
+ * single-pass softmax with a lazily raised reference maximum), two co-resident CTAs per SM.
+ * q/k/v/o: bf16, head h at columns [h*head_dim, (h+1)*head_dim) of each row; packed QKV/KV buffers are addressed by
+ * passing offset base pointers.  rows_q / rows_k = total rows of the q and k/v tensors (TMA bounds).
+ * A work item has two SLOTS, each a query tile of up to 128 rows of one sequence.
  * slots: int32 [n_items][2][8], 16-byte aligned, per slot {first query row (absolute row of q/o), valid rows (0 = empty
- * slot), first key row (absolute row of k/v), number of keys, i + Sk - Sq of the tile's first row (ALiBi position),
- * 0, 0, 0}.  Two slots with the same key range share one K/V stream.  CALLERS MUST NOT put two slots with DIFFERENT
- * key ranges into one item: the kernel has a path for it (each slot streaming its own keys) but that path is not
- * reliable yet (a parity wait across slots can alias; 1 wrong launch in 12 000 under load): give a
- * left-over tile an item of its own with an empty second slot, as ops.SlotMap does.  head_dim in {48, 64}.
- * Same reference call sites as above.
+ * slot; slot 0 of an item is never the empty one), first key row (absolute row of k/v), number of keys (> 0),
+ * i + Sk - Sq of the tile's first row (ALiBi position), 0, 0, 0}.  Two slots with the same (first key row, keys) share
+ * one K/V stream; two slots with different key ranges stream their own keys (any mixture of the two kinds of item in
+ * one launch is fine: the MMA issuers order their ring waits behind the producer's issue counters).
+ * Rows past a sequence's last key that a 64-key block over-fetches are masked in S and cleared in V, so non-finite
+ * values in a neighbouring sequence never reach this one.  slopes: fp32 [heads] ALiBi slopes or NULL.
+ * head_dim in {48, 64}.
+ * Replaces flash_attn_varlen_qkvpacked_func / flash_attn_varlen_kvpacked_func as called through
+ * flash_attn.modules.mha.MHA at seq2reg/modules.py:159-171 and seq2gene/modules/layers.py:344-351, 372-467.
  */
 int vf_attention_mc_varlen(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
                            int64_t rows_q, int64_t rows_k, const int32_t* slots, int n_items, int heads,

@@ -117,13 +117,6 @@ def attention_mc(q, k, v, slots, heads, head_dim, slopes=None, out=None):
     return _store(out, res) if out is not None else res.bfloat16()
 
 
-TC_BLOCK_M = 512
-
-
-def attention_tc(q, k, v, cu_q, cu_k, tiles, heads, head_dim, slopes=None, out=None, key_block=64):
-    return attention(q, k, v, cu_q, cu_k, tiles, heads, head_dim, slopes, out)
-
-
 def label_attention(q, kv9, logc, row_seq, heads, head_dim, out=None):
     D = heads * head_dim
     qq = q.float().reshape(-1, heads, head_dim)

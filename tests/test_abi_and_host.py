@@ -96,27 +96,43 @@ def test_window_arithmetic_matches_oracle():
             assert gene_window(s, e, strand, 1000, 300000) == O.gene_window(s, e, strand == "-")
 
 
-def test_attention_work_items_never_mix_key_ranges():
-    """Host rule behind vf_attention_mc_varlen (include/vf_b200.h): the two slots of an item read the same keys, or the
-    second slot is empty.  Every query row appears exactly once."""
+def test_attention_work_items_cover_every_row_once():
+    """Work tables of vf_attention_mc_varlen (include/vf_b200.h).  Default: left-over tiles are paired even when they
+    read different keys (split items; the kernel orders its waits behind the producer's issue counters).  With pairing
+    off (VF_PAIR_TILES=0) the two slots of an item read the same keys or the second slot is empty.  Either way every
+    query row appears exactly once and slot 0 of an item is never the empty one."""
     from variantformer_b200 import ops
     rng = np.random.default_rng(5)
     lens = rng.integers(1, 700, 300).tolist() + [97] * 40 + [128, 129, 256, 257]
-    sm = ops.SlotMap(lens, "cpu")
-    tab = sm.table.numpy()
-    both = (tab[:, 0, 1] > 0) & (tab[:, 1, 1] > 0)
-    assert both.any() and (~both).any()
-    assert np.all(tab[both, 0, 2] == tab[both, 1, 2]) and np.all(tab[both, 0, 3] == tab[both, 1, 3])
-    assert np.all(tab[~both, 1, :] == 0)
-    rows = np.concatenate([np.arange(r[0], r[0] + r[1]) for r in tab.reshape(-1, 8) if r[1] > 0])
-    assert len(rows) == sum(lens) and len(np.unique(rows)) == len(rows)
-    # explicit units: consecutive units pair only when they read the same key range
     units = np.array([[0, 128, 0, 200, 0], [128, 72, 0, 200, 128], [200, 1, 500, 201, 3], [201, 1, 701, 201, 9],
                       [202, 63, 1000, 1024, 0], [265, 63, 1000, 1024, 0], [328, 63, 1000, 1024, 0]])
-    fu = ops.SlotMap.from_units(units, "cpu").table.numpy()
-    assert fu.shape[0] == 5
-    both = (fu[:, 0, 1] > 0) & (fu[:, 1, 1] > 0)
-    assert both.tolist() == [True, False, False, True, False]
-    assert np.all(fu[both, 0, 2:4] == fu[both, 1, 2:4])
-    got = np.concatenate([fu[:, 0, :5][fu[:, 0, 1] > 0], fu[:, 1, :5][fu[:, 1, 1] > 0]])
-    assert sorted(map(tuple, got)) == sorted(map(tuple, units))
+    saved = ops.PAIR_UNRELATED_TILES
+    try:
+        for pairing in (True, False):
+            ops.PAIR_UNRELATED_TILES = pairing
+            sm = ops.SlotMap(lens, "cpu")
+            tab = sm.table.numpy()
+            both = (tab[:, 0, 1] > 0) & (tab[:, 1, 1] > 0)
+            assert both.any() and np.all(tab[:, 0, 1] > 0)
+            split = both & ((tab[:, 0, 2] != tab[:, 1, 2]) | (tab[:, 0, 3] != tab[:, 1, 3]))
+            assert split.any() == pairing
+            if not pairing:
+                assert (~both).any() and np.all(tab[~both, 1, :] == 0)
+            else:
+                assert (~both).sum() <= 1                              # at most one tile is left without a partner
+            rows = np.concatenate([np.arange(r[0], r[0] + r[1]) for r in tab.reshape(-1, 8) if r[1] > 0])
+            assert len(rows) == sum(lens) and len(np.unique(rows)) == len(rows)
+            fu = ops.SlotMap.from_units(units, "cpu").table.numpy()
+            both = (fu[:, 0, 1] > 0) & (fu[:, 1, 1] > 0)
+            if pairing:
+                assert fu.shape[0] == 4 and both.tolist() == [True, True, True, False]
+            else:                                                      # consecutive units pair only on the same key range
+                assert fu.shape[0] == 5 and both.tolist() == [True, False, False, True, False]
+                assert np.all(fu[both, 0, 2:4] == fu[both, 1, 2:4])
+            got = np.concatenate([fu[:, 0, :5][fu[:, 0, 1] > 0], fu[:, 1, :5][fu[:, 1, 1] > 0]])
+            assert sorted(map(tuple, got)) == sorted(map(tuple, units))
+    finally:
+        ops.PAIR_UNRELATED_TILES = saved
+    # sequences without keys: no work item, their output rows are listed for zero-filling
+    sm = ops.SlotMap([5, 130, 7], "cpu", k_lens=[9, 0, 4])
+    assert sm.keyless == [(5, 135)] and sm.n_items == 1

@@ -227,6 +227,49 @@ def test_vep_triplet_matches_reference_semantics():
             assert np.isfinite(out["pred_gene_exp"][2]).all()
 
 
+@pytest.mark.parametrize("strand", ["+", "-"])
+def test_vep_overlapping_cre_windows_keep_the_last_hit(strand):
+    """cCRE windows are +-50 bp wide, so neighbours overlap: the reference's row loop has no break after a hit
+    (vepdataset.py:367-407) — every overlapping window is re-encoded and cre_token_position is the LAST one in batch
+    order.  On the minus strand its early break (`end_cre < pos`) can stop before a nested window: that one keeps
+    the background sequence."""
+    from variantformer_b200.datasets.vepdataset import VEPBatchBuilder, Variant
+    rng = np.random.default_rng(5)
+    chrom = synth.make_chromosome(rng, 700_000, n_rate=0.0)
+    genome = Genome.from_arrays({"chr1": chrom}, "cuda")
+    cs = np.array([400_000, 400_120, 400_900, 401_000, 401_700]); ce = np.array([400_100, 400_300, 401_600, 401_100, 401_900])
+    g = GeneSpec("chr1", 395_000, 420_000, strand, cs, ce, np.arange(5) % 9, [62])
+    builder = VEPBatchBuilder(genome)
+    bpe = O.OracleBPE()
+    minus = strand == "-"
+    order = np.argsort(cs, kind="stable"); order = order[::-1] if minus else order
+    wins = [cre_window(cs[i], ce[i], 50) for i in order]
+
+    def check(pos0, want_hit, want_applied):
+        ref = chr(chrom[pos0]).upper(); alt = [c for c in "ACGT" if c != ref][0]
+        batch = builder.build(g, Variant("chr1", pos0 + 1, ref, alt, tissue=[62]))
+        assert int(batch["cre_token_position"][0, 0]) == want_hit
+        for k, (w0, w1) in enumerate(wins):
+            s = chrom[w0:w1].tobytes().decode()
+            if k in want_applied:
+                s = s[:pos0 - w0] + alt + s[pos0 - w0 + 1:]
+            s = O.reverse_complement(s) if minus else s
+            tok = O.adjust_length(bpe.encode(s), 200)[0]
+            assert (batch["cre_sequences"][2][k, 0].cpu().numpy() == tok).all(), f"hom tokens of window {k}"
+    # windows 0 and 1 of the + order overlap on [400070, 400150): both get the variant, the later row wins
+    if not minus:
+        check(400_100, 1, {0, 1})
+    else:
+        check(400_100, 4, {3, 4})
+        # nested windows on the minus strand: rows by descending start are [401650,401950) [400950,401150)
+        # [400850,401650) ...: a variant at 401300 lies in the third row only, but the walk stops at the second row
+        # (its end 401150 < pos), so the reference never reaches it: no CRE hit, the window stays unmodified
+        ref = chr(chrom[401_300]).upper(); alt = [c for c in "ACGT" if c != ref][0]
+        batch = builder.build(g, Variant("chr1", 401_301, ref, alt, tissue=[62]))
+        assert bool(torch.isnan(batch["cre_token_position"]).all()) and batch["variant_type"] == "Gene overlap only"
+        assert torch.equal(batch["cre_sequences"][2], batch["cre_sequences"][0])
+
+
 def test_variantprocessor_surface(tmp_path):
     from variantformer_b200.processors.variantprocessor import VariantProcessor
     chroms, var, genes = _world(seed=80, n_genes=2, n_cres=20)

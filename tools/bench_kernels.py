@@ -86,19 +86,7 @@ def main():
         v = torch.randn(nk, d, device=DEV).bfloat16(); o = torch.empty(nq, d, device=DEV, dtype=torch.bfloat16)
         slopes = torch.tensor([2 ** (-8 * (h + 1) / H) for h in range(H)], device=DEV) if alibi else None
         cq, ck = ops.cu_seqlens(lens_q, DEV), ops.cu_seqlens(lk, DEV)
-        tiles = ops.TileMap(lens_q, bm, DEV)
-        ms = timeit(lambda: ops.attention(q, k, v, cq, ck, tiles, H, hd, slopes, out=o))
         fl = sum(4.0 * a * b * d for a, b in zip(lens_q, lk))
-        res.append(dict(kernel="attention", name=name, ms=ms, tflops=fl / ms / 1e9))
-        print(json.dumps(res[-1])); sys.stdout.flush()
-        try:
-            items = ops.TileMap(lens_q, ops.TC_BLOCK_M, DEV, k_lens=lens_k)
-            for kb in (64, 128):
-                ms = timeit(lambda: ops.attention_tc(q, k, v, cq, ck, items, H, hd, slopes, out=o, key_block=kb))
-                res.append(dict(kernel=f"attention_tc{kb}", name=name, ms=ms, tflops=fl / ms / 1e9))
-                print(json.dumps(res[-1])); sys.stdout.flush()
-        except Exception as e:
-            print("attention_tc failed:", e)
         try:
             slots = ops.SlotMap(lens_q, DEV, k_lens=lens_k)
             ms = timeit(lambda: ops.attention_mc(q, k, v, slots, H, hd, slopes, out=o))

@@ -1,7 +1,7 @@
 """Launch ONE kernel configuration a few times (for `ncu --launch-skip 2 --launch-count 1`).  GPU box only.
 
     python tools/prof_one.py gemm M N K epi [full]        full = engine configuration (mirror + stats / LN fold)
-    python tools/prof_one.py attn {gself|gcross|cself|rcre|rgene} [key_block]
+    python tools/prof_one.py attn {gself|gcross|cself|rcre|rgene}
 """
 import sys
 
@@ -48,13 +48,9 @@ def attn(name, kb):
     v = torch.randn(nk, d, device=DEV).bfloat16(); o = torch.empty(nq, d, device=DEV, dtype=torch.bfloat16)
     slopes = torch.tensor([2 ** (-8 * (h + 1) / H) for h in range(H)], device=DEV) if alibi else None
     cq, ck = ops.cu_seqlens(lens_q, DEV), ops.cu_seqlens(lk, DEV)
-    items = ops.TileMap(lens_q, ops.TC_BLOCK_M, DEV, k_lens=lens_k)
     slots = ops.SlotMap(lens_q, DEV, k_lens=lens_k)
     for _ in range(3):
-        if kb == 0:
-            ops.attention_mc(q, k, v, slots, H, hd, slopes, out=o)
-        else:
-            ops.attention_tc(q, k, v, cq, ck, items, H, hd, slopes, out=o, key_block=kb)
+        ops.attention_mc(q, k, v, slots, H, hd, slopes, out=o)
     torch.cuda.synchronize()
 
 

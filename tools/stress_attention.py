@@ -1,7 +1,8 @@
 """Determinism stress of the attention kernel (seq_len <= 128: one-tile sequences — with ops.PAIR_UNRELATED_TILES two
 of them share a work item and stream their own keys; longer: tiles of one sequence share the K/V stream):
 the same launch N times, every output compared bit for bit with the first; a second stream keeps unrelated kernels
-running to perturb the timing.  GPU box only.   python tools/stress_attention.py [launches] [seq_len]
+running to perturb the timing.  GPU box only.   python tools/stress_attention.py [launches] [seq_len | cross | ragged]
+"ragged": 8192 sequences of 1..200 rows (split items whose slots have different numbers of key blocks).
 """
 import os
 import sys
@@ -18,10 +19,14 @@ from variantformer_b200 import ops  # noqa: E402
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
-    L = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2] != "cross" else 97
-    cross = len(sys.argv) > 2 and sys.argv[2] == "cross"     # stacked gene->CRE cross-attention: pairs + left-over tiles
+    mode = sys.argv[2] if len(sys.argv) > 2 else "97"
+    L = int(mode) if mode.isdigit() else 97
+    cross = mode == "cross"                                   # stacked gene->CRE cross-attention: pairs + left-over tiles
     H, hd = (32, 48) if cross else (8, 64)
     lens = [12663] * 8 if cross else [L] * (8192 if L <= 128 else 1600)
+    if mode == "ragged":
+        import numpy as np
+        lens = np.random.default_rng(0).integers(1, 201, 8192).tolist()
     k_lens = [1024] * 8 if cross else None
     d = H * hd
     tot = sum(lens)
@@ -41,7 +46,8 @@ def main():
         ops.attention_mc(q, k, v, slots, H, hd, None, out=out)
         bad += (out.view(torch.int16) != ref.view(torch.int16)).any().to(torch.int64)
     torch.cuda.synchronize()
-    print(f"launches {n} {'cross' if cross else 'seq_len ' + str(L)}: {int(bad.item())} differ from the first")
+    print(f"launches {n} {mode if not mode.isdigit() else 'seq_len ' + str(L)} pairing={ops.PAIR_UNRELATED_TILES} "
+          f"items={slots.n_items}: {int(bad.item())} differ from the first", flush=True)
 
 
 if __name__ == "__main__":

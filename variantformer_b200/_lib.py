@@ -24,10 +24,6 @@ SIGNATURES = {
     "vf_gemm_bf16_ln": ([_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _i32, _vp, _i32,
                          _vp, _i32, _vp, _i32, C.c_float, _vp, _vp], _i32),
     "vf_rowstats": ([_vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp], _i32),
-    "vf_attention_varlen": ([_vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,
-                             _vp, _vp], _i32),
-    "vf_attention_tc_varlen": ([_vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _i32,
-                                _i32, _vp, _i32, _i32, _vp], _i32),
     "vf_attention_mc_varlen": ([_vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _i64, _i64, _vp, _i32, _i32, _i32, _vp,
                                 _vp], _i32),
     "vf_label_attention": ([_vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp], _i32),

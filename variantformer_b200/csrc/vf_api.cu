@@ -52,23 +52,6 @@ int vf_gemm_bf16_ln(const void* A, int lda, const void* W, int ldw, int M, int N
 int vf_rowstats(const float* x, int ldx, int M, int d, float* stats, void* out_bf16, int ldo, void* stream) {
     return rowstats(x, ldx, M, d, stats, out_bf16, ldo, ST(stream));
 }
-int vf_attention_varlen(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
-                        const int32_t* cu_q, const int32_t* cu_k, const int32_t* tile_seq, const int32_t* tile_q0,
-                        int n_tiles, int block_m, int heads, int head_dim, const float* slopes, void* stream) {
-    return attention_varlen(q, ldq, k, ldk, v, ldv, o, ldo, cu_q, cu_k, tile_seq, tile_q0, n_tiles, block_m, heads,
-                            head_dim, slopes, ST(stream));
-}
-int vf_attention_tc_varlen(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
-                           int64_t rows_q, int64_t rows_k, const int32_t* cu_q, const int32_t* cu_k,
-                           const int32_t* item_seq, const int32_t* item_q0, int n_items, int heads, int head_dim,
-                           const float* slopes, int key_block, int short_items, void* stream) {
-    VF_REQUIRE(key_block == 64 || key_block == 128, "attention_tc: key_block must be 64 or 128");
-    if (key_block == 128)
-        return attention_tc128_varlen(q, ldq, k, ldk, v, ldv, o, ldo, (long)rows_q, (long)rows_k, cu_q, cu_k, item_seq,
-                                      item_q0, n_items, heads, head_dim, slopes, ST(stream));
-    return attention_tc_varlen(q, ldq, k, ldk, v, ldv, o, ldo, (long)rows_q, (long)rows_k, cu_q, cu_k, item_seq,
-                               item_q0, n_items, heads, head_dim, slopes, short_items, ST(stream));
-}
 int vf_attention_mc_varlen(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
                            int64_t rows_q, int64_t rows_k, const int32_t* slots, int n_items, int heads,
                            int head_dim, const float* slopes, void* stream) {

@@ -282,6 +282,23 @@ __device__ __forceinline__ void softmax_tile(uint32_t (&r)[64], uint32_t o_addr,
     }
 }
 
+// Shared-memory counters "K / V blocks issued so far", written by the TMA producer, read by the MMA issuers.
+// mbarrier waits are parity waits: they are only sound while the waiter is at most ONE phase behind the barrier.  An
+// issuer does not consume every block that passes through a ring stage (the other slot's blocks of a split-key item,
+// items in which its slot is empty), so the stage's `full` barrier can be more than one phase behind the use the
+// issuer is about to wait for, and a parity test then answers for the wrong phase (round 1: one wrong launch in 12 000
+// on split-key items).  The producer issues load number idx only after BOTH release barriers of the stage's previous
+// use have completed, i.e. after that use's `full` phase has completed; so once an issuer has seen issued > idx the
+// barrier is either in the phase it waits for or one past it, and the parity test is exact.
+__device__ __forceinline__ uint32_t lds_acquire(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_release(uint32_t addr, uint32_t v) {
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 // global position of K/V block (j, slot) of an item inside the CTA's K / V rings, relative to the item's first load.
 // One stream when the slots share their keys; otherwise the blocks of the two slots alternate while both have keys.
 __device__ __forceinline__ int ring_offset(int j, int s, bool same, int nk0, int nk1) {
@@ -315,6 +332,7 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const SmemBar k_full = bars[16], k_empty = k_full[kKStages];  // k_empty[2 * stage + slot]
     const SmemBar v_full = k_empty[2 * kKStages], v_empty = v_full[kVStages];
     const uint32_t tmem_slot = v_empty[2 * kVStages].addr;
+    const uint32_t k_issued = tmem_slot + 8, v_issued = tmem_slot + 12;   // blocks issued so far (see lds_acquire)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_work = p.n_items * p.heads;
@@ -329,6 +347,7 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         for (int i = 0; i < kKStages; ++i) { mbar_init(k_full[i], 1); mbar_init(k_empty[2 * i], 1); mbar_init(k_empty[2 * i + 1], 1); }
         for (int i = 0; i < kVStages; ++i) { mbar_init(v_full[i], 1); mbar_init(v_empty[2 * i], 1); mbar_init(v_empty[2 * i + 1], 1); }
+        sts_release(k_issued, 0u); sts_release(v_issued, 0u);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -356,7 +375,7 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 const int4 r0 = __ldg(recs + 4 * item), r1 = __ldg(recs + 4 * item + 2);   // {qrow, nrows, krow, Sk}
                 const int qrow[2] = {r0.x, r1.x}, krow[2] = {r0.z, r1.z};
                 const int nk[2] = {r0.y > 0 ? (r0.w + kKB - 1) / kKB : 0, r1.y > 0 ? (r1.w + kKB - 1) / kKB : 0};
-                const bool same = nk[0] > 0 && nk[1] > 0 && r0.z == r1.z;
+                const bool same = nk[0] > 0 && nk[1] > 0 && r0.z == r1.z && r0.w == r1.w;
                 const int col = head * HD;
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
@@ -376,6 +395,7 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     VF_IDLE_WAIT(k_empty[2 * st + 1], ((idx / kKStages) & 1) ^ 1);
                     mbar_arrive_expect_tx(k_full[st], kKvBytes);
                     tma_load_2d(sm_k + st * kKvBytes, &tmK, k_full[st], col, krow[s] + j * kKB);
+                    sts_release(k_issued, idx + 1);
                 };
                 auto load_v = [&](int j, int s) {
                     const uint32_t idx = base + ring_offset(j, s, same, nk[0], nk[1]);
@@ -384,6 +404,7 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     VF_IDLE_WAIT(v_empty[2 * st + 1], ((idx / kVStages) & 1) ^ 1);
                     mbar_arrive_expect_tx(v_full[st], kKvBytes);
                     tma_load_2d(sm_v + st * kKvBytes, &tmV, v_full[st], col, krow[s] + j * kKB);
+                    sts_release(v_issued, idx + 1);
                 };
 #pragma unroll
                 for (int s = 0; s < 2; ++s) if (nk[s] > 0 && !(s == 1 && same)) load_k(0, s);
@@ -406,8 +427,9 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const uint32_t s_tmem = tmem_base + s * kKB, o_tmem = tmem_base + 128 + s * 64;
             const uint64_t q_desc = umma_desc_kmajor_sw128(sm_q + s * kQBytes);
             const uint64_t p_desc = umma_desc_kmajor_sw128(sm_p + s * kQBytes);
-            struct It { int nk0, nk1, my_nk; uint32_t base, tile0; bool same; };
+            struct It { int nk0, nk1, my_nk, tail; uint32_t base, tile0; bool same; };   // tail: keys in the last block
             uint32_t ring = 0, n_tiles = 0, n_q = 0, n_done = 0;      // ring position, score tiles / items started / finished
+            uint32_t seen_k = 0, seen_v = 0;                          // last values read from k_issued / v_issued
             int w = blockIdx.x;
             // next work item in which this slot is occupied (the ring position advances over every item)
             auto next_valid = [&](It& it) -> bool {
@@ -416,10 +438,11 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const int4 r0 = __ldg(recs + 4 * item), r1 = __ldg(recs + 4 * item + 2);
                     it.nk0 = r0.y > 0 ? (r0.w + kKB - 1) / kKB : 0;
                     it.nk1 = r1.y > 0 ? (r1.w + kKB - 1) / kKB : 0;
-                    it.same = it.nk0 > 0 && it.nk1 > 0 && r0.z == r1.z;
+                    it.same = it.nk0 > 0 && it.nk1 > 0 && r0.z == r1.z && r0.w == r1.w;
                     it.base = ring;
                     ring += it.same ? it.nk0 : it.nk0 + it.nk1;
                     it.my_nk = s == 0 ? it.nk0 : it.nk1;
+                    it.tail = (s == 0 ? r0.w : r1.w) - (it.my_nk - 1) * kKB;
                     if (it.my_nk > 0) { w += gridDim.x; return true; }
                 }
                 return false;
@@ -430,11 +453,23 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 // must never disagree on whether the early Q K^T went out
                 return __shfl_sync(0xffffffffu, (int)mbar_test_wait(bar, parity), 0) != 0;
             };
+            // has the producer issued block idx of a ring?  (one lane's answer for the warp, as above)
+            auto issued = [&](uint32_t ctr, uint32_t& seen, uint32_t idx, bool blocking) -> bool {
+                if (seen > idx) return true;
+                uint32_t spins = 0;
+                do {
+                    seen = __shfl_sync(0xffffffffu, lds_acquire(ctr), 0);
+                    if (!blocking) break;
+                    if ((++spins & 0xFFFFFFu) == 0 && seen <= idx) __trap();      // ~seconds: a pipeline bug, never a wait
+                } while (seen <= idx);
+                return seen > idx;
+            };
             // S(j) = Q K(j)^T of item `it`; non-blocking mode gives up (nothing issued) if an input has not landed yet
             auto issue_qk = [&](It& it, int j, bool blocking) -> bool {
                 const uint32_t idx = it.base + ring_offset(j, s, it.same, it.nk0, it.nk1);
                 const uint32_t st = idx % kKStages;
                 if (j == 0 && !ready(q_full[s], n_q & 1, blocking)) return false;
+                if (!issued(k_issued, seen_k, idx, blocking)) return false;
                 if (!ready(k_full[st], (idx / kKStages) & 1, blocking)) return false;
                 if (!ready(s_empty[s], (n_tiles & 1) ^ 1, blocking)) return false;      // previous scores are in registers
                 if (j == 0) { ++n_q; it.tile0 = n_tiles; }
@@ -469,11 +504,22 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const uint32_t idx = cur.base + ring_offset(j, s, cur.same, cur.nk0, cur.nk1);
                     const uint32_t st = idx % kVStages;
                     if (j == 0) mbar_wait(o_empty[s], (n_done & 1) ^ 1);   // previous item's O has been read out
+                    issued(v_issued, seen_v, idx, true);
                     mbar_wait(v_full[st], (idx / kVStages) & 1);
+                    const uint32_t vb = sm_v + st * kKvBytes;
+                    if (j + 1 == cur.my_nk && cur.tail < kKB) {
+                        // The last block of a sequence over-fetches rows of whatever follows it in the K/V tensors.  Their
+                        // probabilities are exactly 0, but 0 x NaN/Inf would still poison O: clear those V rows (a row of
+                        // the [64 keys x 64] SWIZZLE_128B tile is 128 contiguous bytes).  Both issuers of a shared stream
+                        // write the same zeros.
+                        for (int r = cur.tail + (lane >> 3); r < kKB; r += 4)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(vb + r * 128 + (lane & 7) * 16), "r"(0u) : "memory");
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                    }
                     mbar_wait(p_full[s], (cur.tile0 + j) & 1);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t vb = sm_v + st * kKvBytes;
                         #pragma unroll
                         for (int kk = 0; kk < kKB / 16; ++kk)
                             umma_bf16(o_tmem, p_desc + 2 * kk, umma_desc_kmajor_sw128(vb + kk * 2048), idesc_pv, (j | kk) != 0);

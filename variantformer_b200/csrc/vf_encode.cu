@@ -81,7 +81,8 @@ encode_windows_kernel(const EncodeParams p) {
         s_n = n; s_total = (w1 - w0) + shift;
         if (bad) atomicMax(p.err, bad);
         if (s_total > p.pitch) atomicMax(p.err, 1);
-        if (blockIdx.x == 0) p.out_len[w] = s_total;
+        // an overflowing window writes nothing: report length 0 (plus err = 1) so the tokenizer never reads past the row
+        if (blockIdx.x == 0) p.out_len[w] = s_total > p.pitch ? 0 : s_total;
     }
     __syncthreads();
     const int n = s_n, total = s_total;
@@ -170,6 +171,8 @@ struct BpeParams {
     int32_t* out_tokens; int out_pitch; int out_cap;          // [n_win, out_pitch]; first out_cap tokens kept, rest of the row zeroed
     int32_t* out_count;                                       // [n_win] total token count (before truncation)
     int32_t* out_start; int64_t start_pitch;                  // optional [n_win, start_pitch]: first base of every token
+    int max_len;                                              // lengths are clamped to this (and to pitch): a corrupt or
+                                                              // overflowed length can never index past a row
 };
 
 __device__ __forceinline__ uint16_t base_symbol(uint8_t c) {
@@ -189,7 +192,7 @@ __global__ void bpe_tokenize_kernel(const BpeParams p) {
     __shared__ int s_warp_tot[32];
     __shared__ int s_any;
     const int w = blockIdx.x;
-    const int n = p.len[w];
+    const int n = max(0, min(p.len[w], p.max_len));
     const int tid = threadIdx.x, nt = blockDim.x;
     const bool in_smem = n <= kBpeSmemSyms;
     uint16_t* sym = in_smem ? s_sym : p.scratch + (size_t)w * p.scratch_pitch;
@@ -314,7 +317,7 @@ bpe_tokenize_cluster_kernel(const BpeParams p, const int seg_cap) {
     __shared__ int s_warp_tot[32];
     const int rank = (int)cluster.block_rank();
     const int w = blockIdx.x / kBpeCluster;
-    const int n = p.len[w];
+    const int n = max(0, min(p.len[w], p.max_len));
     const int tid = threadIdx.x, nt = blockDim.x;
     const int seg = max(8, (n + kBpeCluster - 1) / kBpeCluster);      // <= seg_cap (host guarantees)
     const int lo = min(n, rank * seg), hi = min(n, lo + seg);
@@ -462,7 +465,8 @@ int bpe_tokenize(const uint8_t* seq, int64_t pitch, const int32_t* len, int n_wi
     VF_REQUIRE(out_cap <= out_pitch, "bpe_tokenize: out_cap %d > out_pitch %d", out_cap, out_pitch);
     VF_REQUIRE(out_start == nullptr || start_pitch >= max_len, "bpe_tokenize: start_pitch too small");
     BpeParams p{seq, pitch, len, merge_a, merge_b, merge_new, n_merges, scratch, scratch_pitch,
-                out_tokens, out_pitch, out_cap, out_count, out_start, start_pitch};
+                out_tokens, out_pitch, out_cap, out_count, out_start, start_pitch,
+                (int)(pitch < (int64_t)max_len ? pitch : (int64_t)max_len)};
     if (max_len > kBpeSmemSyms) {
         // cluster path: 8 CTAs per window, segment of the symbol array per CTA in shared memory
         const int seg_cap = (max_len + kBpeCluster - 1) / kBpeCluster + 8;

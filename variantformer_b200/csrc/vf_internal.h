@@ -12,20 +12,6 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
               const void* resid, int resid_bf16, int ldr, void* out, int ldo, void* out2, int ldo2, const float* ln_stats,
               int ln_parts, const float* ln_colsum, int ln_dim, float ln_eps, float* stats_out, cudaStream_t stream);
 
-int attention_varlen(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
-                     const int* cu_q, const int* cu_k, const int* tile_seq, const int* tile_q0, int n_tiles,
-                     int block_m, int heads, int head_dim, const float* slopes, cudaStream_t stream);
-
-int attention_tc_varlen(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
-                        long rows_q, long rows_k, const int* cu_q, const int* cu_k, const int* item_seq,
-                        const int* item_q0, int n_items, int heads, int head_dim, const float* slopes,
-                        int short_items, cudaStream_t stream);
-
-int attention_tc128_varlen(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
-                           long rows_q, long rows_k, const int* cu_q, const int* cu_k, const int* item_seq,
-                           const int* item_q0, int n_items, int heads, int head_dim, const float* slopes,
-                           cudaStream_t stream);
-
 int attention_mc_varlen(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
                         long rows_q, long rows_k, const int* slots, int n_items, int heads, int head_dim,
                         const float* slopes, cudaStream_t stream);

@@ -89,7 +89,18 @@ class VEPBatchBuilder:
         wins = [cre_window(gene.cre_start[i], gene.cre_end[i], self.nb) for i in order]
         g0, g1 = gene_window(gene.start, gene.end, gene.strand, self.up, self.down)
         # overlap tests use 1-based pos against 0-based half-open windows: start < pos <= end
-        cre_hit = next((k for k, (a, b) in enumerate(wins) if a < variant.pos <= b), None)
+        # The reference walks the rows in batch order with no break after a hit (vepdataset.py:367-407): EVERY
+        # overlapping window it reaches gets the variant, cre_token_position is the LAST of them, and the walk stops
+        # early at the first row that starts past the variant (+ strand) / ends before it (- strand, rows descending).
+        hits = []
+        for k, (a, b) in enumerate(wins):
+            if (not minus and a > variant.pos) or (minus and b < variant.pos):
+                break
+            if a < variant.pos <= b:
+                hits.append(k)
+        cre_hit = hits[-1] if hits else None
+        # windows containing the variant that the early break never reached keep their background sequence
+        unreached = [k for k, (a, b) in enumerate(wins) if a < variant.pos <= b and k not in hits]
         gene_hit = g0 < variant.pos <= g1
         if cre_hit is None and not gene_hit:
             return {k: [] for k in ("cre_sequences", "cre_attention_masks", "tissue_context", "labels", "ref_labels",
@@ -112,6 +123,13 @@ class VEPBatchBuilder:
             seq, lens, err1 = self.tok.sequences(self.genome, chroms, [w[0] for w in wins], [w[1] for w in wins],
                                                  [int(minus)] * len(wins), sv)
             ctok, cmask, _ = self.tok.tokenize_fixed(seq, lens, seq.shape[1], typical_len=self.tok.last_max_window)
+            if unreached and sv is not samples[0]:
+                useq, ulens, _ = self.tok.sequences(self.genome, [chroms[k] for k in unreached],
+                                                    [wins[k][0] for k in unreached], [wins[k][1] for k in unreached],
+                                                    [int(minus)] * len(unreached), samples[0])
+                utok, umask, _ = self.tok.tokenize_fixed(useq, ulens, useq.shape[1], typical_len=self.tok.last_max_window)
+                idx = torch.as_tensor(unreached, device=self.device)
+                ctok[idx] = utok; cmask[idx] = umask
             gseq, glens, err2 = self.tok.sequences(self.genome, [gene.chrom], [g0], [g1], [int(minus)], sv)
             cap = self.max_length * self.context_window
             gtok, gcnt, starts = ops.bpe_tokenize(gseq, glens, gseq.shape[1], self.tok.merges, cap, cap, want_starts=True)

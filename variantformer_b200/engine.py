@@ -30,36 +30,27 @@ from ._lib import EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GEGLU_BF16, EPI_BIAS_GEL
 from .utils.alibi import alibi_slopes
 
 NUM_REF_CRES = 9
-# "mc" = tcgen05/TMEM attention, two CTAs per SM, for every attention of the path (default);
-# "legacy" = the round-1 mma.sync kernel everywhere (debug cross-check only)
-ATTENTION_IMPL = os.environ.get("VF_ATTENTION", "mc")
 # run the CRE stack on its own CUDA stream, concurrently with the gene stack ("0": one stream, for A/B and debugging)
 CRE_STREAM = os.environ.get("VF_CRE_STREAM", "1") != "0"
 
 
 class AttnPlan:
-    """Host-built work decomposition of one attention problem (all sequences of a slab, one launch).  The kernel is
-    chosen per ROLE and head size, never per batch content, so results do not depend on how genes are batched."""
+    """Host-built work decomposition of one attention problem (all sequences of a slab, one launch of
+    vf_attention_mc_varlen).  The decomposition depends on the sequence lengths only, never on how genes are batched,
+    so results do not depend on the batching."""
 
     def __init__(self, q_lens, device, head_dim, k_lens=None, units=None):
-        self.mc = ATTENTION_IMPL == "mc" and head_dim in (48, 64)
-        if units is not None:                                  # explicit slot records (mc kernel only)
-            assert self.mc
-            self.slots = ops.SlotMap.from_units(units, device)
-        elif self.mc:
-            self.slots = ops.SlotMap(q_lens, device, k_lens=k_lens)
-        else:
-            kl = q_lens if k_lens is None else k_lens
-            self.cu_q, self.cu_k = ops.cu_seqlens(q_lens, device), ops.cu_seqlens(kl, device)
-            self.tiles = ops.TileMap(q_lens, 64, device, k_lens=k_lens)
+        if head_dim not in (48, 64):
+            raise NotImplementedError(f"attention head size {head_dim}: the B200 kernel is built for 48 and 64 "
+                                      "(vf_model.yaml: 1536/32 = 48; seq2reg 512/8 = 64)")
+        self.slots = ops.SlotMap.from_units(units, device) if units is not None else \
+            ops.SlotMap(q_lens, device, k_lens=k_lens)
 
     def device_tensors(self):
-        return [self.slots.table] if self.mc else [self.cu_q, self.cu_k, self.tiles.tile_seq, self.tiles.tile_q0]
+        return [self.slots.table]
 
     def run(self, q, k, v, heads, head_dim, slopes, out):
-        if self.mc:
-            return ops.attention_mc(q, k, v, self.slots, heads, head_dim, slopes, out=out)
-        return ops.attention(q, k, v, self.cu_q, self.cu_k, self.tiles, heads, head_dim, slopes, out=out)
+        return ops.attention_mc(q, k, v, self.slots, heads, head_dim, slopes, out=out)
 
 
 def sinusoidal_pe(d_model: int, length: int) -> torch.Tensor:
@@ -359,20 +350,19 @@ class Engine:
             need_seq = np.concatenate([need_seq, np.arange(n_seq)]); need_off = np.concatenate([need_off, gp])
         s["last_rows"] = up(reg_rows[need_seq] + need_off, np.int32)
         s["n_need"] = int(len(need_seq))
-        if ATTENTION_IMPL == "mc" and self.w.hd in (48, 64):
-            k = np.arange(len(need_seq))
-            s["plan_last_self"] = AttnPlan(None, dev, self.w.hd, units=np.stack(
-                [k, np.ones_like(k), reg_rows[need_seq], seq_lens[need_seq], need_off], 1))
-            gene_of = np.repeat(np.arange(B), T)[need_seq]                                  # gene of every needed row
-            cu_cre_np = np.concatenate([[0], np.cumsum(C)])
-            units = []
-            start = 0
-            for i in range(1, len(k) + 1):                                                 # runs of one gene, <= 128 rows
-                if i == len(k) or gene_of[i] != gene_of[start] or i - start == 128:
-                    g = gene_of[start]
-                    units.append([start, i - start, cu_cre_np[g], C[g], 0])
-                    start = i
-            s["plan_last_cross"] = AttnPlan(None, dev, self.w.hd, units=np.asarray(units))
+        k = np.arange(len(need_seq))
+        s["plan_last_self"] = AttnPlan(None, dev, self.w.hd, units=np.stack(
+            [k, np.ones_like(k), reg_rows[need_seq], seq_lens[need_seq], need_off], 1))
+        gene_of = np.repeat(np.arange(B), T)[need_seq]                                  # gene of every needed row
+        cu_cre_np = np.concatenate([[0], np.cumsum(C)])
+        units = []
+        start = 0
+        for i in range(1, len(k) + 1):                                                 # runs of one gene, <= 128 rows
+            if i == len(k) or gene_of[i] != gene_of[start] or i - start == 128:
+                g = gene_of[start]
+                units.append([start, i - start, cu_cre_np[g], C[g], 0])
+                start = i
+        s["plan_last_cross"] = AttnPlan(None, dev, self.w.hd, units=np.asarray(units))
         if gene_token_position is not None:
             s["gene_pos_idx"] = up(reg_rows + gp, np.int32)                                 # (:665-666)
         if cre_token_position is not None:

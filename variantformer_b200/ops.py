@@ -4,6 +4,8 @@ torch is used only for device memory and streams; every computation happens in
 libvf_b200.so.  `LAUNCHES` counts kernel launches issued through this module
 (bench.py reports it as `gpu_launches`).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -147,68 +149,19 @@ def rowstats(x, stats=None, out_bf16=None):
     return stats
 
 
-class TileMap:
-    """Query-tile map of a batch of variable-length sequences (host-built, device-resident)."""
-
-    def __init__(self, q_lens, block_m, device, k_lens=None):
-        q_lens = np.asarray(q_lens, np.int64)
-        self.qk_pairs = float((q_lens * (q_lens if k_lens is None else np.asarray(k_lens, np.int64))).sum())
-        nt = (q_lens + block_m - 1) // block_m
-        seq = np.repeat(np.arange(len(q_lens)), nt)
-        first = np.cumsum(nt) - nt
-        q0 = (np.arange(int(nt.sum())) - np.repeat(first, nt)) * block_m
-        self.block_m = block_m
-        self.max_rows = int(q_lens.max()) if len(q_lens) else 0
-        self.n_tiles = int(nt.sum())
-        self.tile_seq = torch.from_numpy(seq.astype(np.int32)).to(device, non_blocking=True)
-        self.tile_q0 = torch.from_numpy(q0.astype(np.int32)).to(device, non_blocking=True)
-
-
 def cu_seqlens(lens, device):
     cu = np.zeros(len(lens) + 1, np.int32)
     np.cumsum(np.asarray(lens, np.int64), out=cu[1:])
     return torch.from_numpy(cu).to(device, non_blocking=True)
 
 
-def attention(q, k, v, cu_q, cu_k, tiles: TileMap, heads, head_dim, slopes=None, out=None):
-    """Varlen attention.  q [Tq, >=H*hd] / k, v [Tk, >=H*hd] bf16 views (row stride arbitrary, unit column stride)."""
-    for t in (q, k, v):
-        assert t.is_cuda and t.dtype == torch.bfloat16 and t.stride(1) == 1
-    if out is None:
-        out = torch.empty((q.shape[0], heads * head_dim), dtype=torch.bfloat16, device=q.device)
-    with _timed("attention", 4.0 * tiles.qk_pairs * heads * head_dim):
-        check(_lib.lib().vf_attention_varlen(ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(out),
-                                             out.stride(0), ptr(cu_q), ptr(cu_k), ptr(tiles.tile_seq),
-                                             ptr(tiles.tile_q0), tiles.n_tiles, tiles.block_m, heads, head_dim,
-                                             ptr(slopes), stream()))
-    return out
-
-
-TC_BLOCK_M = 512          # tcgen05 attention: work items of up to 4 x 128 query rows
-
-
-def attention_tc(q, k, v, cu_q, cu_k, items: TileMap, heads, head_dim, slopes=None, out=None, key_block=64):
-    """Varlen attention on the tcgen05 path (vf_attention_tc_varlen); `items` = TileMap(..., TC_BLOCK_M, ...)."""
-    for t in (q, k, v):
-        assert t.is_cuda and t.dtype == torch.bfloat16 and t.stride(1) == 1
-    assert items.block_m == TC_BLOCK_M
-    if out is None:
-        out = torch.empty((q.shape[0], heads * head_dim), dtype=torch.bfloat16, device=q.device)
-    with _timed("attention", 4.0 * items.qk_pairs * heads * head_dim):
-        check(_lib.lib().vf_attention_tc_varlen(ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0),
-                                                ptr(out), out.stride(0), q.shape[0], k.shape[0], ptr(cu_q), ptr(cu_k),
-                                                ptr(items.tile_seq), ptr(items.tile_q0), items.n_tiles, heads,
-                                                head_dim, ptr(slopes), key_block, int(key_block == 64 and items.max_rows <= 256),
-                                                stream()))
-    return out
-
-
-# Two query tiles that read DIFFERENT key ranges in one work item ("split" items: each slot streams its own K/V
-# through the shared rings) are disabled: a 12 000-launch determinism stress (tools/stress_attention.py) found one
-# launch in 12 000 whose output differed — an MMA issuer waits by parity on a ring stage whose previous use belonged to
-# the other slot, and bulk loads can complete far enough out of order to alias that parity.  Left-over tiles therefore
-# run alone (slot 1 empty: half of the softmax warps idle for those items) until the kernel counts uses per stage.
-PAIR_UNRELATED_TILES = False
+# Left-over query tiles (sequences of <= 128 rows, the odd last tile of longer ones) are paired into one work item even
+# though they read DIFFERENT key ranges ("split" items: each slot streams its own K/V through the shared rings).  Round 1
+# had to switch this off: an MMA issuer waits by parity on a ring stage whose previous use belonged to the other slot, and
+# one launch in 12 000 went wrong.  The kernel now orders those waits behind the producer's issue counters
+# (vf_attention_mc.cu: lds_acquire), so pairing is on again; VF_PAIR_TILES=0 restores the one-tile-per-item tables for
+# A/B runs.  profiles/r02_stress_attention.log holds the determinism stress this rests on.
+PAIR_UNRELATED_TILES = os.environ.get("VF_PAIR_TILES", "1") != "0"
 
 
 class SlotMap:
@@ -233,7 +186,10 @@ class SlotMap:
         rec[:, 2] = cu_k[seq]
         rec[:, 3] = k_lens[seq]
         rec[:, 4] = 128 * t + k_lens[seq] - q_lens[seq]
-        rec = rec[rec[:, 3] > 0]                                          # a sequence without keys has no output
+        # a sequence without keys gets no work item; attention_mc() zero-fills its output rows (what flash_attn
+        # returns for an empty key range) so that a reused buffer never leaks a previous slab's values
+        self.keyless = [(int(cu_q[i]), int(cu_q[i + 1])) for i in np.nonzero((k_lens == 0) & (q_lens > 0))[0]]
+        rec = rec[rec[:, 3] > 0]
         odd = (t == nt[seq] - 1) & (nt[seq] % 2 == 1)
         odd = odd[(k_lens[seq] > 0)]
         pairs, singles = rec[~odd], rec[odd]
@@ -253,6 +209,8 @@ class SlotMap:
         row 0}; consecutive units are paired into items (units with the same key range share their K/V stream)."""
         self = cls.__new__(cls)
         units = np.asarray(units, np.int64).reshape(-1, 5)
+        self.keyless = [(int(u[0]), int(u[0] + u[1])) for u in units if u[3] == 0 and u[1] > 0]
+        units = units[units[:, 3] > 0]
         self.qk_pairs = float((units[:, 1] * units[:, 3]).sum())
         n = len(units)
         if PAIR_UNRELATED_TILES:
@@ -281,6 +239,8 @@ def attention_mc(q, k, v, slots: SlotMap, heads, head_dim, slopes=None, out=None
         assert t.is_cuda and t.dtype == torch.bfloat16 and t.stride(1) == 1
     if out is None:
         out = torch.empty((q.shape[0], heads * head_dim), dtype=torch.bfloat16, device=q.device)
+    for r0, r1 in slots.keyless:
+        out[r0:r1].zero_()
     with _timed("attention", 4.0 * slots.qk_pairs * heads * head_dim,
                 lambda: f"h={heads} hd={head_dim}{' alibi' if slopes is not None else ''} rows={q.shape[0]} keys={k.shape[0]}"):
         check(_lib.lib().vf_attention_mc_varlen(ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0),

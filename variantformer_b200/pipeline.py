@@ -117,7 +117,9 @@ class HotPath:
             except StopIteration:
                 nxt = None
             if to_host:
-                yield out["pred"].cpu().numpy(), out["emb"].cpu().numpy()
+                pred, emb = out["pred"].cpu().numpy(), out["emb"].cpu().numpy()
+                self._raise_on_stage1_error(slab["err"])
+                yield pred, emb
             else:
                 yield out["pred"], out["emb"], slab["err"]
 
@@ -131,7 +133,13 @@ class HotPath:
         if not to_host:
             return out["pred"], out["emb"], t["err"]
         pred = out["pred"].cpu().numpy(); emb = out["emb"].cpu().numpy()
-        code = int(t["err"].item())
+        self._raise_on_stage1_error(t["err"])
+        return pred, emb
+
+    @staticmethod
+    def _raise_on_stage1_error(err):
+        """The encode kernel flags windows it could not build (their tokens are then all padding): never hand out
+        predictions computed from them."""
+        code = int(err.item())
         if code:
             raise RuntimeError(f"stage-1 kernel reported error {code} (1: pitch overflow, 2: >2048 variants/window)")
-        return pred, emb
