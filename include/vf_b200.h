@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VF_B200_ABI_VERSION 1
+#define VF_B200_ABI_VERSION 2
 
 const char* vf_last_error(void);
 int vf_abi_version(void);
@@ -127,9 +127,24 @@ int vf_compact_tokens(const int32_t* tokens, const uint8_t* pad_mask, const int3
 /* x[t] = E[ids[t]] + PE[pos[t]] (pe may be NULL): seq2reg/model.py:214-220. */
 int vf_embed_tokens(const int32_t* ids, const int32_t* pos, const float* emb, const float* pe, int n_tok, int d,
                     float* out, void* stream);
-/* Mean over each window's tokens (seq2reg/model.py:263-267); empty window -> NaN as upstream. */
-int vf_masked_meanpool(const float* x, int ldx, const int32_t* cu, int n_win, int d, void* out_bf16, float* out_f32,
-                       int ldo, void* stream);
+/* Mean over each window's tokens (seq2reg/model.py:263-267); empty window -> NaN as upstream.
+ * pivot (fp32 [n_tok] or NULL): the rows are a centred stream (vf_center_rows); their pivots are added back. */
+int vf_masked_meanpool(const float* x, int ldx, const int32_t* cu, int n_win, int d, const float* pivot, void* out_bf16,
+                       float* out_f32, int ldo, void* stream);
+/*
+ * Row-centred residual streams.  Every consumer of a residual stream of the path is a LayerNorm (invariant under a
+ * per-row shift: seq2reg/modules.py:176,185; layers.py:116,140,158) or a residual add (which carries a shift along), so
+ * a stream may be kept as x' = x - pivot_r.  With pivot_r = the row mean where the stream is assembled, the bf16 mirror
+ * that the LayerNorm-folded GEMMs read keeps the bits of the NORMALISED signal even when |mean| >> std (the reference
+ * normalises in fp32 before rounding to bf16).
+ * vf_center_rows: x <- x - mean_r in place (fp32 [M,d]); pivot[r] = mean_r; stats [M,1,2] = (sum, sum of squares) of
+ * the shifted row; optional bf16 mirror.  Replaces vf_rowstats where a stream is born.
+ * vf_uncenter_rows: out[r] = x[r] + pivot[idx ? idx[r] : r] (fp32 and/or bf16): raw values for the cross-attention
+ * context (layers.py:142-150: context is not normalised) and for the returned embeddings.
+ */
+int vf_center_rows(float* x, int ldx, int M, int d, float* pivot, float* stats, void* out_bf16, int ldo, void* stream);
+int vf_uncenter_rows(const float* x, int ldx, const float* pivot, const int32_t* idx, int M, int d, float* out_f32,
+                     void* out_bf16, int ldo, void* stream);
 /* out[r] = idx[r] >= 0 ? table_a[idx[r]] : table_b[-idx[r]-1]  (registry-token prepend / tissue replication:
  * seq2gene/modules/layers.py:508-521, model_combined_modulator.py:622-649; pool_outputs :391-392). */
 int vf_gather_rows(const float* table_a, int lda, const float* table_b, int ldb, const int32_t* idx, int n_rows, int d,

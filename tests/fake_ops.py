@@ -161,9 +161,27 @@ def embed_tokens(ids, pos, emb, pe):
     return x + pe[pos.long()] if pe is not None else x
 
 
-def masked_meanpool(x, cu, n_win, want_f32=False):
+def center_rows(x, pivot=None, stats=None, out_bf16=None):
+    mean = x.mean(1)
+    x.sub_(mean[:, None])
+    st = torch.stack([x.sum(1), (x * x).sum(1)], 1)[:, None, :]
+    if out_bf16 is not None:
+        out_bf16.copy_(x.bfloat16())
+    pivot = _store(pivot, mean) if pivot is not None else mean
+    return pivot, (_store(stats, st) if stats is not None else st)
+
+
+def uncenter_rows(x, pivot, idx=None, want_f32=True, want_bf16=False, out_bf16=None):
+    y = x + (pivot if idx is None else pivot[idx.long()])[:, None]
+    ob = _store(out_bf16, y) if out_bf16 is not None else (y.bfloat16() if want_bf16 else None)
+    return (y if want_f32 else None), ob
+
+
+def masked_meanpool(x, cu, n_win, want_f32=False, pivot=None):
     lens = torch.from_numpy(np.diff(cu.numpy())).long()
     seg = torch.repeat_interleave(torch.arange(n_win), lens)
+    if pivot is not None:
+        x = x + pivot[:, None]
     p = torch.zeros(n_win, x.shape[1]).index_add_(0, seg, x) / lens[:, None]
     return (p.bfloat16(), p) if want_f32 else p.bfloat16()
 

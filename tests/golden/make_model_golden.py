@@ -78,6 +78,31 @@ def main():
     np.savez_compressed(path, **save)
     print("wrote", path, os.path.getsize(path), "bytes; preds", [p.ravel().tolist() for p in out["pred_gene_exp"]])
 
+    # second, larger fixture from the same reference classes and weights: multi-tile CRE attention (C = 300 > 128 and
+    # > 256), G = 130 gene chunks (> 128: two query tiles per tissue copy), both strand flags, T = 5 and the full
+    # T = 63 tissue axis.  Tokens are stored as int16, masks as uint8 (tests/common.py:load_model_golden widens them).
+    rng = np.random.default_rng(100)
+    big = synth_batch(rng, 2, (300, 301), (130, 131), [[62, 0, 14, 33, 5], list(range(63))])
+    big2 = synth_batch(rng, 1, (150, 151), (40, 41), [list(range(63))])
+    for k in big:                                         # gene 1 of the fixture = the smaller C/G gene with T = 63
+        if k != "strand_val":
+            big[k][1] = big2[k][0]
+    with torch.no_grad():
+        out = model.predict_step(big, 0)
+    save = {"n_genes": 2}
+    for g in range(2):
+        for k in ("cre_sequences", "gene_embeddings"):
+            save[f"{k}_{g}"] = big[k][g].numpy().astype(np.int16)
+        for k in ("cre_attention_masks", "gene_attention_masks"):
+            save[f"{k}_{g}"] = big[k][g].numpy().astype(np.uint8)
+        for k in ("tissue_context", "ref_cre_labels"):
+            save[f"{k}_{g}"] = big[k][g].numpy().astype(np.int16)
+        save[f"pred_{g}"] = out["pred_gene_exp"][g]; save[f"emb_{g}"] = out["embeddings"][g]
+    save["strand_val"] = big["strand_val"].numpy()
+    path = os.path.join(HERE, "model_golden_large.npz")
+    np.savez_compressed(path, **save)
+    print("wrote", path, os.path.getsize(path), "bytes; shapes", [e.shape for e in out["embeddings"]])
+
 
 if __name__ == "__main__":
     main()

@@ -17,7 +17,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()                                    # dlopen only, no device access
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.vf_abi_version() == 1
+    assert lib.vf_abi_version() == 2
 
 
 def test_no_cpu_fallback():

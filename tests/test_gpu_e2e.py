@@ -1,7 +1,8 @@
 """End-to-end parity on the GPU box: CUDA engine vs the fp32 oracle and the reference-generated golden fixture.
 
-Tolerance (BASELINE.json north_star): max rel. error <= 1e-2 (max|got-want| / max|want| over the tensor) and
-Pearson >= 0.9999 on both predicted expression and the 1536-d embeddings; bf16 operands / fp32 accumulate."""
+Tolerance (BASELINE.json north_star; definition and its deviation from SURVEY 8(d) in tests/common.py): max rel.
+error <= 1e-2 (max|got-want| / max|want| over the tensor), max|got-want| / RMS(want) <= 5e-2 and Pearson >= 0.9999 on
+both predicted expression and the embeddings; bf16 operands / fp32 accumulate."""
 import numpy as np
 import pytest
 import torch
@@ -9,11 +10,12 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import model_fp32  # noqa: E402  (checker only)
-from tests.common import GOLD_CFG, GOLD_HP, GOLD_SEED, load_model_golden, pearson, rel_err, synth_batch  # noqa: E402
+from tests.common import (GOLD_CFG, GOLD_HP, GOLD_SEED, PEARSON_MIN, REL_ERR_MAX, REL_ERR_RMS_MAX, load_model_golden,  # noqa: E402
+                          parity_report, pearson, rel_err, synth_batch)
 from variantformer_b200.engine import Engine  # noqa: E402
 from variantformer_b200.utils import random_init  # noqa: E402
 
-REL_TOL, PEARSON_MIN = 1e-2, 0.9999
+REL_TOL = REL_ERR_MAX
 
 
 def _run(engine, batch, **kw):
@@ -28,16 +30,46 @@ def _check(out, want):
     emb = out["emb"].cpu().numpy(); pred = out["pred"].cpu().numpy()
     w_emb = np.concatenate(want["embeddings"]); w_pred = np.concatenate(want["pred_gene_exp"]).ravel()
     assert np.isfinite(emb).all() and np.isfinite(pred).all()
-    e, p = rel_err(emb, w_emb), pearson(emb, w_emb)
-    print(f"emb rel_err {e:.3e} pearson {p:.6f}; pred rel_err {rel_err(pred, w_pred):.3e}")
-    assert e <= REL_TOL and p >= PEARSON_MIN, (e, p)
+    rep = parity_report(emb, w_emb)
+    print(f"emb {rep}; pred rel_err {rel_err(pred, w_pred):.3e}")
+    assert rep["ok"], rep
     assert rel_err(pred, w_pred) <= REL_TOL
+    return rep
 
 
 def test_golden_fixture_from_reference_classes():
     batch, want, _ = load_model_golden()
     eng = Engine(random_init.make_state_dict(GOLD_CFG, GOLD_HP, seed=GOLD_SEED), GOLD_CFG, GOLD_HP)
     _check(_run(eng, batch), want)
+
+
+def test_large_golden_fixture_from_reference_classes():
+    """Reference-generated fixture with multi-tile CRE attention (C = 300), G = 130 chunks, both strand flags, T = 5 and
+    the full T = 63 tissue axis (tests/golden/make_model_golden.py)."""
+    batch, want, _ = load_model_golden("model_golden_large.npz")
+    eng = Engine(random_init.make_state_dict(GOLD_CFG, GOLD_HP, seed=GOLD_SEED), GOLD_CFG, GOLD_HP)
+    out = _run(eng, batch)
+    assert out["T"] == [5, 63]
+    _check(out, want)
+
+
+def test_headline_configuration_full_depth_vs_oracle():
+    """The configuration the benchmark number is quoted on: full-size weights (1536-d, 32 heads, 25 gene + 24 CRE
+    layers; seq2reg 512-d, 8 heads, 6 layers), C = 1024 CRE windows of ~97 tokens, G = 200 full gene chunks, one gene,
+    T = 2 tissues, against the fp32 oracle running the REFERENCE schedule (every tissue copy recomputed)."""
+    cfg = dict(random_init.V4_PCG_MODEL); hp = dict(random_init.SEQ2REG_HP)
+    assert cfg["num_layers"] == 25 and hp["num_layers"] == 6 and cfg["emb_dim"] == 1536
+    sd = random_init.make_state_dict(cfg, hp, seed=0)
+    from variantformer_b200.utils import synth
+    batch = synth.token_batch(5, 1, 1024, 200, 2, tissues=[[62, 7]])
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    want = model_fp32.predict_step(sd, cfg, hp, batch, schedule="reference")
+    eng = Engine({k: v.cuda() for k, v in sd.items()}, cfg, hp)
+    rep = _check(_run(eng, batch), want)
+    # the two tissue copies must differ (otherwise the comparison says nothing about the tissue axis)
+    w = want["embeddings"][0]
+    assert np.abs(w[0] - w[1]).max() > 1e-3 * np.abs(w).max()
+    print("headline-config parity", rep)
 
 
 def test_mid_size_vs_oracle_and_token_positions():

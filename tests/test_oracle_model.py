@@ -22,6 +22,16 @@ def test_oracle_matches_reference_golden():
         np.testing.assert_allclose(got["embeddings"][g], want["embeddings"][g], rtol=2e-4, atol=2e-5)
 
 
+def test_oracle_matches_large_reference_golden():
+    # C = 300 / 150 CREs, G = 130 / 40 chunks, T = 5 / 63, strand flags 0 / 1 — from the reference's own predict_step
+    batch, want, _ = load_model_golden("model_golden_large.npz")
+    got = model_fp32.predict_step(_sd(), GOLD_CFG, GOLD_HP, batch, schedule="dedup")
+    assert [e.shape[0] for e in got["embeddings"]] == [5, 63]
+    for g in range(2):
+        np.testing.assert_allclose(got["pred_gene_exp"][g], want["pred_gene_exp"][g], rtol=5e-5, atol=5e-6)
+        np.testing.assert_allclose(got["embeddings"][g], want["embeddings"][g], rtol=5e-4, atol=5e-5)
+
+
 def test_dedup_schedule_is_exact():
     # the CRE stream is tissue independent
     batch, _, _ = load_model_golden()

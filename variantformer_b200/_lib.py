@@ -31,7 +31,9 @@ SIGNATURES = {
     "vf_window_lengths": ([_vp, _i32, _i32, _vp, _vp], _i32),
     "vf_compact_tokens": ([_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp], _i32),
     "vf_embed_tokens": ([_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp], _i32),
-    "vf_masked_meanpool": ([_vp, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp], _i32),
+    "vf_masked_meanpool": ([_vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp], _i32),
+    "vf_center_rows": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp], _i32),
+    "vf_uncenter_rows": ([_vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp], _i32),
     "vf_gather_rows": ([_vp, _i32, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp], _i32),
     "vf_head_out": ([_vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp], _i32),
     "vf_cast_f32_to_bf16": ([_vp, _vp, _sz, _vp], _i32),
@@ -61,7 +63,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
         fn.argtypes = args
         fn.restype = res
-    if lib.vf_abi_version() != 1:
+    if lib.vf_abi_version() != 2:
         raise VFError("libvf_b200.so ABI version mismatch")
     _lib = lib
     return lib

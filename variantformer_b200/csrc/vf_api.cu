@@ -77,9 +77,16 @@ int vf_embed_tokens(const int32_t* ids, const int32_t* pos, const float* emb, co
                     float* out, void* stream) {
     return embed_tokens(ids, pos, emb, pe, n_tok, d, out, ST(stream));
 }
-int vf_masked_meanpool(const float* x, int ldx, const int32_t* cu, int n_win, int d, void* out_bf16, float* out_f32,
-                       int ldo, void* stream) {
-    return masked_meanpool(x, ldx, cu, n_win, d, out_bf16, out_f32, ldo, ST(stream));
+int vf_masked_meanpool(const float* x, int ldx, const int32_t* cu, int n_win, int d, const float* pivot, void* out_bf16,
+                       float* out_f32, int ldo, void* stream) {
+    return masked_meanpool(x, ldx, cu, n_win, d, pivot, out_bf16, out_f32, ldo, ST(stream));
+}
+int vf_center_rows(float* x, int ldx, int M, int d, float* pivot, float* stats, void* out_bf16, int ldo, void* stream) {
+    return center_rows(x, ldx, M, d, pivot, stats, out_bf16, ldo, ST(stream));
+}
+int vf_uncenter_rows(const float* x, int ldx, const float* pivot, const int32_t* idx, int M, int d, float* out_f32,
+                     void* out_bf16, int ldo, void* stream) {
+    return uncenter_rows(x, ldx, pivot, idx, M, d, out_f32, out_bf16, ldo, ST(stream));
 }
 int vf_gather_rows(const float* table_a, int lda, const float* table_b, int ldb, const int32_t* idx, int n_rows, int d,
                    float* out_f32, void* out_bf16, int ldo, void* stream) {

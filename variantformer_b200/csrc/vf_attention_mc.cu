@@ -507,21 +507,25 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     issued(v_issued, seen_v, idx, true);
                     mbar_wait(v_full[st], (idx / kVStages) & 1);
                     const uint32_t vb = sm_v + st * kKvBytes;
+                    int nkk = kKB / 16;                          // 16-key steps of this block's P V
                     if (j + 1 == cur.my_nk && cur.tail < kKB) {
                         // The last block of a sequence over-fetches rows of whatever follows it in the K/V tensors.  Their
-                        // probabilities are exactly 0, but 0 x NaN/Inf would still poison O: clear those V rows (a row of
-                        // the [64 keys x 64] SWIZZLE_128B tile is 128 contiguous bytes).  Both issuers of a shared stream
-                        // write the same zeros.
-                        for (int r = cur.tail + (lane >> 3); r < kKB; r += 4)
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(vb + r * 128 + (lane & 7) * 16), "r"(0u) : "memory");
-                        fence_proxy_async_smem();
-                        __syncwarp();
+                        // probabilities are exactly 0, but 0 x NaN/Inf would still poison O.  Whole 16-key groups past the
+                        // last key are not multiplied at all; in the partial group the V rows past the end are cleared
+                        // (a row of the [64 keys x 64] SWIZZLE_128B tile is 128 contiguous bytes; at most 15 rows).  Both
+                        // issuers of a shared stream write the same zeros.
+                        nkk = (cur.tail + 15) >> 4;
+                        if (cur.tail & 15) {
+                            for (int r = cur.tail + (lane >> 3); r < nkk * 16; r += 4)
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(vb + r * 128 + (lane & 7) * 16), "r"(0u) : "memory");
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                        }
                     }
                     mbar_wait(p_full[s], (cur.tile0 + j) & 1);
                     tc_fence_after();
                     if (elect_one()) {
-                        #pragma unroll
-                        for (int kk = 0; kk < kKB / 16; ++kk)
+                        for (int kk = 0; kk < nkk; ++kk)
                             umma_bf16(o_tmem, p_desc + 2 * kk, umma_desc_kmajor_sw128(vb + kk * 2048), idesc_pv, (j | kk) != 0);
                         umma_commit(p_empty[s]);
                         umma_commit(v_empty[2 * st + s]);

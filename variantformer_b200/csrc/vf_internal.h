@@ -24,8 +24,11 @@ int compact_tokens(const int* tokens, const uint8_t* pad_mask, const int* cu, in
                    int* out_pos, cudaStream_t s);
 int embed_tokens(const int* ids, const int* pos, const float* emb, const float* pe, int n_tok, int d, float* out,
                  cudaStream_t s);
-int masked_meanpool(const float* x, int ldx, const int* cu, int n_win, int d, void* out_bf16, float* out_f32, int ldo,
-                    cudaStream_t s);
+int center_rows(float* x, int ldx, int M, int d, float* pivot, float* stats, void* out_bf16, int ldo, cudaStream_t s);
+int uncenter_rows(const float* x, int ldx, const float* pivot, const int* idx, int M, int d, float* out_f32,
+                  void* out_bf16, int ldo, cudaStream_t s);
+int masked_meanpool(const float* x, int ldx, const int* cu, int n_win, int d, const float* pivot, void* out_bf16,
+                    float* out_f32, int ldo, cudaStream_t s);
 int gather_rows(const float* ta, int lda, const float* tb, int ldb, const int* idx, int n_rows, int d, float* out_f32,
                 void* out_bf16, int ldo, cudaStream_t s);
 int label_attention(const void* q, int ldq, const float* kv9, const float* logc, const int* row_seq, int n_rows, int H,

@@ -17,6 +17,9 @@ Schedule differences from the reference (results identical, oracle/model_fp32.py
   * every LayerNorm that feeds a Linear is folded into that GEMM: gamma into the weight, beta into the bias, and
     the per-row mean / rstd applied in the GEMM epilogue from (sum, sum of squares) that the epilogue of the GEMM
     which produced the row accumulated.  No LayerNorm pass reads the streams.
+  * residual streams are stored row-centred (x - c_r, c_r = the row mean where the stream is assembled): exact, because
+    every consumer is a LayerNorm or a residual add; raw values are rebuilt where they are needed (cross-attention
+    context, pooled windows, returned embeddings).  Keeps the LayerNorm fold accurate when |mean| >> std.
 Numerics: bf16 GEMM/attention operands, fp32 accumulation, fp32 residual stream and LayerNorm statistics.
 """
 import math
@@ -222,7 +225,10 @@ class Engine:
         qkv = ws.get("r_qkv", (n_tok, 3 * d), torch.bfloat16)
         a = ws.get("r_a", (n_tok, d), torch.bfloat16)
         f = ws.get("r_f", (n_tok, W.layers[0]["g2"].w.shape[1]), torch.bfloat16)
-        ops.rowstats(x, xs0, xb)
+        # the stream is kept row-centred (x - mean of the embedding row): LayerNorm does not see the shift, residual adds
+        # carry it, and the bf16 mirror then spends its 8 bits on the normalised signal (vf_center_rows)
+        piv = ws.get("r_piv", (n_tok,), torch.float32)
+        ops.center_rows(x, piv, xs0, xb)
         for li, L in enumerate(W.layers):
             ops.gemm(xb, L["qkv"].w, EPI_BIAS_BF16, bias=L["qkv"].b, out=qkv,
                      ln=L["qkv"].ln(xs0 if li == 0 else xs))                                           # Wqkv(norm1(x))
@@ -232,7 +238,7 @@ class Engine:
             ops.gemm(a, L["out"].w, EPI_BIAS_RESID_F32, bias=L["out"].b, resid=x, out2=xb, stats_out=s1, mirror_only=True)
             ops.gemm(xb, L["g1"].w, EPI_BIAS_GEGLU_BF16, bias=L["g1"].b, out=f, ln=L["g1"].ln(s1))      # GeGLU(norm2(x1))
             ops.gemm(f, L["g2"].w, EPI_BIAS_RESID_F32, bias=L["g2"].b, resid=x, out=x, out2=xb, stats_out=xs)  # + layer input
-        return ops.masked_meanpool(x, cu, n_win)
+        return ops.masked_meanpool(x, cu, n_win, pivot=piv)
 
     # ---------------------------------------------------------------- one encoder layer of seq2gene
     def _layer(self, L, x, xb, xs, M, self_attn, cross_attn, tag, xb_out=None):
@@ -263,7 +269,7 @@ class Engine:
     def _gene_layer_last(self, L, s, x, xb, xs, kv):
         """The last ContextFlashAttentionEncoderLayer of the gene stream restricted to the rows whose output is read
         (registry rows + VEP token rows): K/V of the self-attention still come from every row, all the rest runs on
-        `need` rows.  Same arithmetic as _layer on those rows.  -> fp32 [n_need, D]."""
+        `need` rows.  Same arithmetic as _layer on those rows.  -> fp32 [n_need, D], still row-centred."""
         ws, w = self.ws, self.w
         D, H, hd = w.D, w.H, w.hd
         M, R = x.shape[0], s["n_need"]
@@ -381,19 +387,21 @@ class Engine:
         # ---- stage 2: window encoders ----
         cre_pooled = self.seq2reg(self.cre_tok, s["ctok"], s["cmsk"], s["clens"], s["c_cu_tok"], s["c_plan_tok"])
         gene_pooled = self.seq2reg(self.gene_tok, s["gtok"], s["gmsk"], s["glens"], s["g_cu_tok"], s["g_plan_tok"])
-        # bf16 mirrors of the CRE stream = cross-attention context of the gene stream: mirror[0] after cre_map,
-        # mirror[i+1] after CRE layer i.  One buffer per layer (25 MB each) so that the CRE stack can run ahead of the
-        # gene stack on its own CUDA stream.
-        mirror = [ws.get(f"cre_bf{i}", (nC, D), torch.bfloat16) for i in range(w.NL)]
         if w.cre_map is None:
             raise NotImplementedError("token_dim == emb_dim (no cre_map) is not wired on the B200 path")
-        cxs = ws.get("cxs", (nC, ops.stats_parts(D), 2), torch.float32)
+        # Both streams are row-centred (see the module docstring): cx / gx hold x - pivot_r, cxb / gxb their bf16 mirrors.
+        # The gene stack's cross-attention reads the RAW CRE stream (the context is not normalised, layers.py:142-150):
+        # `ctx` is its bf16 copy, written by the cre_map epilogue for gene layer 0 and rebuilt (x + pivot) after every
+        # CRE layer, right before the K/V projection that consumes it on the same stream.
+        ctx = ws.get("cre_ctx", (nC, D), torch.bfloat16)
+        cxb = ws.get("cxb", (nC, D), torch.bfloat16)
         cx = ops.gemm(cre_pooled, w.cre_map.w, EPI_BIAS_F32, bias=w.cre_map.b, out=ws.get("cx", (nC, D), torch.float32),
-                      out2=mirror[0], stats_out=cxs)
+                      out2=ctx)
+        cpiv, cxs = ops.center_rows(cx, ws.get("cpiv", (nC,), torch.float32), ws.get("cxs0", (nC, 1, 2), torch.float32), cxb)
         gene_emb = ops.gemm(gene_pooled, w.gene_map.w, EPI_BIAS_F32, bias=w.gene_map.b)
         gx, _ = ops.gather_rows(gene_emb, w.registry, s["gene_idx"])
         gxb = ws.get("gxb", (Mg, D), torch.bfloat16)
-        gxs = ops.rowstats(gx, ws.get("gxs0", (Mg, 1, 2), torch.float32), gxb)
+        gpiv, gxs = ops.center_rows(gx, ws.get("gpiv", (Mg,), torch.float32), ws.get("gxs0", (Mg, 1, 2), torch.float32), gxb)
         st = {"g": gxs, "c": cxs}                                      # current row statistics of each stream
         # K/V of the gene stack's cross-attention, one buffer per gene layer: they depend on the CRE stack only, so the
         # projection of layer i+1 is issued on the CRE stream right behind CRE layer i
@@ -407,7 +415,7 @@ class Engine:
 
         def project_kv(i):
             L = w.gene_layers[i]
-            ops.gemm(mirror[i], L["kv"].w, EPI_BIAS_BF16, bias=L["kv"].b, out=kvs[i])    # shared by every tissue copy
+            ops.gemm(ctx, L["kv"].w, EPI_BIAS_BF16, bias=L["kv"].b, out=kvs[i])          # shared by every tissue copy
 
         def gene_layer(i):
             L, kv = w.gene_layers[i], kvs[i]
@@ -421,7 +429,8 @@ class Engine:
 
             def cross(q, out):
                 ops.label_attention(q, L["kv9"], s["logc"], s["row_seq"], H, hd, out=out)
-            st["c"] = self._layer(L, cx, mirror[i], st["c"], nC, cre_self, cross, "c", xb_out=mirror[i + 1])
+            st["c"] = self._layer(L, cx, cxb, st["c"], nC, cre_self, cross, "c")
+            ops.uncenter_rows(cx, cpiv, want_f32=False, out_bf16=ctx)                    # context of gene layer i + 1
 
         # The CRE stack does not depend on the gene stack (gene layer i+1 reads the output of CRE layer i, never the
         # other way round): it runs on a second CUDA stream and its short kernels (8 192 rows) fill the tails of the
@@ -458,11 +467,12 @@ class Engine:
         n_reg = s["reg_idx"].numel()
         if prune_last:
             last = self._gene_layer_last(w.gene_layers[w.NL - 1], s, gx, gxb, st["g"], kvs[w.NL - 1])
-            emb = last[:n_reg]
-            emb_bf = ops.cast_bf16(emb.contiguous())
+            last, last_bf = ops.uncenter_rows(last, gpiv, idx=s["last_rows"], want_bf16=True)
+            emb, emb_bf = last[:n_reg], last_bf[:n_reg]
         else:
             last = None
-            emb, emb_bf = ops.gather_rows(gx, None, s["reg_idx"], want_f32=True, want_bf16=True)
+            emb, _ = ops.gather_rows(gx, None, s["reg_idx"])
+            emb, emb_bf = ops.uncenter_rows(emb, gpiv, idx=s["reg_idx"], want_bf16=True)
 
         # ---- registry rows -> embeddings -> head ----
         h1 = ops.gemm(emb_bf, w.h0.w, EPI_BIAS_F32, bias=w.h0.b)
@@ -474,9 +484,11 @@ class Engine:
             if last is not None:
                 out["gene_token_embedding"] = last[n_reg:]
             else:
-                out["gene_token_embedding"], _ = ops.gather_rows(gx, None, s["gene_pos_idx"])
+                t, _ = ops.gather_rows(gx, None, s["gene_pos_idx"])
+                out["gene_token_embedding"], _ = ops.uncenter_rows(t, gpiv, idx=s["gene_pos_idx"])
         if "cre_pos_idx" in s:
-            out["cre_token_embedding"], _ = ops.gather_rows(cx, None, s["cre_pos_idx"])
+            t, _ = ops.gather_rows(cx, None, s["cre_pos_idx"])
+            out["cre_token_embedding"], _ = ops.uncenter_rows(t, cpiv, idx=s["cre_pos_idx"])
         return out
 
     def forward_tokens(self, cre_tokens, cre_masks, gene_tokens, gene_masks, tissues, ref_labels, **kw):

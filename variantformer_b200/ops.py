@@ -28,36 +28,37 @@ class EventProfiler:
         e.record()
         return e
 
-    def end(self, e0, kind, flops=0.0, detail=None):
+    def end(self, e0, kind, flops=0.0, detail=None, nbytes=0.0):
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
-        self.items.append((kind, float(flops), e0, e1, detail))
+        self.items.append((kind, float(flops), e0, e1, detail, float(nbytes)))
 
     def summarize(self):
+        """kind -> {ms, flops, bytes (algorithmic operand + result bytes of the launches), n}."""
         torch.cuda.synchronize()
         out = {}
-        for kind, flops, e0, e1, _ in self.items:
-            d = out.setdefault(kind, {"ms": 0.0, "flops": 0.0, "n": 0})
-            d["ms"] += e0.elapsed_time(e1); d["flops"] += flops; d["n"] += 1
+        for kind, flops, e0, e1, _, nbytes in self.items:
+            d = out.setdefault(kind, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
+            d["ms"] += e0.elapsed_time(e1); d["flops"] += flops; d["bytes"] += nbytes; d["n"] += 1
         return out
 
     def summarize_detail(self):
         """Same, keyed by the launch's shape string (GEMM: "N x K epilogue flags"; attention: heads x head_dim, bias)."""
         torch.cuda.synchronize()
         out = {}
-        for kind, flops, e0, e1, detail in self.items:
+        for kind, flops, e0, e1, detail, nbytes in self.items:
             if detail is None:
                 continue
-            d = out.setdefault(f"{kind} {detail}", {"ms": 0.0, "flops": 0.0, "n": 0})
-            d["ms"] += e0.elapsed_time(e1); d["flops"] += flops; d["n"] += 1
+            d = out.setdefault(f"{kind} {detail}", {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
+            d["ms"] += e0.elapsed_time(e1); d["flops"] += flops; d["bytes"] += nbytes; d["n"] += 1
         return out
 
 
 class _timed:
-    __slots__ = ("kind", "flops", "e0", "detail")
+    __slots__ = ("kind", "flops", "e0", "detail", "nbytes")
 
-    def __init__(self, kind, flops=0.0, detail=None):
-        self.kind, self.flops, self.e0, self.detail = kind, flops, None, detail
+    def __init__(self, kind, flops=0.0, detail=None, nbytes=0.0):
+        self.kind, self.flops, self.e0, self.detail, self.nbytes = kind, flops, None, detail, nbytes
 
     def __enter__(self):
         if PROFILER is not None:
@@ -67,7 +68,8 @@ class _timed:
         global LAUNCHES
         LAUNCHES += 1
         if self.e0 is not None and PROFILER is not None:
-            PROFILER.end(self.e0, self.kind, self.flops, self.detail() if callable(self.detail) else self.detail)
+            PROFILER.end(self.e0, self.kind, self.flops, self.detail() if callable(self.detail) else self.detail,
+                         self.nbytes)
         return False
 
 
@@ -118,7 +120,10 @@ def gemm(a, w, epilogue, bias=None, resid=None, out=None, out2=None, ln=None, st
             f"N={N} K={K} {_EPI_NAME[epilogue]}" + (" ln" if ln is not None else "") +
             ("" if resid is None else " resid16" if resid.dtype == torch.bfloat16 else " resid32") +
             (" out32" if out is not None and out.dtype == torch.float32 else "") + (" mirror" if out2 is not None else "") +
-            (" stats" if stats_out is not None else "") + (" M>=64k" if M >= 65536 else " M<64k"))):
+            (" stats" if stats_out is not None else "") + (" M>=64k" if M >= 65536 else " M<64k")),
+            nbytes=2.0 * M * K + 2.0 * N * K + 4.0 * N + (0 if resid is None else M * N * resid.element_size()) +
+            (0 if out is None else M * n_out * out.element_size()) + (0 if out2 is None else 2.0 * M * N) +
+            (0 if ln is None else 8.0 * M * ln_parts) + (0 if stats_out is None else 8.0 * M * stats_parts(N))):
         check(_lib.lib().vf_gemm_bf16_ln(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, epilogue, ptr(bias),
                                          ptr(resid), int(resid is not None and resid.dtype == torch.bfloat16),
                                          resid.stride(0) if resid is not None else 0, ptr(out),
@@ -242,7 +247,8 @@ def attention_mc(q, k, v, slots: SlotMap, heads, head_dim, slopes=None, out=None
     for r0, r1 in slots.keyless:
         out[r0:r1].zero_()
     with _timed("attention", 4.0 * slots.qk_pairs * heads * head_dim,
-                lambda: f"h={heads} hd={head_dim}{' alibi' if slopes is not None else ''} rows={q.shape[0]} keys={k.shape[0]}"):
+                lambda: f"h={heads} hd={head_dim}{' alibi' if slopes is not None else ''} rows={q.shape[0]} keys={k.shape[0]}",
+                nbytes=2.0 * heads * head_dim * (2 * q.shape[0] + 2 * k.shape[0])):
         check(_lib.lib().vf_attention_mc_varlen(ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0),
                                                 ptr(out), out.stride(0), q.shape[0], k.shape[0], ptr(slots.table),
                                                 slots.n_items, heads, head_dim, ptr(slopes), stream()))
@@ -296,12 +302,46 @@ def embed_tokens(ids, pos, emb, pe):
     return out
 
 
-def masked_meanpool(x, cu, n_win, want_f32=False):
+def center_rows(x, pivot=None, stats=None, out_bf16=None):
+    """x <- x - mean_r in place (fp32 [M,d]); -> (pivot fp32 [M], stats fp32 [M,1,2] of the shifted rows); optional
+    bf16 mirror.  The row-centred form of a residual stream (include/vf_b200.h: vf_center_rows)."""
+    assert x.dtype == torch.float32 and x.stride(1) == 1
+    M, d = x.shape
+    if pivot is None:
+        pivot = torch.empty(M, dtype=torch.float32, device=x.device)
+    if stats is None:
+        stats = torch.empty((M, 1, 2), dtype=torch.float32, device=x.device)
+    assert pivot.shape == (M,) and pivot.is_contiguous() and stats.shape == (M, 1, 2) and stats.is_contiguous()
+    if out_bf16 is not None:
+        assert out_bf16.dtype == torch.bfloat16 and out_bf16.shape == (M, d) and out_bf16.stride(1) == 1
+    with _timed("misc"):
+        check(_lib.lib().vf_center_rows(ptr(x), x.stride(0), M, d, ptr(pivot), ptr(stats), ptr(out_bf16),
+                                        out_bf16.stride(0) if out_bf16 is not None else 0, stream()))
+    return pivot, stats
+
+
+def uncenter_rows(x, pivot, idx=None, want_f32=True, want_bf16=False, out_bf16=None):
+    """out[r] = x[r] + pivot[idx[r] if idx is given else r]  ->  (fp32 or None, bf16 or None)."""
+    assert x.dtype == torch.float32 and x.stride(1) == 1 and pivot.dtype == torch.float32 and pivot.is_contiguous()
+    M, d = x.shape
+    assert idx is None or (idx.dtype == torch.int32 and idx.numel() == M)
+    of = torch.empty((M, d), dtype=torch.float32, device=x.device) if want_f32 else None
+    ob = out_bf16 if out_bf16 is not None else \
+        (torch.empty((M, d), dtype=torch.bfloat16, device=x.device) if want_bf16 else None)
+    if ob is not None:
+        assert ob.dtype == torch.bfloat16 and ob.shape == (M, d) and ob.is_contiguous()
+    with _timed("misc"):
+        check(_lib.lib().vf_uncenter_rows(ptr(x), x.stride(0), ptr(pivot), ptr(idx), M, d, ptr(of), ptr(ob), d, stream()))
+    return of, ob
+
+
+def masked_meanpool(x, cu, n_win, want_f32=False, pivot=None):
     d = x.shape[1]
     ob = torch.empty((n_win, d), dtype=torch.bfloat16, device=x.device)
     of = torch.empty((n_win, d), dtype=torch.float32, device=x.device) if want_f32 else None
     with _timed("misc"):
-        check(_lib.lib().vf_masked_meanpool(ptr(x), x.stride(0), ptr(cu), n_win, d, ptr(ob), ptr(of), d, stream()))
+        check(_lib.lib().vf_masked_meanpool(ptr(x), x.stride(0), ptr(cu), n_win, d, ptr(pivot), ptr(ob), ptr(of), d,
+                                            stream()))
     return (ob, of) if want_f32 else ob
 
 
@@ -340,7 +380,7 @@ def encode_windows(genome, win_base, w0, w1, var_lo, var_hi, flags, variants, ma
     out_len = torch.empty(n, dtype=torch.int32, device=genome.device)
     err = torch.zeros(1, dtype=torch.int32, device=genome.device)
     v = variants
-    with _timed("stage1_encode"):
+    with _timed("stage1_encode", nbytes=float(n) * max_window * 2):       # window bytes read + written (upper bound)
         check(_lib.lib().vf_encode_windows(ptr(genome), ptr(win_base), ptr(w0), ptr(w1), ptr(var_lo), ptr(var_hi),
                                            ptr(flags), ptr(v["pos"]), ptr(v["ref_len"]), ptr(v["alt_off"]),
                                            ptr(v["alt_len"]), ptr(v["gt"]), ptr(v["alt_pool"]), n, int(max_window),
@@ -359,7 +399,8 @@ def bpe_tokenize(seq, lens, max_len, merges, out_pitch, out_cap, want_starts=Fal
     threads = 128 if t <= 1024 else (256 if t <= 2048 else (512 if t <= 4096 else 1024))
     starts = torch.empty((n, max_len), dtype=torch.int32, device=dev) if want_starts else None
     a, b, c = merges
-    with _timed("stage1_bpe_cluster" if max_len > 8192 else "stage1_bpe"):
+    # algorithmic bytes: every sequence byte read once (typical length) + int32 tokens of the kept prefix written
+    with _timed("stage1_bpe_cluster" if max_len > 8192 else "stage1_bpe", nbytes=float(n) * (t + 4.0 * out_cap)):
         check(_lib.lib().vf_bpe_tokenize(ptr(seq), pitch, ptr(lens), n, int(max_len), ptr(a), ptr(b), ptr(c), a.numel(),
                                          ptr(scratch), int(max_len) if scratch is not None else 0, ptr(out), out_pitch,
                                          out_cap, ptr(cnt), ptr(starts), int(max_len) if want_starts else 0, threads,
