@@ -427,23 +427,47 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const uint32_t s_tmem = tmem_base + s * kKB, o_tmem = tmem_base + 128 + s * 64;
             const uint64_t q_desc = umma_desc_kmajor_sw128(sm_q + s * kQBytes);
             const uint64_t p_desc = umma_desc_kmajor_sw128(sm_p + s * kQBytes);
-            struct It { int nk0, nk1, my_nk, tail; uint32_t base, tile0; bool same; };   // tail: keys in the last block
+            // One work item as this issuer sees it, packed into four registers (the warpgroup runs on 32 registers per
+            // thread and every spill here is on the critical path of short sequences): key-block counts of both slots,
+            // own block count, keys in the own last block, flags, first ring position, first score tile.
+            struct It {
+                uint32_t nks, meta, base, tile0;
+                __device__ __forceinline__ int nk0() const { return (int)(nks & 0xFFFFu); }
+                __device__ __forceinline__ int nk1() const { return (int)(nks >> 16); }
+                __device__ __forceinline__ int my_nk() const { return (int)(meta & 0xFFFFu); }
+                __device__ __forceinline__ int tail() const { return (int)((meta >> 16) & 0xFFu); }
+                __device__ __forceinline__ bool same() const { return (meta >> 24) & 1u; }
+                __device__ __forceinline__ bool all_mine() const { return (meta >> 25) & 1u; }
+            };
+            bool skipped = false, prev_all_mine = false;
             uint32_t ring = 0, n_tiles = 0, n_q = 0, n_done = 0;      // ring position, score tiles / items started / finished
-            uint32_t seen_k = 0, seen_v = 0;                          // last values read from k_issued / v_issued
+            uint32_t run0 = 0xF0000000u;                              // see `issued` (no run yet)
             int w = blockIdx.x;
             // next work item in which this slot is occupied (the ring position advances over every item)
             auto next_valid = [&](It& it) -> bool {
                 for (; w < n_work; w += gridDim.x) {
                     const int item = w % p.n_items;
                     const int4 r0 = __ldg(recs + 4 * item), r1 = __ldg(recs + 4 * item + 2);
-                    it.nk0 = r0.y > 0 ? (r0.w + kKB - 1) / kKB : 0;
-                    it.nk1 = r1.y > 0 ? (r1.w + kKB - 1) / kKB : 0;
-                    it.same = it.nk0 > 0 && it.nk1 > 0 && r0.z == r1.z && r0.w == r1.w;
+                    const int nk0 = r0.y > 0 ? (r0.w + kKB - 1) / kKB : 0;
+                    const int nk1 = r1.y > 0 ? (r1.w + kKB - 1) / kKB : 0;
+                    const bool same = nk0 > 0 && nk1 > 0 && r0.z == r1.z && r0.w == r1.w;
                     it.base = ring;
-                    ring += it.same ? it.nk0 : it.nk0 + it.nk1;
-                    it.my_nk = s == 0 ? it.nk0 : it.nk1;
-                    it.tail = (s == 0 ? r0.w : r1.w) - (it.my_nk - 1) * kKB;
-                    if (it.my_nk > 0) { w += gridDim.x; return true; }
+                    ring += same ? nk0 : nk0 + nk1;
+                    const int my_nk = s == 0 ? nk0 : nk1;
+                    const int tail = (s == 0 ? r0.w : r1.w) - (my_nk - 1) * kKB;      // keys in the own last block (1..64)
+                    // does this issuer consume every ring position of the item?  (shared stream, or the only occupied slot)
+                    const bool all_mine = my_nk > 0 && (same || (s == 0 ? nk1 : nk0) == 0);
+                    it.nks = (uint32_t)nk0 | ((uint32_t)nk1 << 16);
+                    it.meta = (uint32_t)my_nk | ((uint32_t)(tail & 0xFF) << 16) | ((uint32_t)same << 24) | ((uint32_t)all_mine << 25);
+                    if (my_nk > 0) {
+                        // a run continues only from an item consumed in full, with no item skipped in between
+                        if (!all_mine) run0 = 0xF0000000u;
+                        else if (!prev_all_mine || skipped) run0 = it.base;
+                        prev_all_mine = all_mine; skipped = false;
+                        w += gridDim.x;
+                        return true;
+                    }
+                    skipped = true;                                   // ring positions pass by that this issuer never sees
                 }
                 return false;
             };
@@ -453,23 +477,28 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 // must never disagree on whether the early Q K^T went out
                 return __shfl_sync(0xffffffffu, (int)mbar_test_wait(bar, parity), 0) != 0;
             };
-            // has the producer issued block idx of a ring?  (one lane's answer for the warp, as above)
-            auto issued = [&](uint32_t ctr, uint32_t& seen, uint32_t idx, bool blocking) -> bool {
-                if (seen > idx) return true;
+            // Has the producer issued block idx of a ring?  Needed only when this issuer did not consume the stage's
+            // previous use itself (idx - stages): `run0` is the ring position from which it has consumed EVERY block
+            // (shared streams of items in which its slot is occupied), so inside such a run no check is made at all.
+            // Blocking mode: every lane polls for itself (each one's own later parity test is then sound); non-blocking
+            // mode: one lane's answer for the warp, the lanes must agree on whether the early Q K^T went out.
+            auto issued = [&](uint32_t ctr, uint32_t idx, uint32_t stages, bool blocking) -> bool {
+#ifdef VF_ATTN_NO_ISSUED_CHECK                                         // A/B timing only: NOT safe (see lds_acquire)
+                return true;
+#endif
+                if (idx >= run0 + stages) return true;
+                if (!blocking) return __shfl_sync(0xffffffffu, lds_acquire(ctr), 0) > idx;
                 uint32_t spins = 0;
-                do {
-                    seen = __shfl_sync(0xffffffffu, lds_acquire(ctr), 0);
-                    if (!blocking) break;
-                    if ((++spins & 0xFFFFFFu) == 0 && seen <= idx) __trap();      // ~seconds: a pipeline bug, never a wait
-                } while (seen <= idx);
-                return seen > idx;
+                while (lds_acquire(ctr) <= idx)
+                    if ((++spins & 0xFFFFFFu) == 0) __trap();                     // ~seconds: a pipeline bug, never a wait
+                return true;
             };
             // S(j) = Q K(j)^T of item `it`; non-blocking mode gives up (nothing issued) if an input has not landed yet
             auto issue_qk = [&](It& it, int j, bool blocking) -> bool {
-                const uint32_t idx = it.base + ring_offset(j, s, it.same, it.nk0, it.nk1);
+                const uint32_t idx = it.base + ring_offset(j, s, it.same(), it.nk0(), it.nk1());
                 const uint32_t st = idx % kKStages;
                 if (j == 0 && !ready(q_full[s], n_q & 1, blocking)) return false;
-                if (!issued(k_issued, seen_k, idx, blocking)) return false;
+                if (!issued(k_issued, idx, kKStages, blocking)) return false;
                 if (!ready(k_full[st], (idx / kKStages) & 1, blocking)) return false;
                 if (!ready(s_empty[s], (n_tiles & 1) ^ 1, blocking)) return false;      // previous scores are in registers
                 if (j == 0) { ++n_q; it.tile0 = n_tiles; }
@@ -481,8 +510,8 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     for (int k = 0; k < HD / 16; ++k) umma_bf16(s_tmem, q_desc + 2 * k, db + 2 * k, idesc_qk, k != 0);
                     umma_commit(s_full[s]);
                     umma_commit(k_empty[2 * st + s]);
-                    if (!it.same) umma_commit(k_empty[2 * st + (s ^ 1)]);    // sole user: the other slot's release too
-                    if (j + 1 == it.my_nk) umma_commit(q_empty[s]);          // last Q K^T of the item: Q slot may be refilled
+                    if (!it.same()) umma_commit(k_empty[2 * st + (s ^ 1)]);    // sole user: the other slot's release too
+                    if (j + 1 == it.my_nk()) umma_commit(q_empty[s]);          // last Q K^T of the item: Q slot may be refilled
                 }
                 __syncwarp();
                 return true;
@@ -493,35 +522,39 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             while (have) {
                 const bool have_next = next_valid(nxt);
                 bool next_started = false;
-                for (int j = 0; j < cur.my_nk; ++j) {
+                for (int j = 0; j < cur.my_nk(); ++j) {
                     // S(j+1) is issued as soon as the four softmax warps have S(j) in registers, i.e. BEFORE waiting for
                     // P(j).  At the last block the first score tile of the NEXT item goes out instead — but only if its
                     // inputs have already landed: blocking on them here could deadlock (the producer may need the V
                     // block this slot is about to release before it can reach the next item's loads).
-                    if (j + 1 < cur.my_nk) issue_qk(cur, j + 1, true);
+                    if (j + 1 < cur.my_nk()) issue_qk(cur, j + 1, true);
                     else if (have_next) next_started = issue_qk(nxt, 0, false);
                     // ---- O += P(j) V(j) ----
-                    const uint32_t idx = cur.base + ring_offset(j, s, cur.same, cur.nk0, cur.nk1);
+                    const uint32_t idx = cur.base + ring_offset(j, s, cur.same(), cur.nk0(), cur.nk1());
                     const uint32_t st = idx % kVStages;
                     if (j == 0) mbar_wait(o_empty[s], (n_done & 1) ^ 1);   // previous item's O has been read out
-                    issued(v_issued, seen_v, idx, true);
+                    issued(v_issued, idx, kVStages, true);
                     mbar_wait(v_full[st], (idx / kVStages) & 1);
                     const uint32_t vb = sm_v + st * kKvBytes;
                     int nkk = kKB / 16;                          // 16-key steps of this block's P V
-                    if (j + 1 == cur.my_nk && cur.tail < kKB) {
+#ifndef VF_ATTN_NO_VTAIL                                               // A/B timing only
+                    if (j + 1 == cur.my_nk() && cur.tail() < kKB) {
                         // The last block of a sequence over-fetches rows of whatever follows it in the K/V tensors.  Their
                         // probabilities are exactly 0, but 0 x NaN/Inf would still poison O.  Whole 16-key groups past the
                         // last key are not multiplied at all; in the partial group the V rows past the end are cleared
                         // (a row of the [64 keys x 64] SWIZZLE_128B tile is 128 contiguous bytes; at most 15 rows).  Both
                         // issuers of a shared stream write the same zeros.
-                        nkk = (cur.tail + 15) >> 4;
-                        if (cur.tail & 15) {
-                            for (int r = cur.tail + (lane >> 3); r < nkk * 16; r += 4)
+                        nkk = (cur.tail() + 15) >> 4;
+                        if (cur.tail() & 15) {
+                            for (int r = cur.tail() + (lane >> 3); r < nkk * 16; r += 4)
                                 asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(vb + r * 128 + (lane & 7) * 16), "r"(0u) : "memory");
+#ifndef VF_ATTN_VTAIL_NOFENCE                                          // A/B timing only
                             fence_proxy_async_smem();
+#endif
                             __syncwarp();
                         }
                     }
+#endif
                     mbar_wait(p_full[s], (cur.tile0 + j) & 1);
                     tc_fence_after();
                     if (elect_one()) {
@@ -529,8 +562,8 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                             umma_bf16(o_tmem, p_desc + 2 * kk, umma_desc_kmajor_sw128(vb + kk * 2048), idesc_pv, (j | kk) != 0);
                         umma_commit(p_empty[s]);
                         umma_commit(v_empty[2 * st + s]);
-                        if (!cur.same) umma_commit(v_empty[2 * st + (s ^ 1)]);
-                        if (j + 1 == cur.my_nk) umma_commit(o_full[s]);
+                        if (!cur.same()) umma_commit(v_empty[2 * st + (s ^ 1)]);
+                        if (j + 1 == cur.my_nk()) umma_commit(o_full[s]);
                     }
                     __syncwarp();
                 }

@@ -152,10 +152,31 @@ class Seq2RegWeights:
         self.layers = []
         for l in range(self.L):
             p = f"{prefix}transformer_encoder.{l}."
-            self.layers.append(dict(
-                qkv=_LnLinear(sd, p + "MHA.Wqkv", p + "norm1", device), out=_Linear(sd, p + "MHA.out_proj", device),
+            self.layers.append(seq2reg_layer_weights(sd, p, device))
+
+
+def seq2reg_layer_weights(sd, p, device):
+    """Device weights of one FlashTransformerLayer (seq2reg/modules.py:129-147), LayerNorms folded."""
+    return dict(qkv=_LnLinear(sd, p + "MHA.Wqkv", p + "norm1", device), out=_Linear(sd, p + "MHA.out_proj", device),
                 g1=_LnLinear(sd, p + "linear_geglu_1", p + "norm2", device, geglu=True),
-                g2=_Linear(sd, p + "linear_geglu_2", device)))
+                g2=_Linear(sd, p + "linear_geglu_2", device))
+
+
+def context_layer_weights(sd, p, device, emb9=None):
+    """Device weights of one ContextFlashAttentionEncoderLayer (layers.py:47-86), LayerNorms folded.  emb9 (bf16 [9, D],
+    the label embedding table): the layer's cross-attention context is a label embedding, so K/V of the 9 classes are
+    computed once here (weights only) and `kv` is dropped."""
+    L = dict(qkv=_LnLinear(sd, p + "mixer.MHA.Wqkv", p + "norm1", device),
+             out=_Linear(sd, p + "mixer.MHA.out_proj", device),
+             q=_LnLinear(sd, p + "crossMHA.MHA.Wq", p + "norm2", device),
+             kv=_Linear(sd, p + "crossMHA.MHA.Wkv", device),
+             out2=_Linear(sd, p + "crossMHA.MHA.out_proj", device),
+             g1=_LnLinear(sd, p + "linear_geglu_1", p + "norm3", device, geglu=True),
+             g2=_Linear(sd, p + "linear_geglu_2", device))
+    if emb9 is not None:
+        L["kv9"] = ops.gemm(emb9.contiguous(), L["kv"].w, EPI_BIAS_F32, bias=L["kv"].b)
+        L["kv"] = None
+    return L
 
 
 class Seq2GeneWeights:
@@ -174,18 +195,7 @@ class Seq2GeneWeights:
         emb9 = sd["combined_modulator.second_level_context_embedding.weight"].to(device=device, dtype=torch.bfloat16)
 
         def layer(p, with_kv9):
-            L = dict(qkv=_LnLinear(sd, p + "mixer.MHA.Wqkv", p + "norm1", device),
-                     out=_Linear(sd, p + "mixer.MHA.out_proj", device),
-                     q=_LnLinear(sd, p + "crossMHA.MHA.Wq", p + "norm2", device),
-                     kv=_Linear(sd, p + "crossMHA.MHA.Wkv", device),
-                     out2=_Linear(sd, p + "crossMHA.MHA.out_proj", device),
-                     g1=_LnLinear(sd, p + "linear_geglu_1", p + "norm3", device, geglu=True),
-                     g2=_Linear(sd, p + "linear_geglu_2", device))
-            if with_kv9:
-                # K/V of the 9 label embeddings depend on weights only: computed once here with the same GEMM
-                L["kv9"] = ops.gemm(emb9.contiguous(), L["kv"].w, EPI_BIAS_F32, bias=L["kv"].b)
-                L["kv"] = None
-            return L
+            return context_layer_weights(sd, p, device, emb9 if with_kv9 else None)
 
         self.cre_layers = [layer(f"combined_modulator.cre_layers.{i}.", True) for i in range(self.NL - 1)]
         self.gene_layers = [layer(f"combined_modulator.gene_layers.{i}.", False) for i in range(self.NL)]
