@@ -1,0 +1,126 @@
+"""Layer-level API of the mirror classes (the module forward signatures) on the GPU box: each class's
+`forward`, called the way the reference calls it, against the fp32 oracle's restatement of the same layer."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import model_fp32 as O  # noqa: E402  (checker only)
+from tests.common import parity_report  # noqa: E402
+from variantformer_b200.utils import random_init  # noqa: E402
+
+CFG = dict(random_init.V4_PCG_MODEL, emb_dim=384, gene_emb_dim=256, num_heads=8, num_layers=3, token_dim=256)
+HP = dict(random_init.SEQ2REG_HP, embedding_dim=256, num_heads=4, num_layers=2)
+DEV = "cuda"
+
+
+def _sub(sd, prefix):
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+def _ok(got, want, what):
+    rep = parity_report(got.float().cpu().numpy(), want.numpy())
+    assert rep["ok"], (what, rep)
+
+
+def test_flash_transformer_layer_forward():
+    from variantformer_b200.seq2reg.modules import FlashTransformerLayer
+    sd = random_init.make_state_dict(CFG, HP, seed=11)
+    p = "cre_tokenizer.transformer_encoder.1."
+    layer = FlashTransformerLayer(HP["embedding_dim"], HP["num_heads"]).to(DEV)
+    layer.load_state_dict(_sub(sd, p))
+    g = torch.Generator().manual_seed(0)
+    B, S, d = 5, 200, HP["embedding_dim"]
+    src = torch.randn(B, S, d, generator=g)
+    lens = [200, 97, 1, 130, 64]
+    mask = torch.arange(S)[None, :] >= torch.tensor(lens)[:, None]               # True = padding
+    out = layer(src.to(DEV), src_key_padding_mask=mask.to(DEV))
+    assert out.shape == (B, S, d)
+    num = O._Num()
+    x = src[~mask]
+    cu = [0] + np.cumsum(lens).tolist()
+    a = O._mha_self(num, sd, p + "MHA.", O._ln(sd, p + "norm1.", x), cu, HP["num_heads"], None)
+    x1 = a + x
+    want = O._geglu_ffn(num, sd, p, O._ln(sd, p + "norm2.", x1)) + x
+    _ok(out[~mask.to(DEV)], want, "FlashTransformerLayer")
+    assert bool((out[mask.to(DEV)] == 0).all())
+    # no mask: every position valid
+    out2 = layer(src[:2].to(DEV))
+    a = O._mha_self(num, sd, p + "MHA.", O._ln(sd, p + "norm1.", src[:2].reshape(-1, d)), [0, S, 2 * S], HP["num_heads"], None)
+    x1 = a + src[:2].reshape(-1, d)
+    want2 = O._geglu_ffn(num, sd, p, O._ln(sd, p + "norm2.", x1)) + src[:2].reshape(-1, d)
+    _ok(out2.reshape(-1, d), want2, "FlashTransformerLayer (no mask)")
+
+
+def test_context_encoder_layer_forward_padded_and_unpadded():
+    from variantformer_b200.seq2gene.modules.layers import ContextFlashAttentionEncoderLayer
+    sd = random_init.make_state_dict(CFG, HP, seed=12)
+    p = "combined_modulator.gene_layers.1."
+    D, H = CFG["emb_dim"], CFG["num_heads"]
+    layer = ContextFlashAttentionEncoderLayer(D, H, use_alibi=True).to(DEV)
+    layer.load_state_dict(_sub(sd, p))
+    g = torch.Generator().manual_seed(1)
+    q_lens, k_lens = [201, 40, 130], [300, 64, 9]
+    B, S, Sc = 3, 201, 300
+    src = torch.randn(B, S, D, generator=g); ctx = torch.randn(B, Sc, D, generator=g)
+    qmask = torch.arange(S)[None, :] >= torch.tensor(q_lens)[:, None]
+    kmask = torch.arange(Sc)[None, :] >= torch.tensor(k_lens)[:, None]
+    cu_q = [0] + np.cumsum(q_lens).tolist(); cu_k = [0] + np.cumsum(k_lens).tolist()
+    want = O._context_layer(O._Num(), sd, p, src[~qmask], cu_q, ctx[~kmask], cu_k, H, O.alibi_slopes(H))
+    out = layer(src.to(DEV), ctx.to(DEV), src_key_padding_mask=qmask.to(DEV), context_padding_mask=kmask.to(DEV))
+    assert out.shape == (B, S, D)
+    _ok(out[~qmask.to(DEV)], want, "ContextFlashAttentionEncoderLayer (padded)")
+    # unpadded mode, the way CombinedModulator.forward calls its layers (gene_unpad_info / context_unpad_info)
+    info = lambda cu, m: {"cu_seqlens": torch.tensor(cu, dtype=torch.int32, device=DEV), "max_seqlen": m}
+    out_u = layer(src[~qmask].to(DEV), ctx[~kmask].to(DEV), gene_unpad_info=info(cu_q, S), context_unpad_info=info(cu_k, Sc))
+    assert out_u.shape == (sum(q_lens), D)
+    assert torch.equal(out_u, out[~qmask.to(DEV)])                                # same kernels, same rows: bit-identical
+
+
+def test_tissue_expression_heads_forward():
+    from variantformer_b200.seq2gene.modules.layers import TissueExpressionHeads
+    sd = random_init.make_state_dict(CFG, HP, seed=13)
+    head = TissueExpressionHeads(CFG["emb_dim"], 63, use_bigger_head=True, multi_head=False).to(DEV)
+    head.load_state_dict(_sub(sd, "tissue_heads."))
+    g = torch.Generator().manual_seed(2)
+    e = torch.randn(37, CFG["emb_dim"], generator=g)
+    tv = torch.randint(0, 63, (37, 1), generator=g)
+    out = head(e.to(DEV), tv.to(DEV))
+    want = O.head(O._Num(), sd, e)
+    assert out.shape == (37, 1)
+    assert torch.allclose(out.cpu(), want, atol=2e-2, rtol=2e-2)
+    with pytest.raises(AssertionError, match="not unique"):
+        head(e[:2].to(DEV), torch.tensor([[1, 2], [3, 3]]))
+
+
+def test_combined_modulator_forward():
+    """CombinedModulator.forward with the reference's signature on a padded batch (one row per (gene, tissue) copy, the
+    CRE stream repeated per copy as prepare_input does) against the oracle's layer loop."""
+    from variantformer_b200.seq2gene.model_combined_modulator import CombinedModulator
+    cfg = dict(CFG, num_layers=2)
+    sd = random_init.make_state_dict(cfg, HP, seed=14)
+    D, H = cfg["emb_dim"], cfg["num_heads"]
+    mod = CombinedModulator(D, H, 2, True, 0.0, True, num_ref_cres=9, only_cross_attention=False).to(DEV)
+    mod.load_state_dict(_sub(sd, "combined_modulator."))
+    g = torch.Generator().manual_seed(3)
+    B, Sc, Sg = 2, 150, 41
+    c_lens, g_lens = [150, 33], [41, 12]
+    cre = torch.randn(B, Sc, D, generator=g); gene = torch.randn(B, Sg, D, generator=g)
+    labels = torch.randint(0, 9, (B, Sc), generator=g)
+    cmask = torch.arange(Sc)[None, :] >= torch.tensor(c_lens)[:, None]
+    gmask = torch.arange(Sg)[None, :] >= torch.tensor(g_lens)[:, None]
+    gpos = torch.tensor([[5], [0]]); cpos = torch.tensor([[149], [7]])
+    out, gtok, ctok = mod(cre.to(DEV), gene.to(DEV), context=labels.to(DEV), cre_padding_mask=cmask.to(DEV),
+                          gene_padding_mask=gmask.to(DEV), context_padding_mask=cmask.to(DEV),
+                          cre_token_position=cpos.to(DEV), gene_token_position=gpos.to(DEV))
+    num, slopes = O._Num(), O.alibi_slopes(H)
+    cu_c = [0] + np.cumsum(c_lens).tolist(); cu_g = [0] + np.cumsum(g_lens).tolist()
+    cx, gx = cre[~cmask], gene[~gmask]
+    lab = sd["combined_modulator.second_level_context_embedding.weight"][labels[~cmask]]
+    gx = O._context_layer(num, sd, "combined_modulator.gene_layers.0.", gx, cu_g, cx, cu_c, H, slopes)
+    cx = O._context_layer(num, sd, "combined_modulator.cre_layers.0.", cx, cu_c, lab, cu_c, H, slopes)
+    gx = O._context_layer(num, sd, "combined_modulator.gene_layers.1.", gx, cu_g, cx, cu_c, H, slopes)
+    _ok(out[~gmask.to(DEV)], gx, "CombinedModulator gene output")
+    _ok(gtok, torch.stack([gx[cu_g[0] + 5], gx[cu_g[1] + 0]]), "gene token embedding")
+    _ok(ctok, torch.stack([cx[cu_c[0] + 149], cx[cu_c[1] + 7]]), "cre token embedding")

@@ -292,7 +292,16 @@ def test_variantprocessor_surface(tmp_path):
     assert np.isfinite(hit["gene_exp"]).all() and hit["gene_emb"].iloc[0].shape == (CFG["emb_dim"],)
     miss = out[out["pos"] == 5]
     assert (miss["variant_type"] == "No overlap").all() and miss["gene_exp"].isna().all()
-    scores = VariantProcessor.format_scores(hit)
-    assert {"log2fc_1", "log2fc_2"} <= set(scores.columns) and np.isfinite(scores["log2fc_2"]).all()
+    wide = vp.format_scores(out)                                   # the reference's pivot (:454-497): misses are dropped
+    assert len(wide) == 2 and {"REF_HG38-0-exp", "REF_HG38-1-exp", "REF_HG38-2-exp"} <= set(wide.columns)
+    # no SAMPLE column -> the population aggregate needs the 1KG allele-frequency table of the chromosome
+    af_dir = tmp_path / "_artifacts" / "1KG_af_hg38_tables"
+    os.makedirs(af_dir, exist_ok=True)
+    pd.DataFrame({"chr": ["chr1"], "pos": [pos0 + 1], "ref": [ref], "alt": [alt], "AF_EUR": [0.1], "AF_AFR": ["."],
+                  "AF_EAS": [0.2], "AF_SAS": [0.0], "AF_AMR": [0.3]}).to_csv(af_dir / "1KG_hg38_af_chr1.tsv", sep="\t", index=False)
+    scores = vp.eqtl_scores(wide)
+    assert "VF-REF_HG38-2-exp-log2fc" in scores.columns and np.isfinite(scores["VF-REF_HG38-2-exp-log2fc"]).all()
+    want = np.log2((wide["REF_HG38-2-exp"] + 1e-10) / (wide["REF_HG38-0-exp"] + 1e-10))
+    assert np.allclose(scores["VF-REF_HG38-2-exp-log2fc"], want)
     with pytest.raises(FileExistsError):
         vp.predict(var_df, str(tmp_path / "out"))               # refuses to overwrite, like the reference

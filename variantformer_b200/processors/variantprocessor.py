@@ -44,7 +44,8 @@ class VariantProcessor:
         def fix(node, key):
             if node.get(key) and not os.path.isabs(node[key]):
                 node[key] = os.path.join(base_dir, node[key])
-        fix(self.vep_loader_config, "fasta_path"); fix(self.model_config.dataset, "gencode_v24")
+        fix(self.vep_loader_config, "fasta_path"); fix(self.vep_loader_config, "af_path")
+        fix(self.model_config.dataset, "gencode_v24")
         fix(self.model_config.model, "checkpoint_path")
         fix(self.model_config.model.cre_tokenizer, "path"); fix(self.model_config.model.gene_tokenizer, "path")
         assert torch.cuda.is_available(), "GPU is not available"
@@ -123,11 +124,21 @@ class VariantProcessor:
                         D[key].append(None if empty else pred[src][k][ti])
         return pd.DataFrame(D)
 
-    @staticmethod
-    def format_scores(df):
-        """log2 fold change of het / hom vs ref per (variant, gene, tissue) (utils/functions.py:251-301 core formula)."""
-        key = ["chrom", "pos", "ref", "alt", "genes", "tissues"]
-        wide = df.pivot_table(index=key, columns="zygosity", values="gene_exp", aggfunc="first").reset_index()
-        for z in ("1", "2"):
-            wide[f"log2fc_{z}"] = np.log2(wide[z] / wide["0"])
-        return wide
+    def format_scores(self, df: pd.DataFrame):
+        """Long -> wide (processors/variantprocessor.py:454-497): one row per (variant, gene, tissue) with one expression
+        column per `<population>-<zygosity>-exp`; rows without a reference prediction are dropped."""
+        df = df.copy()
+        df["variant_id"] = df[["chrom", "pos", "ref", "alt"]].astype(str).agg("_".join, axis=1)
+        df["gt-exp"] = df["population"] + "-" + df["zygosity"] + "-exp"
+        df = df.rename(columns={"chrom": "chr"})
+        idx = ["variant_id", "genes", "tissues", "chr", "pos", "ref", "alt", "variant_type"]
+        wide = (df[idx + ["gt-exp", "gene_exp"]]
+                .drop_duplicates(subset=["variant_id", "genes", "tissues", "variant_type", "gt-exp"], keep="first")
+                .pivot(index=idx, columns="gt-exp", values="gene_exp").reset_index())
+        wide.columns.name = None
+        return wide.dropna(subset=["REF_HG38-0-exp"]).reset_index(drop=True)
+
+    def eqtl_scores(self, df: pd.DataFrame):
+        """log2 fold-change scores of the wide table (processors/variantprocessor.py:447-452 -> utils/functions.py:250-301)."""
+        from ..utils.functions import generate_log2fc_score
+        return generate_log2fc_score(df, self.vep_loader_config.af_path)

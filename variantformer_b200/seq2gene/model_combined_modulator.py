@@ -38,6 +38,18 @@ class CombinedModulator(nn.Module):
         self.cre_layers = nn.ModuleList([mk() for _ in range(num_layers - 1)])
         self.gene_layers = nn.ModuleList([mk() for _ in range(num_layers)])
 
+    @torch.no_grad()
+    def forward(self, cre_x, gene_x, context=None, cre_padding_mask=None, gene_padding_mask=None,
+                context_padding_mask=None, precision=None, cre_token_position=None, gene_token_position=None):
+        """model_combined_modulator.py:137-148: cre_x [batch, cre_seq_len, emb_dim], gene_x [batch, gene_seq_len, emb_dim],
+        context int [batch, cre_seq_len] (reference cCRE labels), masks True = padding -> (gene_output [batch,
+        gene_seq_len, emb_dim], gene_token_embedding, cre_token_embedding).  Layer by layer through the layers' own
+        forwards; the batched engine (Seq2GenePredictorCombinedModulator.forward) is the fast path."""
+        from ..layer_ops import combined_modulator_forward
+        assert context is not None, "context (reference cCRE labels) is required when use_context is True"
+        return combined_modulator_forward(self, cre_x, gene_x, context, cre_padding_mask, gene_padding_mask,
+                                          context_padding_mask, cre_token_position, gene_token_position)
+
 
 class Seq2GenePredictorCombinedModulator(nn.Module):
     def __init__(self, num_tissues: int, emb_dim: int, gene_emb_dim: int, num_heads: int, num_layers: int,

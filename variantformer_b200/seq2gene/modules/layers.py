@@ -1,5 +1,6 @@
-"""seq2gene layer containers (parameter layout of the reference's seq2gene/modules/layers.py:47-86, :502-524,
-:1012-1111).  Execution: Engine._layer / Engine.run."""
+"""seq2gene layers (parameter layout of the reference's seq2gene/modules/layers.py:47-86, :502-524, :1012-1111; forward
+signatures :88-98, :1113).  The batched path executes them inside Engine._layer / Engine.run; the `forward` methods
+serve callers of the reference's layer-level API through the same kernels (variantformer_b200/layer_ops.py)."""
 import torch
 import torch.nn as nn
 
@@ -25,6 +26,23 @@ class ContextFlashAttentionEncoderLayer(nn.Module):
         self.use_alibi, self.num_heads = use_alibi, nhead
         if use_alibi:
             self.register_buffer("m", alibi_slopes(nhead))          # persistent, like the reference (unused in forward)
+        self._folded = None
+
+    @torch.no_grad()
+    def forward(self, src, context, src_key_padding_mask=None, context_padding_mask=None, precision=torch.float32,
+                unpad_info=None, context_unpad_info=None, gene_unpad_info=None):
+        """layers.py:88-98.  Padded mode: src [B, S, D], context [B, Sc, D], masks True = padding.  Unpadded mode:
+        src [rows, D] / context [rows_c, D] with `unpad_info` (or `gene_unpad_info`) / `context_unpad_info` dicts holding
+        `cu_seqlens`.  `precision` is accepted for signature parity (bf16 operands, fp32 accumulation)."""
+        from ... import layer_ops as LO
+        if self._folded is None:
+            self._folded = (LO._Cache(), LO.Workspace(src.device))
+        cache, ws = self._folded
+        L = cache.get(self, lambda sd, dev: LO.context_layer_weights(sd, "", dev))
+        D = self.norm1.weight.shape[0]
+        slopes = alibi_slopes(self.num_heads).to(src.device) if self.use_alibi else None
+        return LO.context_layer_forward(L, ws, D, self.num_heads, slopes, src, context, src_key_padding_mask,
+                                        context_padding_mask, unpad_info, context_unpad_info, gene_unpad_info)
 
 
 class MultiRegistry(nn.Module):
@@ -50,3 +68,16 @@ class TissueExpressionHeads(nn.Module):
         self.multi_head = multi_head
         self.tissue_expressions = nn.ModuleDict({"0": Affine(emb_dim, emb_dim), "1": Affine(emb_dim),
                                                  "4": Affine(emb_dim, emb_dim), "6": Affine(1, emb_dim)})
+        self._folded = None
+
+    @torch.no_grad()
+    def forward(self, g_exp, tissue_vector):
+        """layers.py:1113-1144: g_exp [batch, emb_dim], tissue_vector [batch, 1] -> predictions [batch, 1].  With the
+        shared head every row runs the same MLP; tissue_vector is checked like upstream (one unique id per row)."""
+        from ... import layer_ops as LO
+        tv = torch.as_tensor(tissue_vector).reshape(g_exp.shape[0], -1)
+        assert bool((tv == tv[:, :1]).all()), "Tissue vector not unique"
+        if self._folded is None:
+            self._folded = LO._Cache()
+        W = self._folded.get(self, lambda sd, dev: LO.head_weights(sd, dev))
+        return LO.head_forward(W, g_exp)
