@@ -171,7 +171,10 @@ int vf_encode_windows(const uint8_t* genome, const int64_t* win_base, const int3
                       int32_t* err, void* stream);
 /*
  * BPE tokenisation of n_win byte sequences (upper-cased; non-IUPAC characters split words).
- * merge_a/merge_b/merge_new: uint16 [n_merges] rank-ordered merge table.  out_tokens int32 [n_win, out_pitch]:
+ * merge_a/merge_b/merge_new: uint16 [n_merges] rank-ordered merge table.  merge_batch: uint16 [n_merges] nondecreasing
+ * batch ids, or NULL: consecutive ranks with one id are applied in a single sweep with a single barrier — legal when
+ * their {left, right, new} symbol sets are pairwise disjoint and none is a self pair (such merges commute);
+ * at most 16 ranks per batch; NULL = every rank alone (same tokens, three times the barriers).  out_tokens int32 [n_win, out_pitch]:
  * the first min(count, out_cap) ids, remainder of the row zero (<pad>); out_count int32 [n_win] = untruncated
  * token count; out_start (optional) int32 [n_win, start_pitch] = first base index of every token.
  * Windows longer than 8192 symbols run on the cluster/DSMEM kernel (8 CTAs per window); scratch is unused there.
@@ -180,8 +183,8 @@ int vf_encode_windows(const uint8_t* genome, const int64_t* win_base, const int3
  * pad/truncate/chunk steps datasets/vcfdataset.py:198-217, :338-394.
  */
 int vf_bpe_tokenize(const uint8_t* seq, int64_t pitch, const int32_t* len, int n_win, int max_len,
-                    const uint16_t* merge_a, const uint16_t* merge_b, const uint16_t* merge_new, int n_merges,
-                    uint16_t* scratch, int64_t scratch_pitch, int32_t* out_tokens, int out_pitch, int out_cap,
+                    const uint16_t* merge_a, const uint16_t* merge_b, const uint16_t* merge_new,
+                    const uint16_t* merge_batch, int n_merges, uint16_t* scratch, int64_t scratch_pitch, int32_t* out_tokens, int out_pitch, int out_cap,
                     int32_t* out_count, int32_t* out_start, int64_t start_pitch, int block_threads, void* stream);
 
 #ifdef __cplusplus

@@ -46,6 +46,38 @@ def test_bpe_golden_vectors_bit_exact():
             assert (starts[k, :len(want)] == st).all(), f"seq {i} token starts differ"
 
 
+def test_bpe_rank_batches_do_not_change_a_single_token():
+    """Applying the ranks of a batch (pairwise disjoint symbol sets, no self pair) in one sweep must give exactly the
+    tokens of the rank-by-rank sweeps: golden sequences, homopolymer / repeat-rich words, and 301 kb windows through
+    the cluster kernel, batched vs unbatched (merge_batch = NULL) vs the oracle."""
+    from variantformer_b200.stage1 import load_merge_table, merge_batches
+    tk = WindowTokenizer(DEV)
+    a, b, c, _ = load_merge_table()
+    bid = merge_batches(a, b, c)
+    assert len(np.unique(bid)) < 200 and (np.diff(bid.astype(int)) >= 0).all() and np.bincount(bid).max() <= 16
+    for k in np.unique(bid):                                    # the property the kernel relies on
+        rs = np.nonzero(bid == k)[0]
+        syms = [s for r in rs for s in (int(a[r]), int(b[r]), int(c[r]))]
+        assert len(rs) == 1 or (len(set(syms)) == len(syms)), f"batch {k} is not symbol-disjoint"
+        assert len(rs) == 1 or all(a[r] != b[r] for r in rs)
+    rng = np.random.default_rng(17)
+    words = [str(s) for s in G["seqs"]][:60]
+    words += ["".join(rng.choice(list("ACGT"), n, p=[0.4, 0.1, 0.1, 0.4])) for n in (500, 4000, 8000)]
+    words += ["A" * 700 + "ACGT" * 300 + "T" * 513 + "CA" * 400, "".join(rng.choice(list("ACGTRYN"), 3000))]
+    long_words = ["".join(rng.choice(list("ACGT"), 301_000)), "AC" * 60_000 + "".join(rng.choice(list("ACGTN"), 150_000)) + "T" * 31_000]
+    bpe = O.OracleBPE()
+    for group in (words, long_words):
+        buf, lens, mx = _pack(group)
+        cap = mx
+        t1, c1 = ops.bpe_tokenize(buf, lens, mx, tk.merges, cap, cap)
+        t0, c0 = ops.bpe_tokenize(buf, lens, mx, tk.merges[:3], cap, cap)
+        torch.cuda.synchronize()
+        assert torch.equal(c0, c1) and torch.equal(t0, t1)
+        for i, w in enumerate(group):
+            want = bpe.encode(w)
+            assert int(c1[i]) == len(want) and (t1[i, :len(want)].cpu().numpy() == want).all()
+
+
 def test_bpe_fixed_and_chunked_shapes():
     tk = WindowTokenizer(DEV)
     rng = np.random.default_rng(5)

@@ -108,10 +108,10 @@ int vf_encode_windows(const uint8_t* genome, const int64_t* win_base, const int3
                           v_gt, alt_pool, n_win, max_window, out, pitch, out_len, err, ST(stream));
 }
 int vf_bpe_tokenize(const uint8_t* seq, int64_t pitch, const int32_t* len, int n_win, int max_len,
-                    const uint16_t* merge_a, const uint16_t* merge_b, const uint16_t* merge_new, int n_merges,
-                    uint16_t* scratch, int64_t scratch_pitch, int32_t* out_tokens, int out_pitch, int out_cap,
+                    const uint16_t* merge_a, const uint16_t* merge_b, const uint16_t* merge_new,
+                    const uint16_t* merge_batch, int n_merges, uint16_t* scratch, int64_t scratch_pitch, int32_t* out_tokens, int out_pitch, int out_cap,
                     int32_t* out_count, int32_t* out_start, int64_t start_pitch, int block_threads, void* stream) {
-    return bpe_tokenize(seq, pitch, len, n_win, max_len, merge_a, merge_b, merge_new, n_merges, scratch,
+    return bpe_tokenize(seq, pitch, len, n_win, max_len, merge_a, merge_b, merge_new, merge_batch, n_merges, scratch,
                         scratch_pitch, out_tokens, out_pitch, out_cap, out_count, out_start, start_pitch, block_threads,
                         ST(stream));
 }

@@ -159,7 +159,17 @@ int encode_windows(const uint8_t* genome, const int64_t* win_base, const int32_t
 // One CTA per window; symbols in shared memory when the window fits, else in a global
 // scratch row (gene windows: ~301 k symbols).  Ranks whose operands are absent from the
 // window (per-CTA occupancy counters) are skipped without touching the symbols.
+//
+// Rank BATCHES.  Consecutive ranks whose symbol sets {left, right, new} are pairwise disjoint
+// (and none of which is a self pair) commute: a merge only creates adjacencies that involve its
+// own new token, the symbol it kills always sits right behind a symbol of its own left type, so
+// no match of another rank of the batch appears, disappears or moves.  Such a run is applied in
+// ONE sweep with ONE barrier: every position looks its symbol up in a small table (symbol ->
+// rank of the batch whose left operand it is).  The host supplies the batch id of every rank
+// (merge_batch, nondecreasing; stage1.merge_batches builds it: 482 ranks -> 162 batches of up
+// to 12); null = every rank alone.  Self-pair ranks are always alone (detect / apply phases).
 // ---------------------------------------------------------------------------------
+constexpr int kMaxBatch = 16;
 constexpr uint16_t kDead = 0xFFFF, kSep = 0xFFFE;
 constexpr int kBpeSmemSyms = 8192;    // windows up to this many symbols stay in shared memory
 constexpr int kMaxVocab = 512;
@@ -167,6 +177,7 @@ constexpr int kMaxVocab = 512;
 struct BpeParams {
     const uint8_t* seq; int64_t pitch; const int32_t* len;   // [n_win, pitch] bytes
     const uint16_t* merge_a; const uint16_t* merge_b; const uint16_t* merge_new; int n_merges;
+    const uint16_t* merge_batch;                              // [n_merges] nondecreasing batch id per rank, or null (see below)
     uint16_t* scratch; int64_t scratch_pitch;                 // [n_win, scratch_pitch] for long windows (may be null)
     int32_t* out_tokens; int out_pitch; int out_cap;          // [n_win, out_pitch]; first out_cap tokens kept, rest of the row zeroed
     int32_t* out_count;                                       // [n_win] total token count (before truncation)
@@ -207,22 +218,56 @@ __global__ void bpe_tokenize_kernel(const BpeParams p) {
     }
     __syncthreads();
 
-    for (int r = 0; r < p.n_merges; ++r) {
-        const uint16_t a = p.merge_a[r], b = p.merge_b[r], c = p.merge_new[r];
+    __shared__ short s_rk[kMaxVocab];                   // symbol -> index (within the batch) of the rank it is the left operand of
+    __shared__ int s_mcnt[kMaxBatch];
+    for (int i = tid; i < kMaxVocab; i += nt) s_rk[i] = -1;
+    __syncthreads();
+    for (int r0 = 0; r0 < p.n_merges;) {
+        int r1 = r0 + 1;
+        if (p.merge_batch) {
+            const uint16_t bid = p.merge_batch[r0];
+            while (r1 < p.n_merges && r1 - r0 < kMaxBatch && p.merge_batch[r1] == bid) ++r1;
+        }
+        const uint16_t a = p.merge_a[r0], b = p.merge_b[r0], c = p.merge_new[r0];
+        const bool self_pair = a == b;                    // (always a batch of its own)
         // uniform skip: all threads read the same counters (stable since the last barrier)
-        if (s_cnt[a] == 0 || s_cnt[b] == 0 || (a == b && s_cnt[a] < 2)) continue;
-        int merged = 0;
-        if (a != b) {
+        bool any = false;
+        for (int r = r0; r < r1; ++r) {
+            const uint16_t ra = p.merge_a[r], rb = p.merge_b[r];
+            any |= s_cnt[ra] != 0 && s_cnt[rb] != 0 && !(ra == rb && s_cnt[ra] < 2);
+        }
+        if (!any) { r0 = r1; continue; }
+        if (!self_pair) {
             // every thread must have taken the skip decision above before any occupancy counter moves
             __syncthreads();
-            // matches of a non-self pair can never share a symbol: apply immediately
+            if (tid < r1 - r0) {
+                const uint16_t ra = p.merge_a[r0 + tid], rb = p.merge_b[r0 + tid];
+                if (s_cnt[ra] != 0 && s_cnt[rb] != 0) s_rk[ra] = (short)tid;
+                s_mcnt[tid] = 0;
+            }
+            __syncthreads();
+            // matches of the batch's ranks can never share a symbol: apply immediately
             for (int i = tid; i < n; i += nt) {
-                if (sym[i] != a) continue;
+                const uint16_t sy = sym[i];
+                if (sy >= kMaxVocab) continue;            // DEAD / SEP
+                const int k = s_rk[sy];
+                if (k < 0) continue;
                 int j = i + 1;
                 while (j < n && sym[j] == kDead) ++j;
-                if (j < n && sym[j] == b) { sym[i] = c; sym[j] = kDead; ++merged; }
+                if (j < n && sym[j] == p.merge_b[r0 + k]) {
+                    sym[i] = p.merge_new[r0 + k]; sym[j] = kDead;
+                    atomicAdd(&s_mcnt[k], 1);
+                }
+            }
+            __syncthreads();
+            if (tid < r1 - r0) {                          // symbol sets are disjoint: no two threads touch one counter
+                const uint16_t ra = p.merge_a[r0 + tid], rb = p.merge_b[r0 + tid], rc = p.merge_new[r0 + tid];
+                const int m = s_mcnt[tid];
+                if (m) { s_cnt[rc] += m; s_cnt[ra] -= m; s_cnt[rb] -= m; }
+                s_rk[ra] = -1;
             }
         } else {
+            int merged = 0;
             // self pair: within a run of consecutive a's merge (1st,2nd), (3rd,4th), ... -> decide from the
             // parity of the number of a's that precede i in its run; detect first, apply after a barrier
             // (the tentative mark c|0x8000 is treated as `a` by concurrent scans, so marking is race-free)
@@ -253,9 +298,10 @@ __global__ void bpe_tokenize_kernel(const BpeParams p) {
                     sym[j] = kDead; sym[i] = c; ++merged;
                 }
             }
+            if (merged) { atomicAdd(&s_cnt[c], merged); atomicSub(&s_cnt[a], 2 * merged); }
         }
-        if (merged) { atomicAdd(&s_cnt[c], merged); atomicSub(&s_cnt[a], merged); atomicSub(&s_cnt[b], merged); }
         __syncthreads();
+        r0 = r1;
     }
 
     // ---- ordered compaction: each thread owns a contiguous segment ----
@@ -312,7 +358,6 @@ bpe_tokenize_cluster_kernel(const BpeParams p, const int seg_cap) {
     __shared__ int s_cnt[2][kMaxVocab];                  // replicated occupancy counters (double buffered)
     __shared__ uint16_t* s_peer[kBpeCluster];
     __shared__ int* s_peer_cnt[kBpeCluster];
-    __shared__ int s_merged[2];
     __shared__ int s_segcnt[kBpeCluster];
     __shared__ int s_warp_tot[32];
     const int rank = (int)cluster.block_rank();
@@ -328,7 +373,6 @@ bpe_tokenize_cluster_kernel(const BpeParams p, const int seg_cap) {
         s_peer_cnt[tid] = cluster.map_shared_rank(&s_cnt[0][0], tid);
     }
     for (int i = tid; i < 2 * kMaxVocab; i += nt) (&s_cnt[0][0])[i] = 0;
-    if (tid < 2) s_merged[tid] = 0;
     __syncthreads();
     // local histogram in replica 0 slots of a scratch copy: count into registers-free smem then publish
     __shared__ int s_hist[32];                            // base ids 4..17 only
@@ -357,24 +401,53 @@ bpe_tokenize_cluster_kernel(const BpeParams p, const int seg_cap) {
         const int c = pos / seg;
         s_peer[c][pos - c * seg] = v;
     };
-    // Per applied sweep every CTA posts its merge count in its own shared memory (slot k&1); after the cluster
-    // barrier each CTA gathers the 8 counts through DSMEM and updates its private replica of the counters, so all
-    // replicas stay identical without remote atomics.
-    __shared__ int s_pub[2];
-    int k = 0;                                            // applied sweeps so far (cluster-uniform)
-    for (int r = 0; r < p.n_merges; ++r) {
-        const uint16_t a = p.merge_a[r], b = p.merge_b[r], c = p.merge_new[r];
+    // Per applied batch every CTA posts the merge counts of the batch's ranks in its own shared memory (slot k&1); after
+    // the cluster barrier each CTA gathers the 8 count vectors through DSMEM and updates its private replica of the
+    // counters, so all replicas stay identical without remote atomics.
+    __shared__ int s_pub[2][kMaxBatch];
+    __shared__ int s_mcnt[2][kMaxBatch];
+    __shared__ short s_rk[kMaxVocab];                     // symbol -> index (within the batch) of the rank it is the left operand of
+    for (int i = tid; i < kMaxVocab; i += nt) s_rk[i] = -1;
+    if (tid < 2 * kMaxBatch) (&s_mcnt[0][0])[tid] = 0;
+    __syncthreads();
+    int k = 0;                                            // applied batches so far (cluster-uniform)
+    for (int r0 = 0; r0 < p.n_merges;) {
+        int r1 = r0 + 1;
+        if (p.merge_batch) {
+            const uint16_t bid = p.merge_batch[r0];
+            while (r1 < p.n_merges && r1 - r0 < kMaxBatch && p.merge_batch[r1] == bid) ++r1;
+        }
+        const int nb = r1 - r0;
+        const uint16_t a = p.merge_a[r0], b = p.merge_b[r0], c = p.merge_new[r0];
+        const bool self_pair = a == b;                    // (always a batch of its own)
         const int* cnt = s_cnt[0];
-        if (cnt[a] == 0 || cnt[b] == 0 || (a == b && cnt[a] < 2)) continue;       // uniform over the whole cluster
-        int merged = 0;
-        if (a != b) {
+        bool any = false;                                 // uniform over the whole cluster (identical replicas)
+        for (int r = r0; r < r1; ++r) {
+            const uint16_t ra = p.merge_a[r], rb = p.merge_b[r];
+            any |= cnt[ra] != 0 && cnt[rb] != 0 && !(ra == rb && cnt[ra] < 2);
+        }
+        if (!any) { r0 = r1; continue; }
+        int* mc = s_mcnt[k & 1];
+        if (!self_pair) {
+            if (tid < nb) {
+                const uint16_t ra = p.merge_a[r0 + tid], rb = p.merge_b[r0 + tid];
+                if (cnt[ra] != 0 && cnt[rb] != 0) s_rk[ra] = (short)tid;
+            }
+            __syncthreads();
             for (int i = lo + tid; i < hi; i += nt) {
-                if (s_sym[i - lo] != a) continue;
+                const uint16_t sy = s_sym[i - lo];
+                if (sy >= kMaxVocab) continue;            // DEAD / SEP
+                const int kk = s_rk[sy];
+                if (kk < 0) continue;
                 int j = i + 1;
                 while (j < n && LD(j) == kDead) ++j;
-                if (j < n && LD(j) == b) { s_sym[i - lo] = c; ST(j, kDead); ++merged; }
+                if (j < n && LD(j) == p.merge_b[r0 + kk]) {
+                    s_sym[i - lo] = p.merge_new[r0 + kk]; ST(j, kDead);
+                    atomicAdd(&mc[kk], 1);
+                }
             }
         } else {
+            int merged = 0;
             const uint16_t mark = (uint16_t)(c | 0x8000);
             for (int i = lo + tid; i < hi; i += nt) {
                 if (s_sym[i - lo] != a) continue;
@@ -398,21 +471,30 @@ bpe_tokenize_cluster_kernel(const BpeParams p, const int seg_cap) {
                 while (j < n && LD(j) == kDead) ++j;
                 ST(j, kDead); s_sym[i - lo] = c; ++merged;
             }
+            if (merged) atomicAdd(&mc[0], merged);
         }
-        if (merged) atomicAdd(&s_merged[k & 1], merged);
         __syncthreads();
-        if (tid == 0) { s_pub[k & 1] = s_merged[k & 1]; s_merged[(k + 1) & 1] = 0; }
-        cluster.sync();                                   // all merges of this rank + every CTA's count are visible
-        if (tid < 32) {
-            int v = tid < kBpeCluster ? cluster.map_shared_rank(&s_pub[0], tid)[k & 1] : 0;
+        if (tid < kMaxBatch) {
+            s_pub[k & 1][tid] = tid < nb ? mc[tid] : 0;
+            s_mcnt[(k + 1) & 1][tid] = 0;
+            if (tid < nb && !self_pair) s_rk[p.merge_a[r0 + tid]] = -1;
+        }
+        cluster.sync();                                   // all merges of this batch + every CTA's counts are visible
+        if (tid < 32 * kMaxBatch / 4) {                   // 4 ranks per warp: lanes (8 CTAs x 4 ranks)
+            const int q = tid >> 5, lane = tid & 31;      // warp q handles ranks 4q .. 4q+3
+            const int rr = 4 * q + (lane >> 3), cta = lane & 7;
+            int v = rr < nb ? cluster.map_shared_rank(&s_pub[0][0], cta)[(k & 1) * kMaxBatch + rr] : 0;
 #pragma unroll
             for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (tid == 0) {
-                s_cnt[0][c] += v; s_cnt[0][a] -= v; s_cnt[0][b] -= v;
+            if (cta == 0 && rr < nb && v != 0) {          // symbol sets of a batch are disjoint: one writer per counter
+                const uint16_t ra = p.merge_a[r0 + rr], rb = p.merge_b[r0 + rr], rc = p.merge_new[r0 + rr];
+                s_cnt[0][rc] += v;
+                if (ra == rb) s_cnt[0][ra] -= 2 * v; else { s_cnt[0][ra] -= v; s_cnt[0][rb] -= v; }
             }
         }
         __syncthreads();
         ++k;
+        r0 = r1;
     }
     cluster.sync();                                       // no CTA may exit (or reuse s_pub) while peers still read it
 
@@ -458,13 +540,13 @@ bpe_tokenize_cluster_kernel(const BpeParams p, const int seg_cap) {
 }
 
 int bpe_tokenize(const uint8_t* seq, int64_t pitch, const int32_t* len, int n_win, int max_len,
-                 const uint16_t* merge_a, const uint16_t* merge_b, const uint16_t* merge_new, int n_merges,
-                 uint16_t* scratch, int64_t scratch_pitch, int32_t* out_tokens, int out_pitch, int out_cap,
+                 const uint16_t* merge_a, const uint16_t* merge_b, const uint16_t* merge_new,
+                 const uint16_t* merge_batch, int n_merges, uint16_t* scratch, int64_t scratch_pitch, int32_t* out_tokens, int out_pitch, int out_cap,
                  int32_t* out_count, int32_t* out_start, int64_t start_pitch, int block_threads, cudaStream_t s) {
     if (n_win == 0) return 0;
     VF_REQUIRE(out_cap <= out_pitch, "bpe_tokenize: out_cap %d > out_pitch %d", out_cap, out_pitch);
     VF_REQUIRE(out_start == nullptr || start_pitch >= max_len, "bpe_tokenize: start_pitch too small");
-    BpeParams p{seq, pitch, len, merge_a, merge_b, merge_new, n_merges, scratch, scratch_pitch,
+    BpeParams p{seq, pitch, len, merge_a, merge_b, merge_new, n_merges, merge_batch, scratch, scratch_pitch,
                 out_tokens, out_pitch, out_cap, out_count, out_start, start_pitch,
                 (int)(pitch < (int64_t)max_len ? pitch : (int64_t)max_len)};
     if (max_len > kBpeSmemSyms) {

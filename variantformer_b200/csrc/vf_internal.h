@@ -43,8 +43,8 @@ int encode_windows(const uint8_t* genome, const int64_t* win_base, const int32_t
                    const uint8_t* alt_pool, int n_win, int max_window, uint8_t* out, int64_t pitch, int32_t* out_len,
                    int32_t* err, cudaStream_t s);
 int bpe_tokenize(const uint8_t* seq, int64_t pitch, const int32_t* len, int n_win, int max_len,
-                 const uint16_t* merge_a, const uint16_t* merge_b, const uint16_t* merge_new, int n_merges,
-                 uint16_t* scratch, int64_t scratch_pitch, int32_t* out_tokens, int out_pitch, int out_cap,
+                 const uint16_t* merge_a, const uint16_t* merge_b, const uint16_t* merge_new,
+                 const uint16_t* merge_batch, int n_merges, uint16_t* scratch, int64_t scratch_pitch, int32_t* out_tokens, int out_pitch, int out_cap,
                  int32_t* out_count, int32_t* out_start, int64_t start_pitch, int block_threads, cudaStream_t s);
 
 }  // namespace vf

@@ -389,7 +389,8 @@ def encode_windows(genome, win_base, w0, w1, var_lo, var_hi, flags, variants, ma
 
 
 def bpe_tokenize(seq, lens, max_len, merges, out_pitch, out_cap, want_starts=False, typical_len=None):
-    """seq uint8 [n, pitch]; lens int32 [n]; merges = (a, b, new) uint16 device tensors (viewed as int16 storage)."""
+    """seq uint8 [n, pitch]; lens int32 [n]; merges = (a, b, new[, batch]) uint16 device tensors (viewed as int16
+    storage); `batch` = per-rank batch ids (stage1.merge_batches) or absent."""
     n, pitch = seq.shape
     dev = seq.device
     out = torch.empty((n, out_pitch), dtype=torch.int32, device=dev)
@@ -398,10 +399,12 @@ def bpe_tokenize(seq, lens, max_len, merges, out_pitch, out_cap, want_starts=Fal
     t = max_len if typical_len is None else typical_len
     threads = 128 if t <= 1024 else (256 if t <= 2048 else (512 if t <= 4096 else 1024))
     starts = torch.empty((n, max_len), dtype=torch.int32, device=dev) if want_starts else None
-    a, b, c = merges
+    a, b, c = merges[:3]
+    batch = merges[3] if len(merges) > 3 else None         # rank batches (stage1.merge_batches), optional
     # algorithmic bytes: every sequence byte read once (typical length) + int32 tokens of the kept prefix written
     with _timed("stage1_bpe_cluster" if max_len > 8192 else "stage1_bpe", nbytes=float(n) * (t + 4.0 * out_cap)):
-        check(_lib.lib().vf_bpe_tokenize(ptr(seq), pitch, ptr(lens), n, int(max_len), ptr(a), ptr(b), ptr(c), a.numel(),
+        check(_lib.lib().vf_bpe_tokenize(ptr(seq), pitch, ptr(lens), n, int(max_len), ptr(a), ptr(b), ptr(c), ptr(batch),
+                                         a.numel(),
                                          ptr(scratch), int(max_len) if scratch is not None else 0, ptr(out), out_pitch,
                                          out_cap, ptr(cnt), ptr(starts), int(max_len) if want_starts else 0, threads,
                                          stream()))

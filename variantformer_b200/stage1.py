@@ -40,6 +40,20 @@ def load_merge_table(path=_MERGES):
     return np.asarray(left, np.uint16), np.asarray(right, np.uint16), np.asarray(new, np.uint16), vocab
 
 
+def merge_batches(left, right, new, max_batch=16):
+    """Batch id per rank for vf_bpe_tokenize: consecutive ranks share a batch while their {left, right, new} symbol
+    sets are pairwise disjoint; a self-pair rank (left == right) is always alone.  Merges of one batch commute (a merge
+    only creates adjacencies that involve its own new token), so the kernel applies a batch in one sweep."""
+    bid = np.zeros(len(left), np.uint16)
+    cur, size, k, prev_self = set(), 0, 0, False
+    for r, (a, b, c) in enumerate(zip(left.tolist(), right.tolist(), new.tolist())):
+        s = {a, b, c}
+        if size and ((cur & s) or a == b or prev_self or size >= max_batch):
+            k += 1; cur, size = set(), 0
+        cur |= s; size += 1; bid[r] = k; prev_self = a == b
+    return bid
+
+
 def load_merge_table_from_hf_json(path):
     """Same table from a HuggingFace tokenizer JSON (the reference's vocabs/bpe_vocabulary_500.json)."""
     import json
@@ -124,7 +138,9 @@ class WindowTokenizer:
                                (load_merge_table_from_hf_json(merges_path) if merges_path.endswith(".json")
                                 else load_merge_table(merges_path)))
         self.device = torch.device(device)
-        self.merges = tuple(torch.from_numpy(x.view(np.int16)).to(self.device) for x in (a, b, c))
+        # VF_BPE_BATCH=0: every rank its own sweep (A/B timing and the bit-identity test of the batching)
+        batch = merge_batches(a, b, c) if os.environ.get("VF_BPE_BATCH", "1") != "0" else np.arange(len(a), dtype=np.uint16)
+        self.merges = tuple(torch.from_numpy(x.view(np.int16)).to(self.device) for x in (a, b, c, batch))
         self.max_length, self.max_chunks = max_length, max_chunks
         self._no_var = SampleVariants({}, device=self.device)
 
