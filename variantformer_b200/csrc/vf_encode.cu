@@ -10,6 +10,8 @@
 //   __adjust_length / chunkify_data                              (datasets/vcfdataset.py:198-217, :338-394)
 #include <cooperative_groups.h>
 
+#include <stdlib.h>
+
 #include "vf_common.cuh"
 #include "vf_internal.h"
 
@@ -197,74 +199,116 @@ __device__ __forceinline__ uint16_t base_symbol(uint8_t c) {
     }
 }
 
+// Shared by both kernels: the ranks [r0, r0 + nb) of the batch that starts at r0, decided by a whole warp at once
+// (lane t looks at rank r0 + t): nb from the nondecreasing batch ids, `ok` = both operands of the lane's rank occur in
+// the window (two of them for a self pair).  Every warp of the CTA (of the cluster) computes the same answer from the
+// same counters, so the decision is uniform without a barrier.
+struct BatchPick { int nb; unsigned okmask; uint16_t a, b, c; bool ok; };
+__device__ __forceinline__ BatchPick pick_batch(const BpeParams& p, int r0, const int* cnt, int lane) {
+    BatchPick q;
+    const int r = r0 + lane;
+    const bool in = r < p.n_merges && lane < kMaxBatch;
+    uint16_t bid = 0xFFFF;
+    if (in) bid = p.merge_batch ? p.merge_batch[r] : (uint16_t)(lane == 0 ? 0 : 0xFFFE);
+    const uint16_t bid0 = (uint16_t)__shfl_sync(0xffffffffu, (int)bid, 0);
+    const unsigned same = __ballot_sync(0xffffffffu, in && bid == bid0);
+    q.nb = __ffs(~same) - 1;                              // ids are nondecreasing: `same` is a prefix mask (lane 0 always set)
+    q.a = q.b = q.c = 0;
+    q.ok = false;
+    if (lane < q.nb) {
+        q.a = p.merge_a[r]; q.b = p.merge_b[r]; q.c = p.merge_new[r];
+        q.ok = cnt[q.a] != 0 && cnt[q.b] != 0 && !(q.a == q.b && cnt[q.a] < 2);
+    }
+    q.okmask = __ballot_sync(0xffffffffu, q.ok);
+    return q;
+}
+
+// One group of four symbols against the batch's table, branch-free up to the (rare) store: v[0..3] = the group,
+// v[4..11] = the eight slots behind it (a token is at most 8 bases long, so the next alive symbol of v[e] is among
+// v[e+1 .. e+8]).  tab[sy] = right operand | new token << 16 of the batch rank whose LEFT operand is sy (0xFFFFFFFF: none).
+// Calls hit(e, off, packed) for every match: slot e of the group merges with the alive symbol `off` slots behind it.
+// Reading the twelve slots once is sound: a left operand is never killed during its own batch, the alive symbol right
+// behind it can only be killed by this very match, and a symbol that equals the wanted right operand is not a left
+// operand of the batch (disjoint symbol sets), so it cannot change under us.
+template <class Hit>
+__device__ __forceinline__ void sweep_group(const uint16_t (&v)[12], const uint32_t* tab, Hit&& hit) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const uint32_t sy = v[e];
+        if (sy >= (uint32_t)kMaxVocab) continue;                       // DEAD / SEP (cheap, convergent enough)
+        const uint32_t t = tab[sy];
+        uint32_t nxt = kSep, off = 0;
+#pragma unroll
+        for (int d = 8; d >= 1; --d) {                                  // nearest alive slot wins (selects, no branches)
+            const bool alive = v[e + d] != kDead;
+            nxt = alive ? (uint32_t)v[e + d] : nxt;
+            off = alive ? (uint32_t)d : off;
+        }
+        if (t != 0xFFFFFFFFu && nxt == (t & 0xFFFFu)) hit(e, (int)off, t);
+    }
+}
+__device__ __forceinline__ void unpack12(uint2 a, uint2 b, uint2 c, uint16_t (&v)[12]) {
+    v[0] = (uint16_t)a.x; v[1] = (uint16_t)(a.x >> 16); v[2] = (uint16_t)a.y; v[3] = (uint16_t)(a.y >> 16);
+    v[4] = (uint16_t)b.x; v[5] = (uint16_t)(b.x >> 16); v[6] = (uint16_t)b.y; v[7] = (uint16_t)(b.y >> 16);
+    v[8] = (uint16_t)c.x; v[9] = (uint16_t)(c.x >> 16); v[10] = (uint16_t)c.y; v[11] = (uint16_t)(c.y >> 16);
+}
+
 __global__ void bpe_tokenize_kernel(const BpeParams p) {
-    extern __shared__ uint16_t s_sym[];                 // kBpeSmemSyms (only used when the window fits)
+    extern __shared__ __align__(16) uint16_t s_sym[];   // this call's longest window, rounded up to 64 symbols
     __shared__ int s_cnt[kMaxVocab];                    // alive symbols per token id
     __shared__ int s_warp_tot[32];
     __shared__ int s_any;
+    __shared__ uint32_t s_tab[kMaxVocab];               // left operand -> right operand | new token << 16 of its batch rank
+    __shared__ uint8_t s_rk[kMaxVocab];                 // left operand -> index of that rank within the batch
+    __shared__ int s_mcnt[kMaxBatch];
     const int w = blockIdx.x;
     const int n = max(0, min(p.len[w], p.max_len));
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const bool in_smem = n <= kBpeSmemSyms;
-    uint16_t* sym = in_smem ? s_sym : p.scratch + (size_t)w * p.scratch_pitch;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    uint16_t* sym = s_sym;
     const uint8_t* src = p.seq + (size_t)w * p.pitch;
 
-    for (int i = tid; i < kMaxVocab; i += nt) s_cnt[i] = 0;
+    for (int i = tid; i < kMaxVocab; i += nt) { s_cnt[i] = 0; s_tab[i] = 0xFFFFFFFFu; }
     __syncthreads();
-    for (int i = tid; i < n; i += nt) {
-        const uint16_t b = base_symbol(src[i]);
+    const int n4 = (n + 3) >> 2;                          // the sweeps read 4 + 8 symbols at a time: pad with SEP
+    for (int i = tid; i < 4 * n4 + 8; i += nt) {
+        const uint16_t b = i < n ? base_symbol(src[i]) : kSep;
         sym[i] = b;
         if (b != kSep) atomicAdd(&s_cnt[b], 1);
     }
     __syncthreads();
 
-    __shared__ short s_rk[kMaxVocab];                   // symbol -> index (within the batch) of the rank it is the left operand of
-    __shared__ int s_mcnt[kMaxBatch];
-    for (int i = tid; i < kMaxVocab; i += nt) s_rk[i] = -1;
-    __syncthreads();
     for (int r0 = 0; r0 < p.n_merges;) {
-        int r1 = r0 + 1;
-        if (p.merge_batch) {
-            const uint16_t bid = p.merge_batch[r0];
-            while (r1 < p.n_merges && r1 - r0 < kMaxBatch && p.merge_batch[r1] == bid) ++r1;
-        }
-        const uint16_t a = p.merge_a[r0], b = p.merge_b[r0], c = p.merge_new[r0];
-        const bool self_pair = a == b;                    // (always a batch of its own)
-        // uniform skip: all threads read the same counters (stable since the last barrier)
-        bool any = false;
-        for (int r = r0; r < r1; ++r) {
-            const uint16_t ra = p.merge_a[r], rb = p.merge_b[r];
-            any |= s_cnt[ra] != 0 && s_cnt[rb] != 0 && !(ra == rb && s_cnt[ra] < 2);
-        }
-        if (!any) { r0 = r1; continue; }
-        if (!self_pair) {
+        const BatchPick q = pick_batch(p, r0, s_cnt, lane);
+        const int r1 = r0 + q.nb;
+        if (!q.okmask) { r0 = r1; continue; }             // uniform: same counters, stable since the last barrier
+        const uint16_t a = (uint16_t)__shfl_sync(0xffffffffu, (int)q.a, 0), b = (uint16_t)__shfl_sync(0xffffffffu, (int)q.b, 0),
+                       c = (uint16_t)__shfl_sync(0xffffffffu, (int)q.c, 0);
+        if (a != b) {
             // every thread must have taken the skip decision above before any occupancy counter moves
             __syncthreads();
-            if (tid < r1 - r0) {
-                const uint16_t ra = p.merge_a[r0 + tid], rb = p.merge_b[r0 + tid];
-                if (s_cnt[ra] != 0 && s_cnt[rb] != 0) s_rk[ra] = (short)tid;
+            if (tid < q.nb) {
+                if (q.ok) { s_tab[q.a] = (uint32_t)q.b | ((uint32_t)q.c << 16); s_rk[q.a] = (uint8_t)tid; }
                 s_mcnt[tid] = 0;
             }
             __syncthreads();
             // matches of the batch's ranks can never share a symbol: apply immediately
-            for (int i = tid; i < n; i += nt) {
-                const uint16_t sy = sym[i];
-                if (sy >= kMaxVocab) continue;            // DEAD / SEP
-                const int k = s_rk[sy];
-                if (k < 0) continue;
-                int j = i + 1;
-                while (j < n && sym[j] == kDead) ++j;
-                if (j < n && sym[j] == p.merge_b[r0 + k]) {
-                    sym[i] = p.merge_new[r0 + k]; sym[j] = kDead;
-                    atomicAdd(&s_mcnt[k], 1);
-                }
+            const uint2* sym4 = reinterpret_cast<const uint2*>(sym);
+            for (int g = tid; g < n4; g += nt) {
+                const uint2 w4 = sym4[g];
+                if ((w4.x & w4.y) == 0xFFFFFFFFu) continue;           // four DEAD slots
+                uint16_t v[12];
+                unpack12(w4, sym4[g + 1], sym4[g + 2], v);
+                sweep_group(v, s_tab, [&](int e, int off, uint32_t t) {
+                    const int i = 4 * g + e;
+                    sym[i] = (uint16_t)(t >> 16); sym[i + off] = kDead;
+                    atomicAdd(&s_mcnt[s_rk[v[e]]], 1);
+                });
             }
             __syncthreads();
-            if (tid < r1 - r0) {                          // symbol sets are disjoint: no two threads touch one counter
-                const uint16_t ra = p.merge_a[r0 + tid], rb = p.merge_b[r0 + tid], rc = p.merge_new[r0 + tid];
+            if (tid < q.nb) {                             // symbol sets are disjoint: no two threads touch one counter
                 const int m = s_mcnt[tid];
-                if (m) { s_cnt[rc] += m; s_cnt[ra] -= m; s_cnt[rb] -= m; }
-                s_rk[ra] = -1;
+                if (m) { s_cnt[q.c] += m; s_cnt[q.a] -= m; s_cnt[q.b] -= m; }
+                s_tab[q.a] = 0xFFFFFFFFu;
             }
         } else {
             int merged = 0;
@@ -276,13 +320,13 @@ __global__ void bpe_tokenize_kernel(const BpeParams p) {
             __syncthreads();
             for (int i = tid; i < n; i += nt) {
                 if (sym[i] != a) continue;
-                int k = 0, q = i - 1;
+                int k = 0, qq = i - 1;
                 for (;;) {
-                    while (q >= 0 && sym[q] == kDead) --q;
-                    if (q < 0) break;
-                    const uint16_t sq = sym[q];
+                    while (qq >= 0 && sym[qq] == kDead) --qq;
+                    if (qq < 0) break;
+                    const uint16_t sq = sym[qq];
                     if (sq != a && sq != mark) break;
-                    ++k; --q;
+                    ++k; --qq;
                 }
                 if (k & 1) continue;                     // i is the right half of the previous pair
                 int j = i + 1;
@@ -310,7 +354,7 @@ __global__ void bpe_tokenize_kernel(const BpeParams p) {
     int mine = 0;
     for (int i = b0; i < b1; ++i) mine += (sym[i] < kSep);
     int incl = mine;
-    const int lane = tid & 31, wid = tid >> 5;
+    const int wid = tid >> 5;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
     if (lane == 31) s_warp_tot[wid] = incl;
@@ -348,13 +392,13 @@ __global__ void bpe_tokenize_kernel(const BpeParams p) {
 // drive the uniform skip decision are replicated in every CTA and kept identical by gathering the per-CTA merge
 // counts of every applied sweep through DSMEM right after that sweep's cluster barrier.
 // ---------------------------------------------------------------------------------
-constexpr int kBpeCluster = 8;
 
+template <int kBpeCluster>
 __global__ void __launch_bounds__(1024, 1)
 bpe_tokenize_cluster_kernel(const BpeParams p, const int seg_cap) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
-    extern __shared__ uint16_t s_sym[];                  // seg_cap symbols of this CTA's segment
+    extern __shared__ __align__(16) uint16_t s_sym[];    // seg_cap symbols of this CTA's segment
     __shared__ int s_cnt[2][kMaxVocab];                  // replicated occupancy counters (double buffered)
     __shared__ uint16_t* s_peer[kBpeCluster];
     __shared__ int* s_peer_cnt[kBpeCluster];
@@ -364,7 +408,7 @@ bpe_tokenize_cluster_kernel(const BpeParams p, const int seg_cap) {
     const int w = blockIdx.x / kBpeCluster;
     const int n = max(0, min(p.len[w], p.max_len));
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int seg = max(8, (n + kBpeCluster - 1) / kBpeCluster);      // <= seg_cap (host guarantees)
+    const int seg = (max(8, (n + kBpeCluster - 1) / kBpeCluster) + 7) & ~7;   // multiple of 8, <= seg_cap (host guarantees)
     const int lo = min(n, rank * seg), hi = min(n, lo + seg);
     const uint8_t* src = p.seq + (size_t)w * p.pitch;
 
@@ -378,8 +422,8 @@ bpe_tokenize_cluster_kernel(const BpeParams p, const int seg_cap) {
     __shared__ int s_hist[32];                            // base ids 4..17 only
     if (tid < 32) s_hist[tid] = 0;
     cluster.sync();                                       // every CTA's counters are zeroed before anyone publishes
-    for (int i = lo + tid; i < hi; i += nt) {
-        const uint16_t b = base_symbol(src[i]);
+    for (int i = lo + tid; i < lo + (hi < n ? hi - lo : ((hi - lo + 3) & ~3) + 8); i += nt) {   // (4 + 8 slot reads: SEP padding)
+        const uint16_t b = i < hi ? base_symbol(src[i]) : kSep;
         s_sym[i - lo] = b;
         if (b != kSep) atomicAdd(&s_hist[b], 1);
     }
@@ -406,58 +450,58 @@ bpe_tokenize_cluster_kernel(const BpeParams p, const int seg_cap) {
     // counters, so all replicas stay identical without remote atomics.
     __shared__ int s_pub[2][kMaxBatch];
     __shared__ int s_mcnt[2][kMaxBatch];
-    __shared__ short s_rk[kMaxVocab];                     // symbol -> index (within the batch) of the rank it is the left operand of
-    for (int i = tid; i < kMaxVocab; i += nt) s_rk[i] = -1;
+    __shared__ uint32_t s_tab[kMaxVocab];                 // left operand -> right operand | new token << 16 of its batch rank
+    __shared__ uint8_t s_rk[kMaxVocab];                   // left operand -> index of that rank within the batch
+    for (int i = tid; i < kMaxVocab; i += nt) s_tab[i] = 0xFFFFFFFFu;
     if (tid < 2 * kMaxBatch) (&s_mcnt[0][0])[tid] = 0;
     __syncthreads();
+    const int lane = tid & 31;
+    const int len4 = (hi - lo + 3) >> 2;                  // (segment starts are multiples of 8; slots past hi hold SEP)
+    // slots of the local array the 12-slot reads may touch: an inner segment ends where the next CTA's begins; the last
+    // segment (and an empty one) is followed by SEP padding written below
+    const int local_slots = hi < n ? hi - lo : ((hi - lo + 3) & ~3) + 8;
     int k = 0;                                            // applied batches so far (cluster-uniform)
     for (int r0 = 0; r0 < p.n_merges;) {
-        int r1 = r0 + 1;
-        if (p.merge_batch) {
-            const uint16_t bid = p.merge_batch[r0];
-            while (r1 < p.n_merges && r1 - r0 < kMaxBatch && p.merge_batch[r1] == bid) ++r1;
-        }
-        const int nb = r1 - r0;
-        const uint16_t a = p.merge_a[r0], b = p.merge_b[r0], c = p.merge_new[r0];
+        const BatchPick q = pick_batch(p, r0, s_cnt[0], lane);   // uniform over the whole cluster (identical replicas)
+        const int r1 = r0 + q.nb, nb = q.nb;
+        if (!q.okmask) { r0 = r1; continue; }
+        const uint16_t a = (uint16_t)__shfl_sync(0xffffffffu, (int)q.a, 0), b = (uint16_t)__shfl_sync(0xffffffffu, (int)q.b, 0),
+                       c = (uint16_t)__shfl_sync(0xffffffffu, (int)q.c, 0);
         const bool self_pair = a == b;                    // (always a batch of its own)
-        const int* cnt = s_cnt[0];
-        bool any = false;                                 // uniform over the whole cluster (identical replicas)
-        for (int r = r0; r < r1; ++r) {
-            const uint16_t ra = p.merge_a[r], rb = p.merge_b[r];
-            any |= cnt[ra] != 0 && cnt[rb] != 0 && !(ra == rb && cnt[ra] < 2);
-        }
-        if (!any) { r0 = r1; continue; }
         int* mc = s_mcnt[k & 1];
         if (!self_pair) {
-            if (tid < nb) {
-                const uint16_t ra = p.merge_a[r0 + tid], rb = p.merge_b[r0 + tid];
-                if (cnt[ra] != 0 && cnt[rb] != 0) s_rk[ra] = (short)tid;
-            }
+            if (tid < nb && q.ok) { s_tab[q.a] = (uint32_t)q.b | ((uint32_t)q.c << 16); s_rk[q.a] = (uint8_t)tid; }
             __syncthreads();
-            for (int i = lo + tid; i < hi; i += nt) {
-                const uint16_t sy = s_sym[i - lo];
-                if (sy >= kMaxVocab) continue;            // DEAD / SEP
-                const int kk = s_rk[sy];
-                if (kk < 0) continue;
-                int j = i + 1;
-                while (j < n && LD(j) == kDead) ++j;
-                if (j < n && LD(j) == p.merge_b[r0 + kk]) {
-                    s_sym[i - lo] = p.merge_new[r0 + kk]; ST(j, kDead);
-                    atomicAdd(&mc[kk], 1);
+            const uint2* sym4 = reinterpret_cast<const uint2*>(s_sym);
+            for (int g = tid; g < len4; g += nt) {
+                const uint2 w4 = sym4[g];
+                if ((w4.x & w4.y) == 0xFFFFFFFFu) continue;           // four DEAD slots
+                uint16_t v[12];
+                if (4 * g + 12 <= local_slots) {
+                    unpack12(w4, sym4[g + 1], sym4[g + 2], v);
+                } else {                                              // the look-ahead leaves this CTA's segment (last groups)
+                    unpack12(w4, make_uint2(0, 0), make_uint2(0, 0), v);
+#pragma unroll
+                    for (int x = 4; x < 12; ++x) { const int pos = lo + 4 * g + x; v[x] = pos < n ? LD(pos) : kSep; }
                 }
+                sweep_group(v, s_tab, [&](int e, int off, uint32_t t) {
+                    const int i = lo + 4 * g + e;
+                    s_sym[i - lo] = (uint16_t)(t >> 16); ST(i + off, kDead);
+                    atomicAdd(&mc[s_rk[v[e]]], 1);
+                });
             }
         } else {
             int merged = 0;
             const uint16_t mark = (uint16_t)(c | 0x8000);
             for (int i = lo + tid; i < hi; i += nt) {
                 if (s_sym[i - lo] != a) continue;
-                int kk = 0, q = i - 1;
+                int kk = 0, qq = i - 1;
                 for (;;) {
-                    while (q >= 0 && LD(q) == kDead) --q;
-                    if (q < 0) break;
-                    const uint16_t sq = LD(q);
+                    while (qq >= 0 && LD(qq) == kDead) --qq;
+                    if (qq < 0) break;
+                    const uint16_t sq = LD(qq);
                     if (sq != a && sq != mark) break;
-                    ++kk; --q;
+                    ++kk; --qq;
                 }
                 if (kk & 1) continue;
                 int j = i + 1;
@@ -477,15 +521,16 @@ bpe_tokenize_cluster_kernel(const BpeParams p, const int seg_cap) {
         if (tid < kMaxBatch) {
             s_pub[k & 1][tid] = tid < nb ? mc[tid] : 0;
             s_mcnt[(k + 1) & 1][tid] = 0;
-            if (tid < nb && !self_pair) s_rk[p.merge_a[r0 + tid]] = -1;
+            if (tid < nb && !self_pair) s_tab[q.a] = 0xFFFFFFFFu;
         }
         cluster.sync();                                   // all merges of this batch + every CTA's counts are visible
-        if (tid < 32 * kMaxBatch / 4) {                   // 4 ranks per warp: lanes (8 CTAs x 4 ranks)
-            const int q = tid >> 5, lane = tid & 31;      // warp q handles ranks 4q .. 4q+3
-            const int rr = 4 * q + (lane >> 3), cta = lane & 7;
+        constexpr int kRanksPerWarp = 32 / kBpeCluster;   // lanes = (ranks of the warp) x (CTAs of the cluster)
+        if (tid < 32 * kMaxBatch / kRanksPerWarp) {
+            const int wq = tid >> 5;
+            const int rr = kRanksPerWarp * wq + lane / kBpeCluster, cta = lane % kBpeCluster;
             int v = rr < nb ? cluster.map_shared_rank(&s_pub[0][0], cta)[(k & 1) * kMaxBatch + rr] : 0;
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            for (int o = kBpeCluster / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
             if (cta == 0 && rr < nb && v != 0) {          // symbol sets of a batch are disjoint: one writer per counter
                 const uint16_t ra = p.merge_a[r0 + rr], rb = p.merge_b[r0 + rr], rc = p.merge_new[r0 + rr];
                 s_cnt[0][rc] += v;
@@ -505,7 +550,7 @@ bpe_tokenize_cluster_kernel(const BpeParams p, const int seg_cap) {
     int mine = 0;
     for (int i = b0; i < b1; ++i) mine += (s_sym[i] < kSep);
     int incl = mine;
-    const int lane = tid & 31, wid = tid >> 5;
+    const int wid = tid >> 5;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
     if (lane == 31) s_warp_tot[wid] = incl;
@@ -550,29 +595,42 @@ int bpe_tokenize(const uint8_t* seq, int64_t pitch, const int32_t* len, int n_wi
                 out_tokens, out_pitch, out_cap, out_count, out_start, start_pitch,
                 (int)(pitch < (int64_t)max_len ? pitch : (int64_t)max_len)};
     if (max_len > kBpeSmemSyms) {
-        // cluster path: 8 CTAs per window, segment of the symbol array per CTA in shared memory
-        const int seg_cap = (max_len + kBpeCluster - 1) / kBpeCluster + 8;
-        const size_t smem = (size_t)seg_cap * sizeof(uint16_t);
-        VF_REQUIRE(smem <= 200 * 1024, "bpe_tokenize: window of %d symbols exceeds the cluster kernel's capacity", max_len);
-        static size_t attr_smem = 0;
-        if (smem > attr_smem) {
-            VF_CUDA_OK(cudaFuncSetAttribute(bpe_tokenize_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)smem));
-            attr_smem = smem;
+        // cluster path: CL CTAs per window, segment of the symbol array per CTA in shared memory.  16-CTA clusters (non
+        // portable size) put a slab's 8 gene windows on 128 SMs instead of 64; VF_BPE_CLUSTER=8 selects the portable size.
+        static int cl = 0;
+        if (cl == 0) {
+            const char* e = getenv("VF_BPE_CLUSTER");
+            cl = (e && atoi(e) == 8) ? 8 : 16;
         }
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(n_win * kBpeCluster); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = kBpeCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        VF_CUDA_OK(cudaLaunchKernelEx(&cfg, bpe_tokenize_cluster_kernel, p, seg_cap));
-        return 0;
+        auto launch = [&](auto kern, int CL) -> int {
+            const int seg_cap = (max_len + CL - 1) / CL + 32;
+            const size_t smem = (size_t)seg_cap * sizeof(uint16_t);
+            VF_REQUIRE(smem <= 200 * 1024, "bpe_tokenize: window of %d symbols exceeds the cluster kernel's capacity", max_len);
+            VF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (CL > 8) VF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(n_win * CL); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            VF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p, seg_cap));
+            return 0;
+        };
+        return cl == 16 ? launch(bpe_tokenize_cluster_kernel<16>, 16) : launch(bpe_tokenize_cluster_kernel<8>, 8);
     }
-    // block size is a pure performance hint (typical window length); any value works for any window
-    const int threads = (block_threads == 128 || block_threads == 256 || block_threads == 512 || block_threads == 1024)
-                            ? block_threads : (max_len <= 1024 ? 128 : 1024);
-    const size_t smem = (size_t)kBpeSmemSyms * sizeof(uint16_t);
+    // Block size is a pure performance hint (typical window length); any value works for any window.  Short windows are
+    // latency bound (one barrier per rank batch, a handful of symbols per thread): what pays is WINDOWS IN FLIGHT, so
+    // the shared-memory footprint is sized to this call's longest window (not the 8192-symbol maximum) and cCRE-sized
+    // windows run on 64 threads — 32 resident CTAs per SM instead of 11.
+    const int threads = (block_threads == 64 || block_threads == 128 || block_threads == 256 || block_threads == 512 ||
+                         block_threads == 1024) ? block_threads : (max_len <= 1024 ? 64 : 1024);
+    const size_t smem = (size_t)((max_len + 16 + 63) / 64 * 64) * sizeof(uint16_t);   // + the sweeps' 8-slot look-ahead
+    static size_t attr_smem1 = 0;
+    if (smem > 40 * 1024 && smem > attr_smem1) {
+        VF_CUDA_OK(cudaFuncSetAttribute(bpe_tokenize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem1 = smem;
+    }
     bpe_tokenize_kernel<<<n_win, threads, smem, s>>>(p);
     VF_LAUNCH_OK("bpe_tokenize_kernel launch");
     return 0;

@@ -397,7 +397,8 @@ def bpe_tokenize(seq, lens, max_len, merges, out_pitch, out_cap, want_starts=Fal
     cnt = torch.empty(n, dtype=torch.int32, device=dev)
     scratch = None                      # long windows run on the cluster kernel, which keeps symbols in shared memory
     t = max_len if typical_len is None else typical_len
-    threads = 128 if t <= 1024 else (256 if t <= 2048 else (512 if t <= 4096 else 1024))
+    # short windows are latency bound: small CTAs, many windows in flight per SM (vf_encode.cu: bpe_tokenize)
+    threads = 64 if t <= 1024 else (256 if t <= 2048 else (512 if t <= 4096 else 1024))
     starts = torch.empty((n, max_len), dtype=torch.int32, device=dev) if want_starts else None
     a, b, c = merges[:3]
     batch = merges[3] if len(merges) > 3 else None         # rank batches (stage1.merge_batches), optional

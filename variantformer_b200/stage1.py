@@ -41,17 +41,32 @@ def load_merge_table(path=_MERGES):
 
 
 def merge_batches(left, right, new, max_batch=16):
-    """Batch id per rank for vf_bpe_tokenize: consecutive ranks share a batch while their {left, right, new} symbol
-    sets are pairwise disjoint; a self-pair rank (left == right) is always alone.  Merges of one batch commute (a merge
-    only creates adjacencies that involve its own new token), so the kernel applies a batch in one sweep."""
-    bid = np.zeros(len(left), np.uint16)
-    cur, size, k, prev_self = set(), 0, 0, False
-    for r, (a, b, c) in enumerate(zip(left.tolist(), right.tolist(), new.tolist())):
-        s = {a, b, c}
-        if size and ((cur & s) or a == b or prev_self or size >= max_batch):
-            k += 1; cur, size = set(), 0
-        cur |= s; size += 1; bid[r] = k; prev_self = a == b
-    return bid
+    """Schedule of the merge table for vf_bpe_tokenize -> (order, batch): `order` permutes the ranks, `batch` is the
+    nondecreasing batch id of every permuted rank.
+
+    Two merges whose symbol sets {left, right, new} are disjoint commute (a merge only creates adjacencies that involve
+    its own new token), so any order that keeps every pair of INTERACTING ranks in its original relative order gives the
+    tokens of the rank-by-rank sweeps.  Rank r gets level 1 + max(level of the earlier ranks it shares a symbol with);
+    ranks of one level are pairwise disjoint and become one batch (split at max_batch), applied in one sweep with one
+    barrier; a self pair (left == right) needs its detect / apply phases and is a batch of its own.
+    bpe500: 482 ranks -> 87 levels -> 113 batches."""
+    n = len(left)
+    last, level = {}, np.zeros(n, np.int64)
+    for r, syms in enumerate(zip(left.tolist(), right.tolist(), new.tolist())):
+        level[r] = 1 + max(last.get(s, -1) for s in syms)
+        for s in syms:
+            last[s] = level[r]
+    selfp = np.asarray(left) == np.asarray(right)
+    order, batch, k = [], [], 0
+    for lv in range(int(level.max()) + 1 if n else 0):
+        idx = np.nonzero(level == lv)[0]
+        plain = idx[~selfp[idx]]
+        for c0 in range(0, len(plain), max_batch):
+            chunk = plain[c0:c0 + max_batch]
+            order += chunk.tolist(); batch += [k] * len(chunk); k += 1
+        for r in idx[selfp[idx]]:
+            order.append(int(r)); batch.append(k); k += 1
+    return np.asarray(order, np.int64), np.asarray(batch, np.uint16)
 
 
 def load_merge_table_from_hf_json(path):
@@ -139,8 +154,12 @@ class WindowTokenizer:
                                 else load_merge_table(merges_path)))
         self.device = torch.device(device)
         # VF_BPE_BATCH=0: every rank its own sweep (A/B timing and the bit-identity test of the batching)
-        batch = merge_batches(a, b, c) if os.environ.get("VF_BPE_BATCH", "1") != "0" else np.arange(len(a), dtype=np.uint16)
-        self.merges = tuple(torch.from_numpy(x.view(np.int16)).to(self.device) for x in (a, b, c, batch))
+        if os.environ.get("VF_BPE_BATCH", "1") != "0":
+            order, batch = merge_batches(a, b, c)
+            a, b, c = a[order], b[order], c[order]           # the kernel walks the table in this (equivalent) order
+        else:
+            batch = np.arange(len(a), dtype=np.uint16)
+        self.merges = tuple(torch.from_numpy(np.ascontiguousarray(x).view(np.int16)).to(self.device) for x in (a, b, c, batch))
         self.max_length, self.max_chunks = max_length, max_chunks
         self._no_var = SampleVariants({}, device=self.device)
 
