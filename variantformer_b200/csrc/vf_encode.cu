@@ -237,6 +237,7 @@ __device__ __forceinline__ void sweep_group(const uint16_t (&v)[12], const uint3
         const uint32_t sy = v[e];
         if (sy >= (uint32_t)kMaxVocab) continue;                       // DEAD / SEP (cheap, convergent enough)
         const uint32_t t = tab[sy];
+        if (t == 0xFFFFFFFFu) continue;                                 // not a left operand of this batch
         uint32_t nxt = kSep, off = 0;
 #pragma unroll
         for (int d = 8; d >= 1; --d) {                                  // nearest alive slot wins (selects, no branches)
@@ -244,7 +245,7 @@ __device__ __forceinline__ void sweep_group(const uint16_t (&v)[12], const uint3
             nxt = alive ? (uint32_t)v[e + d] : nxt;
             off = alive ? (uint32_t)d : off;
         }
-        if (t != 0xFFFFFFFFu && nxt == (t & 0xFFFFu)) hit(e, (int)off, t);
+        if (nxt == (t & 0xFFFFu)) hit(e, (int)off, t);
     }
 }
 __device__ __forceinline__ void unpack12(uint2 a, uint2 b, uint2 c, uint16_t (&v)[12]) {
