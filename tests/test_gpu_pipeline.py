@@ -124,6 +124,33 @@ def _write_artifacts(tmp_path, chroms, var, genes):
     return art, rows
 
 
+def test_predict_to_parquet_is_resumable_and_equals_predict(tmp_path):
+    """The production loop: pinned double-buffered D2H + background Parquet writer, one file per slab; an interrupted
+    run resumes from the files that exist and ends with the same bits as HotPath.predict."""
+    from variantformer_b200.writer import ResultWriter
+    chroms, var, genes = _world(seed=81, n_genes=5, n_cres=24)
+    sd = random_init.make_state_dict(CFG, HP, seed=9)
+    hot = HotPath(Engine(sd, CFG, HP), Genome.from_arrays(chroms, "cuda"))
+    variants = SampleVariants(var, "cuda")
+    slabs = [genes[:2], genes[2:3], genes[3:]]
+    want = [hot.predict(g, variants) for g in slabs]
+    out = str(tmp_path / "run")
+    w = ResultWriter(out, CFG["emb_dim"], meta={"seed": 9})
+    assert hot.predict_to_parquet(slabs, variants, w, sample="S1") == 3
+    w.close()
+    assert w.done() == {0, 1, 2}
+    os.remove(w.path(1))                                          # "crash" after slab 0 and 2 were written
+    w = ResultWriter(out, CFG["emb_dim"], meta={"seed": 9})
+    assert w.done() == {0, 2} and hot.predict_to_parquet(slabs, variants, w, sample="S1") == 1
+    assert hot.predict_to_parquet(slabs, variants, w, sample="S1") == 0
+    w.close()
+    df = w.read_all()
+    pred = np.concatenate([p for p, _ in want]); emb = np.concatenate([e for _, e in want])
+    assert len(df) == len(pred) and np.array_equal(df["predicted_expression"].to_numpy(), pred)
+    assert np.array_equal(np.stack(df["embeddings"].to_numpy()), emb)
+    assert df["tissue"].tolist() == [t for g in genes for t in g.tissues] and set(df["sample"]) == {"S1"}
+
+
 def test_vcfprocessor_surface_end_to_end(tmp_path):
     from variantformer_b200.processors.vcfprocessor import VCFProcessor
     chroms, var, genes = _world(seed=78, n_genes=2, n_cres=24)

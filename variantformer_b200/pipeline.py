@@ -123,6 +123,54 @@ class HotPath:
             else:
                 yield out["pred"], out["emb"], slab["err"]
 
+    def predict_to_parquet(self, slabs, variants: SampleVariants, writer, sample="sample", gene_ids=None, start=0):
+        """The production loop: every slab of `slabs` (an iterable of gene lists) through the
+        pipelined path; results leave the device by an asynchronous copy into pinned, double-buffered host memory on a
+        copy stream and are written as one Parquet file per slab by `writer` (variantformer_b200.writer.ResultWriter)
+        in the background while the next slab computes.  Slabs whose file already exists are skipped, so an interrupted
+        run resumes (`start` = index of the first slab of the iterable).  gene_ids: optional callable
+        (slab index, position) -> gene id string.  -> number of slabs computed in this call."""
+        from .writer import PinnedRing
+        dev = self.engine.device
+        done = writer.done()
+        slabs = list(slabs)
+        todo = [(start + i, g) for i, g in enumerate(slabs) if start + i not in done]
+        if not todo:
+            return 0
+        main = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_copy"):
+            self._copy, self._ring = torch.cuda.Stream(dev), PinnedRing()
+        pending = None                                   # (event, slab index, genes, buffer, n, err tensor)
+
+        def flush(p):
+            ev, idx, genes, buf, n, err = p
+            ev.synchronize()
+            self._raise_on_stage1_error(err)
+            D = self.engine.w.D
+            rows, item = [], 0
+            for k, g in enumerate(genes):
+                gid = gene_ids(idx, k) if gene_ids is not None else f"{g.chrom}:{g.start}-{g.end}"
+                rows += [(item, sample, gid, int(t)) for t in g.tissues]
+                item += 1
+            writer.submit(idx, rows, buf["pred"][:n].numpy(), buf["emb"][:n * D].view(n, D).numpy(),
+                          release=lambda b=buf: self._ring.release(b))
+        it = iter(todo)
+        for (idx, genes), (pred, emb, err) in zip(todo, self.predict_pipelined((g for _, g in todo), variants, to_host=False)):
+            n, D = pred.shape[0], emb.shape[1]
+            buf = self._ring.acquire(n, D)               # blocks only if both buffers are still being written out
+            self._copy.wait_stream(main)
+            with torch.cuda.stream(self._copy):
+                buf["pred"][:n].copy_(pred, non_blocking=True)
+                buf["emb"][:n * D].view(n, D).copy_(emb, non_blocking=True)
+                ev = torch.cuda.Event(); ev.record(self._copy)
+            pred.record_stream(self._copy); emb.record_stream(self._copy)
+            if pending is not None:
+                flush(pending)                           # slab i-1 goes to the writer while slab i computes
+            pending = (ev, idx, genes, buf, n, err)
+        if pending is not None:
+            flush(pending)
+        return len(todo)
+
     def predict(self, genes, variants: SampleVariants = None, to_host=True):
         """-> (pred [sum T], emb [sum T, D]) as numpy (to_host) or device tensors."""
         t = self.tokenize(genes, variants)
