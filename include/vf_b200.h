@@ -30,6 +30,9 @@ extern "C" {
 
 const char* vf_last_error(void);
 int vf_abi_version(void);
+/* Kernels launched by this library since it was loaded (process-wide; bench.py reports the difference over its timed
+ * region as gpu_launches). */
+unsigned long long vf_launch_count(void);
 /* Device sanity: returns 0 iff the current device is compute capability 10.x; fills sm_count. */
 int vf_device_check(int* sm_count);
 
@@ -186,6 +189,95 @@ int vf_bpe_tokenize(const uint8_t* seq, int64_t pitch, const int32_t* len, int n
                     const uint16_t* merge_a, const uint16_t* merge_b, const uint16_t* merge_new,
                     const uint16_t* merge_batch, int n_merges, uint16_t* scratch, int64_t scratch_pitch, int32_t* out_tokens, int out_pitch, int out_cap,
                     int32_t* out_count, int32_t* out_start, int64_t start_pitch, int block_threads, void* stream);
+
+/* ---- coarse entry points: whole-module forwards, layer loop inside the library ---------------------------------- */
+/*
+ * Weight-pointer tables.  Every pointer is a DEVICE pointer; the tables themselves (and the per-layer arrays they point
+ * to) live in HOST memory and are only read during the call.  A linear is {w bf16 [N, K] (nn.Linear layout), b fp32 [N],
+ * cs fp32 [N] or NULL}: with cs != NULL the LayerNorm in front of the Linear is folded in — w = bf16(W * gamma),
+ * b = bias + W beta, cs = row sums of that bf16 w (vf_gemm_bf16_ln).  linear_geglu_1 (w, b, cs) is tile-interleaved as
+ * VF_EPI_BIAS_GEGLU_BF16 wants it.  variantformer_b200/engine.py builds exactly these tables from a reference state_dict.
+ */
+typedef struct { const void* w; const float* b; const float* cs; } vf_linear_t;
+
+/* seq2reg/modules.py:129-147: qkv = Wqkv(norm1 folded), out = out_proj, g1 = linear_geglu_1(norm2 folded), g2 = linear_geglu_2 */
+typedef struct { vf_linear_t qkv, out, g1, g2; } vf_seq2reg_layer_t;
+typedef struct {
+    int d, heads, n_layers, ffn_hidden, token_length;   /* 512, 8, 6, 2048, 200 for the configured tokenizers */
+    float ln_eps;
+    const float* emb;                                   /* fp32 [vocab, d]           seq2reg/model.py:214 */
+    const float* pe;                                    /* fp32 [token_length, d] or NULL (ALiBi)   :15-37, :219-220 */
+    const float* slopes;                                /* fp32 [heads] ALiBi slopes or NULL */
+    const vf_seq2reg_layer_t* layers;                   /* host array [n_layers] */
+} vf_seq2reg_weights_t;
+
+/*
+ * Seq2RegPredictor.forward(only_embed=True) for n_win windows (seq2reg/model.py:193-279, seq2reg/modules.py:149-191):
+ * tokens int32 [n_win, L], pad_mask uint8 [n_win, L] (1 = padding), cu int32 [n_win + 1] prefix sums of the valid
+ * counts, n_tok = cu[n_win]; slots / n_items = attention work table of the windows' valid lengths
+ * (vf_attention_build_slots); workspace: caller-owned device memory of vf_seq2reg_workspace_bytes(w, n_tok) bytes,
+ * 256-byte aligned.  out_bf16 [n_win, d] = mean over each window's valid tokens of the last layer (NaN for an empty
+ * window, as upstream).
+ */
+size_t vf_seq2reg_workspace_bytes(const vf_seq2reg_weights_t* w, int64_t n_tok);
+int vf_seq2reg_forward(const vf_seq2reg_weights_t* w, const int32_t* tokens, const uint8_t* pad_mask, const int32_t* cu,
+                       int n_win, int L, int64_t n_tok, const int32_t* slots, int n_items, void* workspace,
+                       size_t workspace_bytes, void* out_bf16, void* stream);
+
+/* layers.py:47-86: qkv = mixer Wqkv(norm1), out = mixer out_proj, q = crossMHA Wq(norm2), kv = crossMHA Wkv (plain; w NULL
+ * for a CRE layer), out2 = crossMHA out_proj, g1 = linear_geglu_1(norm3), g2 = linear_geglu_2; kv9 fp32 [9, 2D] =
+ * Wkv Emb9 + b of a CRE layer (vf_label_attention), NULL for a gene layer. */
+typedef struct { vf_linear_t qkv, out, q, kv, out2, g1, g2; const float* kv9; } vf_context_layer_t;
+typedef struct {
+    int D, heads, n_layers, ffn_hidden, token_dim;      /* 1536, 32, 25, 2048, 512 */
+    float ln_eps;
+    const float* slopes;                                /* fp32 [heads] ALiBi slopes (self-attention) or NULL */
+    const float* registry;                              /* fp32 [num_tissues, D]  start_tkn.registry_tokens (layers.py:508-521) */
+    vf_linear_t cre_map, gene_map;                      /* model_combined_modulator.py:502-507 (plain linears) */
+    const vf_context_layer_t* cre_layers;               /* host array [n_layers - 1] */
+    const vf_context_layer_t* gene_layers;              /* host array [n_layers] */
+    vf_linear_t h0, h4;                                 /* tissue_heads.tissue_expressions.0 / .4 (layers.py:1078-1087) */
+    const float* hn_g; const float* hn_b;               /* ... .1 LayerNorm */
+    const float* h6_w; const float* h6_b;               /* ... .6 Linear(D, 1) */
+} vf_seq2gene_weights_t;
+/*
+ * Index tables of one slab of genes (device pointers, built by the caller: engine.py:Engine.prepare is the reference
+ * builder).  Gene-stream rows: per gene, per tissue: [registry(tissue); chunk_0 .. chunk_{G-1}], tissues of a gene
+ * contiguous.  n_reg = sum of tissues over the slab's genes = number of predictions.
+ */
+typedef struct {
+    int n_cre, n_gene_chunks, n_gene_rows, n_reg, n_need;
+    int single_stream;              /* != 0: CRE stack on the caller's stream (profiling); 0: on the library's side stream */
+    const int32_t* gene_idx;        /* [n_gene_rows]: >= 0 row of gene_map's output, < 0 registry token -(tissue + 1) */
+    const int32_t* row_seq;         /* [n_cre] gene of every CRE row */
+    const float* logc;              /* [genes, 9] log(#CREs of the class in the gene), -inf when absent */
+    const int32_t* last_rows;       /* [n_need] rows whose last-layer output is read: the n_reg registry rows first */
+    const int32_t* cre_pos_idx;     /* [n_reg] CRE row per prediction (VEP token gather) or NULL */
+    const int32_t* slots_gself; int n_gself;            /* work tables (vf_attention_build_slots layout): gene self, */
+    const int32_t* slots_gcross; int n_gcross;          /* stacked gene -> CRE cross (queries: all tissue copies of a gene), */
+    const int32_t* slots_cself; int n_cself;            /* CRE self, */
+    const int32_t* slots_last_self; int n_last_self;    /* last layer: one-row query tiles against their own sequence, */
+    const int32_t* slots_last_cross; int n_last_cross;  /* last layer: runs of one gene's needed rows against its CREs */
+} vf_seq2gene_slab_t;
+/*
+ * cre_map / gene_map, registry-token assembly, CombinedModulator, pool_outputs and the expression head for one slab
+ * (model_combined_modulator.py:137-328, 540-720; layers.py:88-165, 508-521, 1078-1144).  cre_pooled_bf16 [n_cre,
+ * token_dim] / gene_pooled_bf16 [n_gene_chunks, token_dim]: outputs of vf_seq2reg_forward.  pred fp32 [n_reg]
+ * (Softplus applied), emb fp32 [n_reg, D]; gene_token_emb fp32 [n_need - n_reg, D] and cre_token_emb fp32 [n_reg, D]
+ * may be NULL.  The CRE stack runs on a side stream owned by the library (one forward in flight per device).
+ */
+size_t vf_seq2gene_workspace_bytes(const vf_seq2gene_weights_t* w, const vf_seq2gene_slab_t* slab);
+int vf_seq2gene_forward(const vf_seq2gene_weights_t* w, const vf_seq2gene_slab_t* slab, const void* cre_pooled_bf16,
+                        const void* gene_pooled_bf16, void* workspace, size_t workspace_bytes, float* pred, float* emb,
+                        float* gene_token_emb, float* cre_token_emb, void* stream);
+/*
+ * HOST helper: work table of vf_attention_mc_varlen for n_seq sequences of q_lens query rows and k_lens keys (NULL =
+ * self-attention), rows packed back to back.  out_table: HOST int32 [max_items][2][8] (NULL: only count).  Consecutive
+ * 128-row tiles of a sequence share an item; left-over tiles are paired with each other when pair_unrelated != 0.
+ * Returns the number of items (>= 0) or a negative error.  Same tables as variantformer_b200.ops.SlotMap.
+ */
+int vf_attention_build_slots(const int32_t* q_lens, const int32_t* k_lens, int n_seq, int pair_unrelated,
+                             int32_t* out_table, int max_items);
 
 #ifdef __cplusplus
 }

@@ -136,3 +136,24 @@ def test_attention_work_items_cover_every_row_once():
     # sequences without keys: no work item, their output rows are listed for zero-filling
     sm = ops.SlotMap([5, 130, 7], "cpu", k_lens=[9, 0, 4])
     assert sm.keyless == [(5, 135)] and sm.n_items == 1
+
+
+def test_attention_build_slots_equals_the_python_tables():
+    from variantformer_b200 import _lib, ops
+    lib = _lib.load()
+    rng = np.random.default_rng(2)
+    for q_lens, k_lens in [(rng.integers(1, 700, 200), None), ([97] * 33, None), ([12663] * 3, [1024, 5, 300]),
+                           ([5, 130, 7, 0, 64], [9, 0, 4, 3, 1])]:
+        q = np.asarray(q_lens, np.int32); k = None if k_lens is None else np.asarray(k_lens, np.int32)
+        for pairing in (1, 0):
+            ops.PAIR_UNRELATED_TILES, saved = bool(pairing), ops.PAIR_UNRELATED_TILES
+            try:
+                want = ops.SlotMap(q, "cpu", k_lens=k).table.numpy()
+            finally:
+                ops.PAIR_UNRELATED_TILES = saved
+            n = lib.vf_attention_build_slots(q.ctypes.data, None if k is None else k.ctypes.data, len(q), pairing, None, 0)
+            assert n == want.shape[0]
+            got = np.zeros((n, 2, 8), np.int32)
+            assert lib.vf_attention_build_slots(q.ctypes.data, None if k is None else k.ctypes.data, len(q), pairing,
+                                                got.ctypes.data, n) == n
+            assert np.array_equal(got, want)

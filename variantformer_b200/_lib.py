@@ -19,6 +19,12 @@ _vp, _i32, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
 SIGNATURES = {
     "vf_last_error": ([], C.c_char_p),
     "vf_abi_version": ([], _i32),
+    "vf_launch_count": ([], C.c_ulonglong),
+    "vf_attention_build_slots": ([_vp, _vp, _i32, _i32, _vp, _i32], _i32),
+    "vf_seq2reg_workspace_bytes": ([_vp, _i64], _sz),
+    "vf_seq2reg_forward": ([_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _i32, _vp, _sz, _vp, _vp], _i32),
+    "vf_seq2gene_workspace_bytes": ([_vp, _vp], _sz),
+    "vf_seq2gene_forward": ([_vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp], _i32),
     "vf_device_check": ([_vp], _i32),
     "vf_gemm_bf16": ([_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _vp], _i32),
     "vf_gemm_bf16_ln": ([_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _i32, _vp, _i32,

@@ -6,6 +6,7 @@
 #include "vf_internal.h"
 
 namespace vf {
+unsigned long long g_launches = 0;
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -26,6 +27,7 @@ extern "C" {
 
 const char* vf_last_error(void) { return g_err; }
 int vf_abi_version(void) { return VF_B200_ABI_VERSION; }
+unsigned long long vf_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int vf_device_check(int* sm_count) {
     int dev = 0, major = 0, sms = 0;

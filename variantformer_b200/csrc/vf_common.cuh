@@ -23,10 +23,13 @@ int  cuda_fail(cudaError_t e, const char* what);
         cudaError_t e__ = (call);                                        \
         if (e__ != cudaSuccess) return ::vf::cuda_fail(e__, #call);      \
     } while (0)
+// every kernel launch of the library passes through here: g_launches is what vf_launch_count() reports
+extern unsigned long long g_launches;
 #define VF_LAUNCH_OK(what)                                               \
     do {                                                                 \
         cudaError_t e__ = cudaGetLastError();                            \
         if (e__ != cudaSuccess) return ::vf::cuda_fail(e__, what);       \
+        __atomic_add_fetch(&::vf::g_launches, 1ull, __ATOMIC_RELAXED);   \
     } while (0)
 #define VF_REQUIRE(cond, ...)                                            \
     do {                                                                 \

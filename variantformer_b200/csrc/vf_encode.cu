@@ -616,6 +616,7 @@ int bpe_tokenize(const uint8_t* seq, int64_t pitch, const int32_t* len, int n_wi
             at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
             VF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p, seg_cap));
+            VF_LAUNCH_OK("bpe_tokenize_cluster_kernel launch");
             return 0;
         };
         return cl == 16 ? launch(bpe_tokenize_cluster_kernel<16>, 16) : launch(bpe_tokenize_cluster_kernel<8>, 8);

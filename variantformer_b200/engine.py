@@ -33,6 +33,10 @@ from ._lib import EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GEGLU_BF16, EPI_BIAS_GEL
 from .utils.alibi import alibi_slopes
 
 NUM_REF_CRES = 9
+# "coarse" (default): the forward of a slab is three calls into the library (vf_seq2reg_forward x2, vf_seq2gene_forward)
+# with the layer loop in C++; "fine": one Python call per kernel — the same kernels in the same order, bit-identical
+# results; used when a launch profiler is attached (bench.py's per-kernel pass) and for A/B runs (VF_ENGINE=fine).
+COARSE = os.environ.get("VF_ENGINE", "coarse") != "fine"
 # run the CRE stack on its own CUDA stream, concurrently with the gene stack ("0": one stream, for A/B and debugging)
 CRE_STREAM = os.environ.get("VF_CRE_STREAM", "1") != "0"
 
@@ -153,6 +157,14 @@ class Seq2RegWeights:
         for l in range(self.L):
             p = f"{prefix}transformer_encoder.{l}."
             self.layers.append(seq2reg_layer_weights(sd, p, device))
+        self._abi = None
+
+    def abi(self):
+        """Weight-pointer table of vf_seq2reg_forward (built once; the ctypes arrays are kept alive here)."""
+        if self._abi is None:
+            from . import _abi
+            self._abi = _abi.seq2reg_table(self)
+        return self._abi[0]
 
 
 def seq2reg_layer_weights(sd, p, device):
@@ -203,6 +215,15 @@ class Seq2GeneWeights:
         self.h0 = _Linear(sd, p + "0", device); self.hn = _Norm(sd, p + "1", device); self.h4 = _Linear(sd, p + "4", device)
         self.h6_w = sd[p + "6.weight"].to(device=device, dtype=torch.float32).reshape(-1).contiguous()
         self.h6_b = sd[p + "6.bias"].to(device=device, dtype=torch.float32).contiguous()
+        self.token_dim = self.gene_map.w.shape[1]
+        self._abi = None
+
+    def abi(self):
+        """Weight-pointer table of vf_seq2gene_forward (built once; the ctypes arrays are kept alive here)."""
+        if self._abi is None:
+            from . import _abi
+            self._abi = _abi.seq2gene_table(self, self.token_dim)
+        return self._abi[0]
 
 
 class Engine:
@@ -224,6 +245,12 @@ class Engine:
         ws = self.ws
         n_win = tokens_i32.shape[0]
         n_tok = int(lens_host.sum())
+        if COARSE and ops.PROFILER is None and hasattr(W, "abi"):
+            import ctypes as C
+            from . import _lib
+            nbytes = int(_lib.lib().vf_seq2reg_workspace_bytes(C.addressof(W.abi()), n_tok))
+            return ops.seq2reg_forward(W.abi(), tokens_i32, mask_u8, cu, n_tok, plan.slots,
+                                       ws.get("coarse_r", (nbytes,), torch.uint8), W.d)
         ids, pos = ops.compact_tokens(tokens_i32, mask_u8, cu, n_tok)
         x = ops.embed_tokens(ids, pos, W.emb, W.pe)
         d, H, hd = W.d, W.H, W.hd
@@ -397,6 +424,8 @@ class Engine:
         # ---- stage 2: window encoders ----
         cre_pooled = self.seq2reg(self.cre_tok, s["ctok"], s["cmsk"], s["clens"], s["c_cu_tok"], s["c_plan_tok"])
         gene_pooled = self.seq2reg(self.gene_tok, s["gtok"], s["gmsk"], s["glens"], s["g_cu_tok"], s["g_plan_tok"])
+        if COARSE and ops.PROFILER is None and w.cre_map is not None:
+            return self._run_coarse(s, cre_pooled, gene_pooled)
         if w.cre_map is None:
             raise NotImplementedError("token_dim == emb_dim (no cre_map) is not wired on the B200 path")
         # Both streams are row-centred (see the module docstring): cx / gx hold x - pivot_r, cxb / gxb their bf16 mirrors.
@@ -499,6 +528,33 @@ class Engine:
         if "cre_pos_idx" in s:
             t, _ = ops.gather_rows(cx, None, s["cre_pos_idx"])
             out["cre_token_embedding"], _ = ops.uncenter_rows(t, cpiv, idx=s["cre_pos_idx"])
+        return out
+
+    def _run_coarse(self, s, cre_pooled, gene_pooled):
+        """Stages 3-4 of a prepared slab through vf_seq2gene_forward (layer loop in the library)."""
+        import ctypes as C
+        from . import _abi, _lib
+        w = self.w
+        if "_abi_slab" not in s:
+            tab = lambda k: (s[k].slots.table.data_ptr(), s[k].slots.n_items)
+            n_reg = s["reg_idx"].numel()
+            cpos = s.get("cre_pos_idx")
+            s["_abi_slab"] = _abi.Seq2GeneSlab(
+                int(s["C"].sum()), int(s["G"].sum()), s["Mg"], n_reg, s["n_need"], 0,
+                s["gene_idx"].data_ptr(), s["row_seq"].data_ptr(), s["logc"].data_ptr(), s["last_rows"].data_ptr(),
+                None if cpos is None else cpos.data_ptr(), *tab("plan_gself"), *tab("plan_gcross"), *tab("plan_cself"),
+                *tab("plan_last_self"), *tab("plan_last_cross"))
+        slab = s["_abi_slab"]
+        slab.single_stream = 0 if (CRE_STREAM and self.device.type == "cuda") else 1
+        nbytes = int(_lib.lib().vf_seq2gene_workspace_bytes(C.addressof(w.abi()), C.addressof(slab)))
+        pred, emb, gtok, ctok = ops.seq2gene_forward(w.abi(), slab, cre_pooled, gene_pooled,
+                                                     self.ws.get("coarse_g", (nbytes,), torch.uint8), slab.n_reg,
+                                                     slab.n_need - slab.n_reg, w.D, "cre_pos_idx" in s)
+        out = {"pred": pred, "emb": emb, "T": s["T"].tolist()}
+        if "gene_pos_idx" in s:
+            out["gene_token_embedding"] = gtok
+        if ctok is not None:
+            out["cre_token_embedding"] = ctok
         return out
 
     def forward_tokens(self, cre_tokens, cre_masks, gene_tokens, gene_masks, tissues, ref_labels, **kw):

@@ -154,6 +154,39 @@ def rowstats(x, stats=None, out_bf16=None):
     return stats
 
 
+def launch_count():
+    """Kernels launched by libvf_b200.so since it was loaded (counted inside the library)."""
+    return int(_lib.load().vf_launch_count())
+
+
+def seq2reg_forward(table, tokens_i32, pad_mask_u8, cu, n_tok, slots, workspace, d):
+    """Whole window encoder in one call (vf_seq2reg_forward): -> bf16 [n_win, d]."""
+    import ctypes as C
+    n_win, L = tokens_i32.shape
+    out = torch.empty((n_win, d), dtype=torch.bfloat16, device=tokens_i32.device)
+    with _timed("seq2reg_forward"):
+        check(_lib.lib().vf_seq2reg_forward(C.addressof(table), ptr(tokens_i32), ptr(pad_mask_u8), ptr(cu), n_win, L,
+                                            int(n_tok), ptr(slots.table), slots.n_items, ptr(workspace),
+                                            workspace.numel(), ptr(out), stream()))
+    return out
+
+
+def seq2gene_forward(table, slab, cre_pooled, gene_pooled, workspace, n_reg, n_tok_rows, D, want_cre_tok):
+    """Whole seq2gene forward of one slab in one call (vf_seq2gene_forward).
+    -> (pred fp32 [n_reg], emb fp32 [n_reg, D], gene token embeddings or None, CRE token embeddings or None)."""
+    import ctypes as C
+    dev = cre_pooled.device
+    pred = torch.empty(n_reg, dtype=torch.float32, device=dev)
+    emb = torch.empty((n_reg, D), dtype=torch.float32, device=dev)
+    gtok = torch.empty((n_tok_rows, D), dtype=torch.float32, device=dev) if n_tok_rows else None
+    ctok = torch.empty((n_reg, D), dtype=torch.float32, device=dev) if want_cre_tok else None
+    with _timed("seq2gene_forward"):
+        check(_lib.lib().vf_seq2gene_forward(C.addressof(table), C.addressof(slab), ptr(cre_pooled), ptr(gene_pooled),
+                                             ptr(workspace), workspace.numel(), ptr(pred), ptr(emb), ptr(gtok), ptr(ctok),
+                                             stream()))
+    return pred, emb, gtok, ctok
+
+
 def cu_seqlens(lens, device):
     cu = np.zeros(len(lens) + 1, np.int32)
     np.cumsum(np.asarray(lens, np.int64), out=cu[1:])
