@@ -301,14 +301,14 @@ class Bench:
         -> (milliseconds, fn's result, kernel launches, clocks sampled under load)."""
         torch = self.torch
         sampler = ClockSampler(self.local); sampler.start()
-        n0 = self.ops.LAUNCHES
+        n0 = self.ops.launch_count()                      # counted inside libvf_b200.so (vf_launch_count)
         self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         res = fn()
         e1.record()
         self.barrier()
-        return self.max_over_ranks(e0.elapsed_time(e1)), res, self.ops.LAUNCHES - n0, sampler.stop()
+        return self.max_over_ranks(e0.elapsed_time(e1)), res, self.ops.launch_count() - n0, sampler.stop()
 
     def time_wall(self, fn):
         self.barrier()

@@ -154,7 +154,6 @@ class HotPath:
                 item += 1
             writer.submit(idx, rows, buf["pred"][:n].numpy(), buf["emb"][:n * D].view(n, D).numpy(),
                           release=lambda b=buf: self._ring.release(b))
-        it = iter(todo)
         for (idx, genes), (pred, emb, err) in zip(todo, self.predict_pipelined((g for _, g in todo), variants, to_host=False)):
             n, D = pred.shape[0], emb.shape[1]
             buf = self._ring.acquire(n, D)               # blocks only if both buffers are still being written out
@@ -169,6 +168,7 @@ class HotPath:
             pending = (ev, idx, genes, buf, n, err)
         if pending is not None:
             flush(pending)
+        writer.flush()                                   # when this returns, every slab of the call is on disk
         return len(todo)
 
     def predict(self, genes, variants: SampleVariants = None, to_host=True):

@@ -72,6 +72,7 @@ class ResultWriter:
         while True:
             job = self._q.get()
             if job is None:
+                self._q.task_done()
                 return
             slab, rows, pred, emb, release = job
             try:
@@ -90,6 +91,13 @@ class ResultWriter:
             finally:
                 if release is not None:
                     release()
+                self._q.task_done()
+
+    def flush(self):
+        """Block until every submitted slab is on disk (or failed: the error is raised here)."""
+        self._q.join()
+        if self._err is not None:
+            raise self._err
 
     def close(self):
         self._q.put(None)
