@@ -124,3 +124,122 @@ def test_combined_modulator_forward():
     _ok(out[~gmask.to(DEV)], gx, "CombinedModulator gene output")
     _ok(gtok, torch.stack([gx[cu_g[0] + 5], gx[cu_g[1] + 0]]), "gene token embedding")
     _ok(ctok, torch.stack([cx[cu_c[0] + 149], cx[cu_c[1] + 7]]), "cre token embedding")
+
+
+# ---- layer variants the reference can build from other config flags (a16, a25) --------------------------
+def _init(module, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in module.named_parameters():
+            if n.endswith("norm1.weight") or n.endswith("norm2.weight") or n.endswith("norm3.weight"):
+                p.copy_(1 + 0.2 * torch.randn(p.shape, generator=g))
+            elif p.dim() >= 2:
+                p.copy_(torch.randn(p.shape, generator=g) / (p.shape[-1] ** 0.5))
+            else:
+                p.copy_(0.1 * torch.randn(p.shape, generator=g))
+    return {k: v.detach().clone().float().cpu() for k, v in module.state_dict().items()}
+
+
+def _ffn_tail(sd, p, x1, src, norm):
+    return O._geglu_ffn(O._Num(), sd, p, O._ln(sd, p + norm + ".", x1)) + src
+
+
+def test_self_only_and_cross_only_layer_variants():
+    from variantformer_b200.seq2gene.modules.layers import (ContextFlashCrossAttentionEncoderLayer,
+                                                            FlashAttentionEncoderLayer)
+    D, H = 384, 8
+    g = torch.Generator().manual_seed(5)
+    q_lens, k_lens = [130, 201, 7], [64, 300, 9]
+    B, S, Sc = 3, 201, 300
+    src = torch.randn(B, S, D, generator=g); ctx = torch.randn(B, Sc, D, generator=g)
+    qmask = torch.arange(S)[None, :] >= torch.tensor(q_lens)[:, None]
+    kmask = torch.arange(Sc)[None, :] >= torch.tensor(k_lens)[:, None]
+    cu_q = [0] + np.cumsum(q_lens).tolist(); cu_k = [0] + np.cumsum(k_lens).tolist()
+    num, slopes = O._Num(), O.alibi_slopes(H)
+    x = src[~qmask]
+    # FlashAttentionEncoderLayer (use_context=False CRE layers): self-attention + FFN(norm2); norm3 is never read
+    layer = FlashAttentionEncoderLayer(D, H, use_alibi=True)
+    sd = _init(layer, 1); layer = layer.to(DEV)
+    a = O._mha_self(num, sd, "mixer.MHA.", O._ln(sd, "norm1.", x), cu_q, H, slopes)
+    want = _ffn_tail(sd, "", a + x, x, "norm2")
+    out = layer(src.to(DEV), src_key_padding_mask=qmask.to(DEV))
+    _ok(out[~qmask.to(DEV)], want, "FlashAttentionEncoderLayer")
+    # ContextFlashCrossAttentionEncoderLayer (only_cross_attention gene layers), without and with cross ALiBi
+    for cross_alibi in (False, True):
+        layer = ContextFlashCrossAttentionEncoderLayer(D, H, use_alibi=True, cross_alibi=cross_alibi)
+        sd = _init(layer, 2 + cross_alibi); layer = layer.to(DEV)
+        xn = O._ln(sd, "norm1.", x)
+        n = xn.shape[0]
+        qq = F_linear(xn, sd, "crossMHA.MHA.Wq").view(n, H, D // H)
+        kv = F_linear(ctx[~kmask], sd, "crossMHA.MHA.Wkv").view(-1, 2, H, D // H)
+        o = O._attention(num, qq, kv[:, 0], kv[:, 1], cu_q, cu_k, slopes if cross_alibi else None).reshape(n, D)
+        c = F_linear(o, sd, "crossMHA.MHA.out_proj")
+        want = _ffn_tail(sd, "", c + x, x, "norm2")
+        out = layer(src.to(DEV), ctx.to(DEV), context_padding_mask=kmask.to(DEV), src_key_padding_mask=qmask.to(DEV))
+        _ok(out[~qmask.to(DEV)], want, f"ContextFlashCrossAttentionEncoderLayer cross_alibi={cross_alibi}")
+
+
+def F_linear(x, sd, name):
+    return torch.nn.functional.linear(x, sd[name + ".weight"], sd[name + ".bias"])
+
+
+def test_combined_modulator_other_flag_combinations():
+    """use_context=False (self-only CRE layers), only_cross_attention=True gene layers, use_res=True."""
+    from variantformer_b200.seq2gene.model_combined_modulator import CombinedModulator
+    D, H = 384, 8
+    mod = CombinedModulator(D, H, 2, True, 0.0, False, only_cross_attention=True, use_res=True)
+    sd = _init(mod, 7); mod = mod.to(DEV)
+    g = torch.Generator().manual_seed(6)
+    B, Sc, Sg = 2, 140, 33
+    c_lens, g_lens = [140, 20], [33, 5]
+    cre = torch.randn(B, Sc, D, generator=g); gene = torch.randn(B, Sg, D, generator=g)
+    cmask = torch.arange(Sc)[None, :] >= torch.tensor(c_lens)[:, None]
+    gmask = torch.arange(Sg)[None, :] >= torch.tensor(g_lens)[:, None]
+    out, _, _ = mod(cre.to(DEV), gene.to(DEV), cre_padding_mask=cmask.to(DEV), gene_padding_mask=gmask.to(DEV))
+    num, slopes = O._Num(), O.alibi_slopes(H)
+    cu_c = [0] + np.cumsum(c_lens).tolist(); cu_g = [0] + np.cumsum(g_lens).tolist()
+    cx, gx = cre[~cmask], gene[~gmask]
+    gres = gx.clone()
+
+    def gene_layer(i, gx, cx):
+        p = f"gene_layers.{i}."
+        xn = O._ln(sd, p + "norm1.", gx); n = xn.shape[0]
+        qq = F_linear(xn, sd, p + "crossMHA.MHA.Wq").view(n, H, D // H)
+        kv = F_linear(cx, sd, p + "crossMHA.MHA.Wkv").view(-1, 2, H, D // H)
+        o = O._attention(num, qq, kv[:, 0], kv[:, 1], cu_g, cu_c, None).reshape(n, D)
+        x1 = F_linear(o, sd, p + "crossMHA.MHA.out_proj") + gx
+        return _ffn_tail(sd, p, x1, gx, "norm2") + gres
+    gx = gene_layer(0, gx, cx)
+    a = O._mha_self(num, sd, "cre_layers.0.mixer.MHA.", O._ln(sd, "cre_layers.0.norm1.", cx), cu_c, H, slopes)
+    cx = _ffn_tail(sd, "cre_layers.0.", a + cx, cx, "norm2")
+    gx = gene_layer(1, gx, cx)
+    _ok(out[~gmask.to(DEV)], gx, "CombinedModulator(use_context=False, only_cross_attention, use_res)")
+
+
+@pytest.mark.parametrize("expand", [False, True])
+def test_seq2reg_with_label_context(expand):
+    """Seq2RegPredictor(use_context=True) (seq2reg/model.py:222-250): label embedding as cross-attention context."""
+    from variantformer_b200.seq2reg.model import Seq2RegPredictor
+    hp = dict(HP, use_context=True, expand_context=expand, token_length=200, num_layers=2)
+    model = Seq2RegPredictor(**hp)
+    sd = _init(model, 11 + expand); model = model.to(DEV)
+    g = torch.Generator().manual_seed(8)
+    b, L, d, H = 6, 200, hp["embedding_dim"], hp["num_heads"]
+    lens = [200, 97, 3, 150, 64, 1]
+    tok = torch.randint(4, 500, (b, 1, L), generator=g)
+    mask = (torch.arange(L)[None, :] >= torch.tensor(lens)[:, None])[:, None, :]
+    labels = torch.randint(0, 9, (b,), generator=g)
+    out = model(tok.to(DEV), mask.to(DEV), None, context=labels.to(DEV), only_embed=True)
+    assert out.shape == (b, 1, d)
+    num = O._Num()
+    keep = ~mask[:, 0]
+    cu = [0] + np.cumsum(lens).tolist()
+    x = sd["token_embedding.weight"][tok[:, 0]] + O.sinusoidal_pe(d, L)
+    ctx = sd["context_embedding.weight"][labels][:, None, :]
+    ctx = ctx * sd["expand_context.weight"].reshape(1, L, 1) + sd["expand_context.bias"].reshape(1, L, 1) if expand \
+        else ctx.expand(b, L, d)
+    x, ctx = x[keep], ctx[keep]
+    for l in range(2):
+        x = O._context_layer(num, sd, f"transformer_encoder.{l}.", x, cu, ctx, cu, H, None)
+    want = torch.stack([x[cu[i]:cu[i + 1]].mean(0) for i in range(b)])
+    _ok(out[:, 0], want, f"Seq2RegPredictor use_context expand={expand}")

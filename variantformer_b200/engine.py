@@ -167,9 +167,10 @@ class Seq2RegWeights:
         return self._abi[0]
 
 
-def seq2reg_layer_weights(sd, p, device):
-    """Device weights of one FlashTransformerLayer (seq2reg/modules.py:129-147), LayerNorms folded."""
-    return dict(qkv=_LnLinear(sd, p + "MHA.Wqkv", p + "norm1", device), out=_Linear(sd, p + "MHA.out_proj", device),
+def seq2reg_layer_weights(sd, p, device, mha="MHA."):
+    """Device weights of one FlashTransformerLayer (seq2reg/modules.py:129-147), LayerNorms folded.  mha="mixer.MHA.":
+    the same layer shape under seq2gene's names (FlashAttentionEncoderLayer, layers.py:166-228)."""
+    return dict(qkv=_LnLinear(sd, p + mha + "Wqkv", p + "norm1", device), out=_Linear(sd, p + mha + "out_proj", device),
                 g1=_LnLinear(sd, p + "linear_geglu_1", p + "norm2", device, geglu=True),
                 g2=_Linear(sd, p + "linear_geglu_2", device))
 
@@ -189,6 +190,14 @@ def context_layer_weights(sd, p, device, emb9=None):
         L["kv9"] = ops.gemm(emb9.contiguous(), L["kv"].w, EPI_BIAS_F32, bias=L["kv"].b)
         L["kv"] = None
     return L
+
+
+def cross_layer_weights(sd, p, device):
+    """Device weights of one ContextFlashCrossAttentionEncoderLayer (layers.py:231-265): cross-attention + GeGLU FFN."""
+    return dict(q=_LnLinear(sd, p + "crossMHA.MHA.Wq", p + "norm1", device), kv=_Linear(sd, p + "crossMHA.MHA.Wkv", device),
+                out2=_Linear(sd, p + "crossMHA.MHA.out_proj", device),
+                g1=_LnLinear(sd, p + "linear_geglu_1", p + "norm2", device, geglu=True),
+                g2=_Linear(sd, p + "linear_geglu_2", device))
 
 
 class Seq2GeneWeights:

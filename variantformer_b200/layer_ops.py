@@ -22,7 +22,8 @@ import torch
 
 from . import ops
 from ._lib import EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GEGLU_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32
-from .engine import (AttnPlan, Engine, Workspace, _Linear, _Norm, context_layer_weights, seq2reg_layer_weights)
+from .engine import (AttnPlan, Engine, Workspace, _Linear, _Norm, context_layer_weights, cross_layer_weights,
+                     seq2reg_layer_weights)
 
 
 def _require_cuda(t, what):
@@ -81,11 +82,13 @@ def _runner(ws, D):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def seq2reg_layer_forward(L, ws, nhead, slopes, src, src_key_padding_mask=None):
-    """FlashTransformerLayer.forward: x = MHA(LN1(src)) + src; out = FFN(LN2(x)) + src."""
+def seq2reg_layer_forward(L, ws, nhead, slopes, src, src_key_padding_mask=None, unpad_info=None):
+    """FlashTransformerLayer.forward / seq2gene FlashAttentionEncoderLayer.forward: x = MHA(LN1(src)) + src;
+    out = FFN(LN2(x)) + src (padded [B, S, d] with a mask, or unpadded [rows, d] with unpad_info)."""
     _require_cuda(src, "FlashTransformerLayer")
-    B, S, d = src.shape
-    lens, keep = _lens_from(src_key_padding_mask, None, B, S)
+    B, S = (src.shape[0], src.shape[1]) if src.dim() == 3 else (0, 0)
+    d = src.shape[-1]
+    lens, keep = _lens_from(src_key_padding_mask, unpad_info, B, S)
     x = _unpad(src, keep)
     n = x.shape[0]
     dev = x.device
@@ -104,8 +107,9 @@ def seq2reg_layer_forward(L, ws, nhead, slopes, src, src_key_padding_mask=None):
 
 
 def context_layer_forward(L, ws, D, nhead, slopes, src, context, src_key_padding_mask=None, context_padding_mask=None,
-                          unpad_info=None, context_unpad_info=None, gene_unpad_info=None):
-    """ContextFlashAttentionEncoderLayer.forward (layers.py:88-165) on padded [B, S, D] or unpadded [rows, D] input."""
+                          unpad_info=None, context_unpad_info=None, gene_unpad_info=None, cross_slopes=None):
+    """ContextFlashAttentionEncoderLayer.forward (layers.py:88-165) on padded [B, S, D] or unpadded [rows, D] input.
+    cross_slopes: ALiBi slopes of the cross-attention (cross_alibi=True: bias -slope |i + Sk - Sq - j|) or None."""
     _require_cuda(src, "ContextFlashAttentionEncoderLayer")
     src_info = gene_unpad_info if gene_unpad_info is not None else unpad_info
     if context_padding_mask is None and src_key_padding_mask is not None and context_unpad_info is None:
@@ -127,8 +131,35 @@ def context_layer_forward(L, ws, D, nhead, slopes, src, context, src_key_padding
         plan_self.run(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], nhead, hd, slopes, out)
 
     def cross_attn(q, out):
-        plan_cross.run(q, kv[:, :D], kv[:, D:], nhead, hd, None, out)
+        plan_cross.run(q, kv[:, :D], kv[:, D:], nhead, hd, cross_slopes, out)
     _runner(ws, D)._layer(L, x, xb, st0, n, self_attn, cross_attn, "m")
+    out, _ = ops.uncenter_rows(x, piv)
+    return _repad(out, keep, src).to(src.dtype)
+
+
+def cross_layer_forward(L, ws, D, nhead, cross_slopes, src, context, src_key_padding_mask=None, context_padding_mask=None,
+                        gene_unpad_info=None, context_unpad_info=None):
+    """ContextFlashCrossAttentionEncoderLayer.forward (layers.py:268-325): x = MHAcross(LN1(src), context) + src;
+    out = FFN(LN2(x)) + src.  cross_slopes: ALiBi slopes of the cross-attention (cross_alibi=True) or None."""
+    _require_cuda(src, "ContextFlashCrossAttentionEncoderLayer")
+    B, S = (src.shape[0], src.shape[1]) if src.dim() == 3 else (0, 0)
+    q_lens, keep = _lens_from(src_key_padding_mask, gene_unpad_info, B, S)
+    Bc, Sc = (context.shape[0], context.shape[1]) if context.dim() == 3 else (0, 0)
+    k_lens, ckeep = _lens_from(context_padding_mask, context_unpad_info, Bc, Sc)
+    assert len(q_lens) == len(k_lens), "src and context must hold the same number of sequences"
+    x = _unpad(src, keep)
+    ctx = ops.cast_bf16(_unpad(context, ckeep))
+    n, dev, hd = x.shape[0], x.device, D // nhead
+    xb = torch.empty((n, D), dtype=torch.bfloat16, device=dev)
+    piv, st0 = ops.center_rows(x, out_bf16=xb)
+    kv = ops.gemm(ctx, L["kv"].w, EPI_BIAS_BF16, bias=L["kv"].b)
+    q = ops.gemm(xb, L["q"].w, EPI_BIAS_BF16, bias=L["q"].b, ln=L["q"].ln(st0))
+    a = torch.empty((n, D), dtype=torch.bfloat16, device=dev)
+    AttnPlan(q_lens, dev, hd, k_lens=k_lens).run(q, kv[:, :D], kv[:, D:], nhead, hd, cross_slopes, a)
+    s1 = torch.empty((n, ops.stats_parts(D), 2), dtype=torch.float32, device=dev)
+    ops.gemm(a, L["out2"].w, EPI_BIAS_RESID_F32, bias=L["out2"].b, resid=x, out2=xb, stats_out=s1, mirror_only=True)
+    f = ops.gemm(xb, L["g1"].w, EPI_BIAS_GEGLU_BF16, bias=L["g1"].b, ln=L["g1"].ln(s1))
+    ops.gemm(f, L["g2"].w, EPI_BIAS_RESID_F32, bias=L["g2"].b, resid=x, out=x)
     out, _ = ops.uncenter_rows(x, piv)
     return _repad(out, keep, src).to(src.dtype)
 
@@ -152,17 +183,29 @@ def head_forward(W, g_exp):
 
 def combined_modulator_forward(mod, cre_x, gene_x, context=None, cre_padding_mask=None, gene_padding_mask=None,
                                context_padding_mask=None, cre_token_position=None, gene_token_position=None):
-    """CombinedModulator.forward (model_combined_modulator.py:137-328): gene_0(g, cre); for i: cre_i(cre, label
-    context); gene_{i+1}(g, cre) — on whatever batch the caller assembled (one CRE stream per batch row, no tissue
-    de-duplication: that is the engine's job).  -> (gene_out [B, Sg, D], gene_token_embedding, cre_token_embedding)."""
+    """CombinedModulator.forward (model_combined_modulator.py:137-328): gene_0(g, cre); for i: cre_i(cre[, label
+    context]); gene_{i+1}(g, cre) [+ gene_res when use_res] — on whatever batch the caller assembled (one CRE stream per
+    batch row, no tissue de-duplication: that is the engine's job).  Serves every layer variant the reference can
+    build: use_context (CRE layers with label cross-attention) or not, only_cross_attention gene layers, use_res,
+    cross_alibi.  -> (gene_out [B, Sg, D], gene_token_embedding, cre_token_embedding)."""
     B = cre_x.shape[0]
-    ctx_emb = mod.second_level_context_embedding.weight[context.long()]           # [B, Sc, D]
+    ctx_emb = None
+    if mod.use_context and context is not None:
+        ctx_emb = mod.second_level_context_embedding.weight[context.long()]       # [B, Sc, D]
     cmask = context_padding_mask if context_padding_mask is not None else cre_padding_mask
     g, c = gene_x, cre_x
-    g = mod.gene_layers[0](g, c, src_key_padding_mask=gene_padding_mask, context_padding_mask=cre_padding_mask)
+    gene_res = gene_x.clone() if mod.use_res else None
+
+    def gene_layer(i, g, c):
+        g = mod.gene_layers[i](g, c, src_key_padding_mask=gene_padding_mask, context_padding_mask=cre_padding_mask)
+        return g + gene_res if gene_res is not None else g
+    g = gene_layer(0, g, c)
     for i in range(mod.num_layers - 1):
-        c = mod.cre_layers[i](c, ctx_emb, src_key_padding_mask=cre_padding_mask, context_padding_mask=cmask)
-        g = mod.gene_layers[i + 1](g, c, src_key_padding_mask=gene_padding_mask, context_padding_mask=cre_padding_mask)
+        if mod.use_context:
+            c = mod.cre_layers[i](c, ctx_emb, src_key_padding_mask=cre_padding_mask, context_padding_mask=cmask)
+        else:
+            c = mod.cre_layers[i](c, src_key_padding_mask=cre_padding_mask)
+        g = gene_layer(i + 1, g, c)
     ar = torch.arange(B, device=g.device)
     zeros = torch.zeros(B, g.shape[2], device=g.device, dtype=g.dtype)
     gtok = g[ar, gene_token_position.long().reshape(-1)] if gene_token_position is not None else zeros
@@ -170,5 +213,6 @@ def combined_modulator_forward(mod, cre_x, gene_x, context=None, cre_padding_mas
     return g, gtok, ctok
 
 
-__all__ = ["seq2reg_layer_forward", "context_layer_forward", "head_forward", "combined_modulator_forward",
-           "seq2reg_layer_weights", "context_layer_weights", "head_weights", "Workspace", "_Cache"]
+__all__ = ["seq2reg_layer_forward", "context_layer_forward", "cross_layer_forward", "head_forward",
+           "combined_modulator_forward", "seq2reg_layer_weights", "context_layer_weights", "cross_layer_weights",
+           "head_weights", "Workspace", "_Cache"]

@@ -10,7 +10,8 @@ import torch.nn as nn
 
 from .._params import Affine, Table
 from ..utils.functions import precision2dtype
-from .modules.layers import ContextFlashAttentionEncoderLayer, MultiRegistry, TissueExpressionHeads
+from .modules.layers import (ContextFlashAttentionEncoderLayer, ContextFlashCrossAttentionEncoderLayer,
+                             FlashAttentionEncoderLayer, MultiRegistry, TissueExpressionHeads)
 
 logger = logging.getLogger(__name__)
 NUM_REF_CRES = 9
@@ -25,18 +26,35 @@ class CombinedModulator(nn.Module):
 
     def __init__(self, emb_dim, num_heads, num_layers, use_alibi, mlp_dout, use_context, num_ref_cres=None,
                  only_cross_attention=True, use_res=False, cross_alibi=False, flash_attn_3=False):
+        """Layer variants exactly as the reference builds them (model_combined_modulator.py:69-135): CRE layers with the
+        label cross-attention (use_context) or self-attention only; gene layers with self + cross attention or cross
+        attention only (only_cross_attention); use_res adds the gene input after every gene layer.  The batched engine
+        implements the vf_model.yaml combination (use_context, full gene layers, no use_res); the other combinations
+        run layer by layer through `forward`."""
         super().__init__()
-        if not use_context or only_cross_attention or use_res or cross_alibi or flash_attn_3:
-            raise NotImplementedError("only the vf_model.yaml variant (use_context, full gene layers, no use_res / "
-                                      "cross_alibi / flash_attn_3) is implemented on the B200 path")
-        assert num_ref_cres is not None, "num_ref_cres must be provided when use_context is True"
+        if flash_attn_3:
+            raise NotImplementedError("flash_attn_3=True is not implemented (the reference itself rejects it for cross attention)")
         self.emb_dim, self.num_heads, self.num_layers = emb_dim, num_heads, num_layers
-        self.use_context, self.only_cross_attention, self.use_res, self.cross_alibi = True, False, False, False
-        self.second_level_context_embedding = Table(num_ref_cres, emb_dim)
-        mk = lambda: ContextFlashAttentionEncoderLayer(d_model=emb_dim, nhead=num_heads, batch_first=True,
-                                                       use_alibi=use_alibi, mlp_dout=mlp_dout)
-        self.cre_layers = nn.ModuleList([mk() for _ in range(num_layers - 1)])
-        self.gene_layers = nn.ModuleList([mk() for _ in range(num_layers)])
+        self.use_context, self.only_cross_attention, self.use_res, self.cross_alibi = \
+            use_context, only_cross_attention, use_res, cross_alibi
+        if use_context:
+            assert num_ref_cres is not None, "num_ref_cres must be provided when use_context is True"
+            self.second_level_context_embedding = Table(num_ref_cres, emb_dim)
+            mk_cre = lambda: ContextFlashAttentionEncoderLayer(d_model=emb_dim, nhead=num_heads, batch_first=True,
+                                                               use_alibi=use_alibi, mlp_dout=mlp_dout)
+        else:
+            mk_cre = lambda: FlashAttentionEncoderLayer(d_model=emb_dim, nhead=num_heads, batch_first=True,
+                                                        use_alibi=use_alibi, mlp_dout=mlp_dout)
+        if only_cross_attention:
+            mk_gene = lambda: ContextFlashCrossAttentionEncoderLayer(d_model=emb_dim, nhead=num_heads, batch_first=True,
+                                                                     use_alibi=use_alibi, mlp_dout=mlp_dout,
+                                                                     cross_alibi=cross_alibi)
+        else:
+            mk_gene = lambda: ContextFlashAttentionEncoderLayer(d_model=emb_dim, nhead=num_heads, batch_first=True,
+                                                                use_alibi=use_alibi, mlp_dout=mlp_dout,
+                                                                cross_alibi=cross_alibi)
+        self.cre_layers = nn.ModuleList([mk_cre() for _ in range(num_layers - 1)])
+        self.gene_layers = nn.ModuleList([mk_gene() for _ in range(num_layers)])
 
     @torch.no_grad()
     def forward(self, cre_x, gene_x, context=None, cre_padding_mask=None, gene_padding_mask=None,
@@ -46,7 +64,8 @@ class CombinedModulator(nn.Module):
         gene_seq_len, emb_dim], gene_token_embedding, cre_token_embedding).  Layer by layer through the layers' own
         forwards; the batched engine (Seq2GenePredictorCombinedModulator.forward) is the fast path."""
         from ..layer_ops import combined_modulator_forward
-        assert context is not None, "context (reference cCRE labels) is required when use_context is True"
+        assert context is not None or not self.use_context, \
+            "context (reference cCRE labels) is required when use_context is True"
         return combined_modulator_forward(self, cre_x, gene_x, context, cre_padding_mask, gene_padding_mask,
                                           context_padding_mask, cre_token_position, gene_token_position)
 

@@ -6,7 +6,7 @@ import torch
 import torch.nn as nn
 
 from .._params import Affine, Table
-from .modules import FlashTransformerLayer
+from .modules import ContextFlashAttentionEncoderLayer, FlashTransformerLayer
 
 
 class _HParams(dict):
@@ -23,9 +23,6 @@ class Seq2RegPredictor(nn.Module):
         super().__init__()
         assert use_flash, "Only Flash is supported"                       # seq2reg/model.py:72
         assert positional_encoding in ("sinusoidal", "alibi"), "Position encoding must be either 'sinusoidal' or 'alibi'"
-        if use_context:
-            raise NotImplementedError("Seq2RegPredictor(use_context=True) is not on the B200 hot path "
-                                      "(both tokenizers of vf_model.yaml use use_context=False)")
         if seq_pool != "mean":
             raise NotImplementedError("only seq_pool='mean' is implemented")
         hp = dict(vocab_size=vocab_size, embedding_dim=embedding_dim, num_heads=num_heads, num_layers=num_layers,
@@ -36,9 +33,22 @@ class Seq2RegPredictor(nn.Module):
         self.hparams = _HParams(hp)
         self.token_embedding = Table(vocab_size, embedding_dim)
         self.pos_encoding_type = positional_encoding
-        self.transformer_encoder = nn.ModuleList(
-            [FlashTransformerLayer(embedding_dim, num_heads, use_alibi=(positional_encoding == "alibi"))
-             for _ in range(num_layers)])
+        use_alibi = positional_encoding == "alibi"
+        if use_context:
+            # seq2reg/model.py:93-121: label-context variant — a learned embedding per reference cCRE class, optionally
+            # expanded along the token axis by Linear(1, token_length); layers with a cross-attention to that context.
+            # Not the configured tokenizers (vf_model.yaml): runs layer by layer through the layers' own forwards.
+            from ..utils.constants import REF_CREs
+            self.context_embedding = Table(len(REF_CREs), embedding_dim)
+            self.expand_context_type = expand_context
+            if expand_context:
+                self.expand_context = Affine(token_length, 1)
+            self.transformer_encoder = nn.ModuleList(
+                [ContextFlashAttentionEncoderLayer(d_model=embedding_dim, nhead=num_heads, batch_first=True,
+                                                   use_alibi=use_alibi, mlp_dout=mlp_dout) for _ in range(num_layers)])
+        else:
+            self.transformer_encoder = nn.ModuleList(
+                [FlashTransformerLayer(embedding_dim, num_heads, use_alibi=use_alibi) for _ in range(num_layers)])
         out_dim = embedding_dim * 2 if strand_agg == "concat" else embedding_dim
         self.tissue_classifiers = nn.ModuleDict({str(t): Affine(num_classes, out_dim) for t in range(num_tissues)})
         self.use_context = use_context
@@ -69,6 +79,8 @@ class Seq2RegPredictor(nn.Module):
         Only `only_embed=True` (the inference hot path, model_combined_modulator.py:776-783) is implemented."""
         if not only_embed:
             raise NotImplementedError("tissue-classifier logits are a training-time output, outside the hot path")
+        if self.use_context:
+            return self._forward_with_context(x, padding_mask, context)
         from .. import ops
         from ..engine import AttnPlan, Engine
         W, ws = self._weights()
@@ -80,3 +92,32 @@ class Seq2RegPredictor(nn.Module):
         eng = Engine.__new__(Engine); eng.device = dev; eng.ws = ws
         pooled = eng.seq2reg(W, tok, msk, lens, ops.cu_seqlens(lens, dev), AttnPlan(lens, dev, W.hd))
         return pooled.float().view(b, s, -1)
+
+    @torch.no_grad()
+    def _forward_with_context(self, x, padding_mask, context):
+        """use_context=True (seq2reg/model.py:222-250): context int [batch] reference-cCRE class of every window."""
+        from .. import ops
+        from ..engine import sinusoidal_pe
+        assert context is not None, "context (reference cCRE class per window) is required when use_context is True"
+        b, s, L = x.shape
+        dev = self.token_embedding.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("Seq2RegPredictor runs on a B200 only: move the module to CUDA first (no CPU path)")
+        tok = x.reshape(b * s, L).to(dev).long()
+        mask = padding_mask.reshape(b * s, L).to(dev).bool()
+        h = self.token_embedding.weight[tok]
+        if self.pos_encoding_type == "sinusoidal":
+            h = h + sinusoidal_pe(h.shape[-1], L).to(dev)
+        ctx = self.context_embedding.weight[context.to(dev).long()]                    # [b, d]
+        ctx = ctx[:, None, :].expand(b, s, -1).reshape(b * s, 1, -1)
+        if self.expand_context_type:                                                     # Linear(1, token_length) per element
+            ctx = ctx * self.expand_context.weight.reshape(1, L, 1) + self.expand_context.bias.reshape(1, L, 1)
+        else:
+            ctx = ctx.expand(b * s, L, -1)
+        ctx = ctx.contiguous()
+        for layer in self.transformer_encoder:
+            h = layer(h, ctx, key_padding_mask=mask)
+        lens = (~mask).sum(1)
+        cu = ops.cu_seqlens(lens.cpu().numpy(), dev)
+        pooled = ops.masked_meanpool(h[~mask].float().contiguous(), cu, b * s, want_f32=True)[1]
+        return pooled.view(b, s, -1)
