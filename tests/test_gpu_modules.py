@@ -243,3 +243,38 @@ def test_seq2reg_with_label_context(expand):
         x = O._context_layer(num, sd, f"transformer_encoder.{l}.", x, cu, ctx, cu, H, None)
     want = torch.stack([x[cu[i]:cu[i + 1]].mean(0) for i in range(b)])
     _ok(out[:, 0], want, f"Seq2RegPredictor use_context expand={expand}")
+
+
+def test_generic_top_level_forward_agrees_with_the_engine_and_serves_other_variants():
+    """Seq2GenePredictorCombinedModulator._forward_generic restates the reference's forward (:540-720) module by module.
+    On the vf_model.yaml architecture it must agree with the batched engine (same kernels, different schedule: no tissue
+    de-duplication, padded batches); other gene_pooling / context flags must run through it."""
+    from tests.common import synth_batch
+    from variantformer_b200.seq2gene.model_combined_modulator import Seq2GenePredictorCombinedModulator, attach_trainer
+    from variantformer_b200.seq2reg.model import Seq2RegPredictor
+    sd = random_init.make_state_dict(CFG, HP, seed=21)
+    model = Seq2GenePredictorCombinedModulator(cre_tokenizer=Seq2RegPredictor(**HP), gene_tokenizer=Seq2RegPredictor(**HP), **CFG)
+    model.load_state_dict(sd); model.eval().to(DEV); attach_trainer(model)
+    batch = synth_batch(5, 2, [40, 150], [3, 5], [[62, 3], [7]])
+    args = (batch["cre_sequences"], batch["cre_attention_masks"], batch["tissue_context"], batch["ref_cre_labels"],
+            batch["strand_val"], batch["gene_embeddings"], batch["gene_attention_masks"])
+    assert model._engine_variant()
+    pred_e, _, emb_e, _, _ = model(*args, return_embedding=True)
+    pred_g, _, emb_g, _, _ = model._forward_generic(args[0], args[1], args[2], args[3], args[5], args[6], True)
+    rep = parity_report(emb_g.cpu().numpy(), emb_e.cpu().numpy())
+    assert rep["ok"], rep
+    assert torch.allclose(pred_g.cpu(), pred_e.cpu(), atol=2e-2, rtol=2e-2)
+    # another architecture: start token pooling, cross-attention-only gene layers, use_res, tissue context added to the CREs
+    cfg = dict(CFG, gene_pooling="start_token", only_cross_attention=True, use_res=True, add_context_to_cres=True, num_layers=2)
+    other = Seq2GenePredictorCombinedModulator(cre_tokenizer=Seq2RegPredictor(**HP), gene_tokenizer=Seq2RegPredictor(**HP), **cfg)
+    _init(other, 22); other.eval().to(DEV); attach_trainer(other)
+    assert not other._engine_variant()
+    pred, donors, emb, _, _ = other(*args, return_embedding=True)
+    assert pred.shape == (3, 1) and emb.shape == (3, CFG["emb_dim"]) and donors == [0, 1]
+    assert bool(torch.isfinite(pred).all()) and bool(torch.isfinite(emb).all())
+    assert (emb[0] - emb[1]).abs().max() > 0                    # the two tissues of gene 0 differ (AddContext)
+    mx = Seq2GenePredictorCombinedModulator(cre_tokenizer=Seq2RegPredictor(**HP), gene_tokenizer=Seq2RegPredictor(**HP),
+                                            **dict(CFG, gene_pooling="max", num_layers=2))
+    _init(mx, 23); mx.eval().to(DEV); attach_trainer(mx)
+    pred, _ = mx(*args)
+    assert pred.shape == (3, 1) and bool(torch.isfinite(pred).all())

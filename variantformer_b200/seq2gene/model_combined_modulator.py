@@ -10,8 +10,8 @@ import torch.nn as nn
 
 from .._params import Affine, Table
 from ..utils.functions import precision2dtype
-from .modules.layers import (ContextFlashAttentionEncoderLayer, ContextFlashCrossAttentionEncoderLayer,
-                             FlashAttentionEncoderLayer, MultiRegistry, TissueExpressionHeads)
+from .modules.layers import (AddContext, ContextFlashAttentionEncoderLayer, ContextFlashCrossAttentionEncoderLayer,
+                             FlashAttentionEncoderLayer, MultiRegistry, StartToken, TissueExpressionHeads)
 
 logger = logging.getLogger(__name__)
 NUM_REF_CRES = 9
@@ -80,16 +80,19 @@ class Seq2GenePredictorCombinedModulator(nn.Module):
         super().__init__()
         assert gene_pooling in ["mean", "max", "start_token", "multi_registry"], \
             "gene_pooling must be one of mean, max, start_token, or multi_registry"
-        if gene_pooling != "multi_registry":
-            raise NotImplementedError("only gene_pooling='multi_registry' (vf_model.yaml) is implemented")
-        if kwargs.get("add_context_to_cres", False):
-            raise NotImplementedError("add_context_to_cres=True is not implemented")
+        if gene_pooling == "mean":
+            # the reference's own 'mean' branch never reduces over the sequence axis (pool_outputs :372-377 returns a
+            # [batch, seq, emb] tensor that the head cannot consume): there is no behaviour to reproduce
+            raise NotImplementedError("gene_pooling='mean' is broken upstream (pool_outputs does not reduce); not implemented")
         self.hparams = _HParams(dict(num_tissues=num_tissues, emb_dim=emb_dim, gene_emb_dim=gene_emb_dim,
                                      num_heads=num_heads, num_layers=num_layers, use_alibi=use_alibi, mlp_dout=mlp_dout,
                                      use_context=use_context, token_dim=token_dim, gene_pooling=gene_pooling, **kwargs))
         self.precision = None
         self.gene_pooling = gene_pooling
-        self.start_tkn = MultiRegistry(num_tissues, emb_dim)
+        self.start_tkn = (MultiRegistry(num_tissues, emb_dim) if gene_pooling == "multi_registry" else
+                          StartToken(emb_dim) if gene_pooling == "start_token" else None)
+        self.add_context_to_cres = kwargs.get("add_context_to_cres", False)
+        self.add_context = AddContext(num_tissues, emb_dim) if self.add_context_to_cres else None
         self.cre_tokenizer, self.gene_tokenizer = cre_tokenizer, gene_tokenizer
         self.emb_dim, self.use_context, self.tissues = emb_dim, use_context, tissues
         self.use_res = kwargs.get("use_res", False)
@@ -151,6 +154,9 @@ class Seq2GenePredictorCombinedModulator(nn.Module):
         cre_context: list of ref-cCRE label ids [C_i].  -> (pred [sum T,1], donors[, emb [sum T, D], gene_token_emb,
         cre_token_emb]) exactly like the reference (:705-720)."""
         self._check_precision()
+        if not self._engine_variant():
+            return self._forward_generic(inp, attention_mask, tissue_vector, cre_context, gene_embedding, gene_att_mask,
+                                         return_embedding, **kwargs)
         sq = lambda xs: [x[:, 0, :] if x.dim() == 3 else x for x in xs]
         cpos, gpos = kwargs.get("cre_token_position"), kwargs.get("gene_token_position")
         out = self.engine().forward_tokens(
@@ -166,6 +172,90 @@ class Seq2GenePredictorCombinedModulator(nn.Module):
             return pred, donors
         zeros = lambda: torch.zeros(emb.shape[0], emb.shape[1], device=emb.device)
         return (pred, donors, emb, out.get("gene_token_embedding", zeros()), out.get("cre_token_embedding", zeros()))
+
+    def _engine_variant(self):
+        """True for the architecture the batched engine implements (configs/vf_model.yaml): label-context CRE layers, full
+        gene layers, per-tissue registry token, shared bigger head, no use_res / cross_alibi / add_context_to_cres."""
+        cm = self.combined_modulator
+        return (self.gene_pooling == "multi_registry" and cm.use_context and not cm.only_cross_attention and
+                not cm.use_res and not cm.cross_alibi and not self.add_context_to_cres and
+                not self.cre_tokenizer.use_context and not self.gene_tokenizer.use_context)
+
+    @torch.no_grad()
+    def _forward_generic(self, inp, attention_mask, tissue_vector, cre_context, gene_embedding, gene_att_mask,
+                         return_embedding=False, **kwargs):
+        """The reference's forward (model_combined_modulator.py:540-720) step by step for the configurations the batched
+        engine does not cover (gene_pooling start_token / max, add_context_to_cres, only_cross_attention, use_res,
+        use_context=False, cross_alibi): window encoders, cre_map / gene_map, per-tissue replication, AddContext,
+        prepare_input, CombinedModulator.forward, pool_outputs, head — every layer through the modules' own forwards
+        (same kernels).  No tissue de-duplication here: this path serves correctness, not the benchmark."""
+        from .. import ops
+        from .._lib import EPI_BIAS_F32
+        dev = self.gene_map.weight.device
+        D = self.emb_dim
+
+        def encode(tok_list, mask_list, labels, tokenizer):
+            """-> padded [n_items, max_windows, d], mask [n_items, max_windows] (True = pad)"""
+            embs = []
+            for i, (t, m) in enumerate(zip(tok_list, mask_list)):
+                t = t if t.dim() == 3 else t[:, None, :]
+                m = m if m.dim() == 3 else m[:, None, :]
+                ctx = None if labels is None else torch.as_tensor(labels[i]).to(dev)
+                embs.append(tokenizer(t.to(dev), m.to(dev), None, context=ctx, only_embed=True)[:, 0, :])
+            n = max(e.shape[0] for e in embs)
+            x = torch.zeros(len(embs), n, embs[0].shape[1], device=dev)
+            mask = torch.ones(len(embs), n, dtype=torch.bool, device=dev)
+            for i, e in enumerate(embs):
+                x[i, :e.shape[0]] = e; mask[i, :e.shape[0]] = False
+            return x, mask
+
+        def linear(x, lin):
+            y = ops.gemm(ops.cast_bf16(x.reshape(-1, x.shape[-1]).float().contiguous()),
+                         lin.weight.to(torch.bfloat16).contiguous(), EPI_BIAS_F32, bias=lin.bias.float().contiguous())
+            return y.view(*x.shape[:-1], -1)
+        cre_labels = list(cre_context) if self.cre_tokenizer.use_context else None
+        x, mask_c = encode(inp, attention_mask, cre_labels, self.cre_tokenizer)
+        gene_labels = [torch.zeros(g.shape[0], dtype=torch.long) for g in gene_embedding] \
+            if self.gene_tokenizer.use_context else None
+        xg, mask_g = encode(gene_embedding, gene_att_mask, gene_labels, self.gene_tokenizer)
+        n_c = x.shape[1]
+        context = torch.zeros(len(inp), n_c, dtype=torch.long, device=dev)
+        for i, c in enumerate(cre_context):
+            context[i, :len(c)] = torch.as_tensor(c).to(dev).long()
+        if x.shape[-1] != D:
+            x = linear(x, self.cre_map)
+        xg = linear(xg, self.gene_map)
+        T = [len(t) for t in tissue_vector]
+        rep = torch.repeat_interleave(torch.arange(len(T), device=dev), torch.tensor(T, device=dev))
+        x, mask_c, context, xg, mask_g = x[rep], mask_c[rep], context[rep], xg[rep], mask_g[rep]
+        tv = torch.cat([torch.as_tensor(t).reshape(-1) for t in tissue_vector]).to(dev).long()[:, None]
+        cpos, gpos = kwargs.get("cre_token_position"), kwargs.get("gene_token_position")
+        rp = lambda p: None if p is None else torch.repeat_interleave(
+            torch.as_tensor([int(v) for v in p], device=dev), torch.tensor(T, device=dev))
+        cpos, gpos = rp(cpos), rp(gpos)
+        if gpos is not None and self.start_tkn is not None:
+            gpos = gpos + 1
+        if self.add_context_to_cres:
+            x = self.add_context(x, tv)
+        g = xg
+        if self.gene_pooling == "start_token":
+            g = torch.cat((self.start_tkn(g), g), dim=1)
+        elif self.gene_pooling == "multi_registry":
+            g, _ = self.start_tkn(g, tv)
+        if self.start_tkn is not None:
+            mask_g = torch.cat((torch.zeros(mask_g.shape[0], 1, dtype=torch.bool, device=dev), mask_g), dim=1)
+        g, gtok, ctok = self.combined_modulator(cre_x=x, gene_x=g, context=context, cre_padding_mask=mask_c,
+                                                gene_padding_mask=mask_g, context_padding_mask=mask_c,
+                                                cre_token_position=cpos, gene_token_position=gpos)
+        if self.gene_pooling == "max":
+            g = g.masked_fill(mask_g[:, :, None], float("-inf")).max(dim=1).values
+        else:
+            g = g[:, 0, :]
+        donors = list(range(len(inp)))
+        if kwargs.get("only_embedding", False):
+            return {"embedding": g, "donors": donors}
+        pred = self.tissue_heads(g.contiguous(), tv)
+        return (pred, donors, g, gtok, ctok) if return_embedding else (pred, donors)
 
     def predict_step(self, batch, batch_idx, dataloader_idx=None):
         """:857-907 — one batch of genes -> per-gene numpy predictions and registry-token embeddings."""
