@@ -29,7 +29,10 @@ def _describe_mismatch(got, want, tol):
 
 
 GEMM_SHAPES = [(128, 256, 64), (128, 256, 512), (300, 576, 192), (9, 3072, 1536), (1000, 512, 1024),
-               (4096, 4608, 1536), (12663, 1536, 1536), (777, 1536, 512)]
+               (4096, 4608, 1536), (12663, 1536, 1536), (777, 1536, 512),
+               # M >= 4096: the residual epilogue runs as the split (reader / writer warp pairs) kernel — single CTA (K < 1024)
+               # and CTA pair, a ragged last row block, N that leaves slabs of the last column tile empty
+               (5001, 512, 512), (4500, 576, 192), (20000, 1536, 1024), (4097, 328, 1024)]
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
@@ -87,7 +90,8 @@ def test_gemm_inplace_residual_and_strided_output():
     assert big[:, :N].abs().max() == 0 and big[:, 2 * N:].abs().max() == 0
 
 
-@pytest.mark.parametrize("M,N,K", [(300, 512, 512), (1000, 1536, 1536), (4099, 4608, 1536), (77, 256, 192)])
+@pytest.mark.parametrize("M,N,K", [(300, 512, 512), (1000, 1536, 1536), (4099, 4608, 1536), (77, 256, 192), (9000, 512, 512),
+                                   (4200, 1536, 1024)])
 def test_gemm_stats_out_and_layernorm_fold(M, N, K):
     """The epilogue of an fp32 GEMM accumulates each output row's (sum, sum of squares); a following GEMM on the bf16
     mirror with gamma/beta folded into W/bias reproduces Linear(LayerNorm(x)) (layers.py:116-163)."""
