@@ -37,6 +37,11 @@ NUM_REF_CRES = 9
 # with the layer loop in C++; "fine": one Python call per kernel — the same kernels in the same order, bit-identical
 # results; used when a launch profiler is attached (bench.py's per-kernel pass) and for A/B runs (VF_ENGINE=fine).
 COARSE = os.environ.get("VF_ENGINE", "coarse") != "fine"
+# x1 = x + MHA(..) exists only as a bf16 mirror (its consumers are a LayerNorm-folded GEMM and the next residual add), so
+# the out_proj epilogue may read its residual from the bf16 mirror of x instead of the fp32 stream: half the residual
+# bytes of the most HBM-bound GEMMs of the layer.  The fp32 stream itself is untouched (the layer's own residual add reads
+# it in full precision).  VF_RESID16_OUTPROJ=0: fp32 residual there too (A/B).
+OUT_PROJ_RESID16 = os.environ.get("VF_RESID16_OUTPROJ", "1") != "0"
 # run the CRE stack on its own CUDA stream, concurrently with the gene stack ("0": one stream, for A/B and debugging)
 CRE_STREAM = os.environ.get("VF_CRE_STREAM", "1") != "0"
 
@@ -281,7 +286,8 @@ class Engine:
             plan.run(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], H, hd, W.slopes, a)
             # x1 = x + MHA(..) is consumed only through norm2 -> linear_geglu_1 (the layer's residual is its INPUT,
             # modules.py:189): it exists as a bf16 mirror + row statistics only
-            ops.gemm(a, L["out"].w, EPI_BIAS_RESID_F32, bias=L["out"].b, resid=x, out2=xb, stats_out=s1, mirror_only=True)
+            ops.gemm(a, L["out"].w, EPI_BIAS_RESID_F32, bias=L["out"].b, resid=xb if OUT_PROJ_RESID16 else x, out2=xb,
+                     stats_out=s1, mirror_only=True)
             ops.gemm(xb, L["g1"].w, EPI_BIAS_GEGLU_BF16, bias=L["g1"].b, out=f, ln=L["g1"].ln(s1))      # GeGLU(norm2(x1))
             ops.gemm(f, L["g2"].w, EPI_BIAS_RESID_F32, bias=L["g2"].b, resid=x, out=x, out2=xb, stats_out=xs)  # + layer input
         return ops.masked_meanpool(x, cu, n_win, pivot=piv)
@@ -301,7 +307,8 @@ class Engine:
         self_attn(qkv, a)
         # x1 = x + selfMHA(..) and x1' = x1 + crossMHA(..) are consumed only through norm2 / norm3 -> bf16 GEMM and as
         # each other's residual (the layer's own residual is its INPUT, layers.py:163): bf16 mirror + statistics only
-        ops.gemm(a, L["out"].w, EPI_BIAS_RESID_F32, bias=L["out"].b, resid=x, out2=hb, stats_out=s1, mirror_only=True)
+        ops.gemm(a, L["out"].w, EPI_BIAS_RESID_F32, bias=L["out"].b, resid=xb if OUT_PROJ_RESID16 else x, out2=hb,
+                 stats_out=s1, mirror_only=True)
         q = qkv[:, :D]                                                  # reuse the qkv buffer for the cross query
         ops.gemm(hb, L["q"].w, EPI_BIAS_BF16, bias=L["q"].b, out=q, ln=L["q"].ln(s1))                  # Wq(norm2(x1))
         cross_attn(q, a)
@@ -332,7 +339,8 @@ class Engine:
         s["plan_last_self"].run(q, kvs[:, :D], kvs[:, D:], H, hd, w.slopes, a)
         hb = torch.empty((R, D), dtype=torch.bfloat16, device=x.device)
         s1 = torch.empty((R, ops.stats_parts(D), 2), dtype=torch.float32, device=x.device)
-        ops.gemm(a, L["out"].w, EPI_BIAS_RESID_F32, bias=L["out"].b, resid=xR, out2=hb, stats_out=s1, mirror_only=True)
+        ops.gemm(a, L["out"].w, EPI_BIAS_RESID_F32, bias=L["out"].b, resid=xbR if OUT_PROJ_RESID16 else xR, out2=hb,
+                 stats_out=s1, mirror_only=True)
         ops.gemm(hb, L["q"].w, EPI_BIAS_BF16, bias=L["q"].b, out=q, ln=L["q"].ln(s1))
         s["plan_last_cross"].run(q, kv[:, :D], kv[:, D:], H, hd, None, a)
         ops.gemm(a, L["out2"].w, EPI_BIAS_RESID_F32, bias=L["out2"].b, resid=hb, out2=hb, stats_out=s1, mirror_only=True)
