@@ -157,6 +157,20 @@ int vf_head_out(const void* h_bf16, int ldh, const float* w, const float* b, int
                 float* out, void* stream);
 int vf_cast_f32_to_bf16(const float* x, void* y_bf16, size_t n, void* stream);
 
+/*
+ * Gradient-boosted forest inference on embeddings — the AD-risk head.  Replaces treelite.gtil.predict per (gene, tissue)
+ * row (processors/ad_risk.py:41-52, 157-176).  x fp32 [n_rows, d]; row_forest int32 [n_rows] = forest of every row;
+ * forest_tree_off int32 [n_forests + 1] = range of the forest's trees in tree_root; forest_base fp32 [n_forests] = raw
+ * score offset; tree_root int32 [n_trees] = root node of every tree; nodes (SoA over all forests): node_feat int32 (-1 =
+ * leaf; bit 31 set on a split = missing values go left), node_thr fp32, node_left / node_right int32 (absolute node
+ * indices), node_value fp32 (leaf contribution, learning rate folded in).  op_lt: 0 = "x <= thr goes left" (sklearn,
+ * treelite "<="), 1 = "x < thr" (xgboost).  out fp32 [n_rows] = sigmoid(base + sum of leaf values) = P(class 1).
+ */
+int vf_forest_predict(const float* x, int ldx, int n_rows, int d, const int32_t* row_forest, const int32_t* forest_tree_off,
+                      const float* forest_base, const int32_t* tree_root, const int32_t* node_feat, const float* node_thr,
+                      const int32_t* node_left, const int32_t* node_right, const float* node_value, int op_lt, float* out,
+                      void* stream);
+
 /* ---- stage 1: genotype -> IUPAC sequence -> BPE-500 tokens (integer work, bit-exact) -------------- */
 /*
  * Per window w: slice [w0,w1) of the chromosome starting at genome + win_base[w], apply the sample's

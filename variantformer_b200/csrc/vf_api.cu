@@ -101,6 +101,13 @@ int vf_head_out(const void* h_bf16, int ldh, const float* w, const float* b, int
 int vf_cast_f32_to_bf16(const float* x, void* y_bf16, size_t n, void* stream) {
     return cast_f32_to_bf16(x, y_bf16, n, ST(stream));
 }
+int vf_forest_predict(const float* x, int ldx, int n_rows, int d, const int32_t* row_forest, const int32_t* forest_tree_off,
+                      const float* forest_base, const int32_t* tree_root, const int32_t* node_feat, const float* node_thr,
+                      const int32_t* node_left, const int32_t* node_right, const float* node_value, int op_lt, float* out,
+                      void* stream) {
+    return forest_predict(x, ldx, n_rows, d, row_forest, forest_tree_off, forest_base, tree_root, node_feat, node_thr,
+                          node_left, node_right, node_value, op_lt, out, ST(stream));
+}
 int vf_encode_windows(const uint8_t* genome, const int64_t* win_base, const int32_t* w0, const int32_t* w1,
                       const int32_t* var_lo, const int32_t* var_hi, const uint8_t* flags, const int32_t* v_pos,
                       const int32_t* v_ref_len, const int32_t* v_alt_off, const int32_t* v_alt_len, const uint8_t* v_gt,

@@ -526,4 +526,64 @@ int cast_f32_to_bf16(const float* x, void* y, size_t n, cudaStream_t s) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------
+// Gradient-boosted forest inference on embeddings: the AD-risk head (processors/ad_risk.py:41-52, 157-176 evaluates one
+// treelite GBDT per (gene, tissue) on the 1536-d registry embedding with treelite.gtil.predict, one Python call per row).
+// Here every row picks its forest; one warp per row: the row is staged in shared memory, lane l walks trees l, l + 32,
+// ... of the row's forest (nodes: split feature or -1 for a leaf, threshold, children, leaf value), the leaf values are
+// summed over the warp and squashed: p = sigmoid(base + sum).  Split rule x[feature] <= threshold goes left (sklearn /
+// treelite "<="; op_lt != 0: strict "<", the xgboost convention); NaN goes to `default_left`'s side (bit 31 of feat).
+// ---------------------------------------------------------------------------------
+constexpr int kForestWarps = 8;
+__global__ void __launch_bounds__(kForestWarps * 32)
+forest_predict_kernel(const float* __restrict__ x, int ldx, int n_rows, int d, const int* __restrict__ row_forest,
+                      const int* __restrict__ forest_tree_off, const float* __restrict__ forest_base,
+                      const int* __restrict__ tree_root, const int* __restrict__ node_feat,
+                      const float* __restrict__ node_thr, const int* __restrict__ node_left,
+                      const int* __restrict__ node_right, const float* __restrict__ node_value, int op_lt,
+                      float* __restrict__ out) {
+    extern __shared__ float s_row[];                          // kForestWarps x d
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kForestWarps + warp;
+    if (row >= n_rows) return;
+    float* xr = s_row + (size_t)warp * d;
+    for (int c = lane; c < d; c += 32) xr[c] = x[(size_t)row * ldx + c];
+    __syncwarp();
+    const int f = row_forest[row];
+    const int t0 = forest_tree_off[f], t1 = forest_tree_off[f + 1];
+    float acc = 0.f;
+    for (int t = t0 + lane; t < t1; t += 32) {
+        int n = tree_root[t];
+        for (int depth = 0; depth < 64; ++depth) {            // (bounded: a malformed table cannot hang the GPU)
+            const int ft = node_feat[n];
+            if (ft == -1) break;
+            const float v = xr[ft & 0x7fffffff], thr = node_thr[n];
+            const bool left = (v != v) ? (ft < 0) : (op_lt ? v < thr : v <= thr);
+            n = left ? node_left[n] : node_right[n];
+        }
+        acc += node_value[n];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[row] = 1.0f / (1.0f + __expf(-(forest_base[f] + acc)));
+}
+
+int forest_predict(const float* x, int ldx, int n_rows, int d, const int* row_forest, const int* forest_tree_off,
+                   const float* forest_base, const int* tree_root, const int* node_feat, const float* node_thr,
+                   const int* node_left, const int* node_right, const float* node_value, int op_lt, float* out,
+                   cudaStream_t s) {
+    if (n_rows == 0) return 0;
+    const size_t smem = (size_t)kForestWarps * d * sizeof(float);
+    VF_REQUIRE(d > 0 && smem <= 200 * 1024, "forest_predict: %d features do not fit the row staging buffer", d);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        VF_CUDA_OK(cudaFuncSetAttribute(forest_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    forest_predict_kernel<<<(n_rows + kForestWarps - 1) / kForestWarps, kForestWarps * 32, smem, s>>>(
+        x, ldx, n_rows, d, row_forest, forest_tree_off, forest_base, tree_root, node_feat, node_thr, node_left, node_right,
+        node_value, op_lt, out);
+    VF_LAUNCH_OK("forest_predict_kernel launch");
+    return 0;
+}
+
 }  // namespace vf

@@ -36,6 +36,10 @@ int label_attention(const void* q, int ldq, const float* kv9, const float* logc,
 int head_out(const void* h, int ldh, const float* w, const float* b, int n_rows, int d, int softplus, float* out,
              cudaStream_t s);
 int cast_f32_to_bf16(const float* x, void* y, size_t n, cudaStream_t s);
+int forest_predict(const float* x, int ldx, int n_rows, int d, const int* row_forest, const int* forest_tree_off,
+                   const float* forest_base, const int* tree_root, const int* node_feat, const float* node_thr,
+                   const int* node_left, const int* node_right, const float* node_value, int op_lt, float* out,
+                   cudaStream_t s);
 
 int encode_windows(const uint8_t* genome, const int64_t* win_base, const int32_t* w0, const int32_t* w1,
                    const int32_t* var_lo, const int32_t* var_hi, const uint8_t* flags, const int32_t* v_pos,

@@ -405,6 +405,21 @@ def cast_bf16(x):
     return y
 
 
+def forest_predict(x, row_forest, forest, out=None):
+    """P(class 1) of every row of x fp32 [n, d] under its gradient-boosted forest (vf_forest_predict).
+    forest: dict of device tensors tree_off, base, tree_root, feat, thr, left, right, value (+ op_lt int)."""
+    assert x.dtype == torch.float32 and x.stride(1) == 1 and row_forest.dtype == torch.int32
+    n, d = x.shape
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32, device=x.device)
+    f = forest
+    with _timed("forest"):
+        check(_lib.lib().vf_forest_predict(ptr(x), x.stride(0), n, d, ptr(row_forest), ptr(f["tree_off"]), ptr(f["base"]),
+                                           ptr(f["tree_root"]), ptr(f["feat"]), ptr(f["thr"]), ptr(f["left"]),
+                                           ptr(f["right"]), ptr(f["value"]), int(f.get("op_lt", 0)), ptr(out), stream()))
+    return out
+
+
 # ---- stage 1 -------------------------------------------------------------------------------
 def encode_windows(genome, win_base, w0, w1, var_lo, var_hi, flags, variants, max_window, pitch):
     """variants: dict of device tensors pos/ref_len/alt_off/alt_len (int32), gt (uint8), alt_pool (uint8)."""
