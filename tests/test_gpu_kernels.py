@@ -364,6 +364,32 @@ def test_mc_tail_rows_and_keyless_sequences_do_not_leak():
     assert torch.allclose(out[234:].float(), want[234:], atol=2e-2, rtol=2e-2)
 
 
+def test_mc_output_of_a_sequence_does_not_depend_on_its_neighbours():
+    """Batching invariance down to the bit: the rows of a tile past a sequence's last query row belong to whatever
+    follows it in the q tensor; they must not influence the live rows (they once voted on the lazy raise of the
+    reference maximum, which changes the bf16 rounding of the probabilities — found by the 8-rank gather check)."""
+    H, hd = 4, 48
+    d = H * hd
+    g = torch.Generator(device="cpu").manual_seed(31)
+    la, lb = 201, 333
+    qa = (torch.randn(la, d, generator=g) * 2).to(DEV).bfloat16()
+    ka = (torch.randn(la, d, generator=g) * 2 * torch.linspace(0.3, 2.5, la)[:, None]).to(DEV).bfloat16()   # scores grow
+    va = torch.randn(la, d, generator=g).to(DEV).bfloat16()
+    slopes = torch.tensor([2 ** (-8 * (h + 1) / H) for h in range(H)], device=DEV)
+    outs = []
+    for scale in (0.1, 30.0):                         # a tame and a wild neighbour behind sequence A
+        qb = (torch.randn(lb, d, generator=g) * scale).to(DEV).bfloat16()
+        kb = (torch.randn(lb, d, generator=g) * scale).to(DEV).bfloat16()
+        vb = torch.randn(lb, d, generator=g).to(DEV).bfloat16()
+        q, k, v = torch.cat([qa, qb]), torch.cat([ka, kb]), torch.cat([va, vb])
+        outs.append(ops.attention_mc(q, k, v, ops.SlotMap([la, lb], DEV), H, hd, slopes)[:la].clone())
+    alone = ops.attention_mc(qa, ka, va, ops.SlotMap([la], DEV), H, hd, slopes)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], alone)
+    want = _ref_attention(qa, ka, va, [la], [la], H, hd, slopes)
+    assert torch.allclose(alone.float(), want, atol=3e-2, rtol=3e-2)
+
+
 def test_mc_large_scores_raise_the_lazy_maximum():
     """Scores that grow along the key axis force the reference maximum to be raised (O rescaled in TMEM) many times."""
     H, hd, lens = 4, 48, [700, 130]

@@ -191,14 +191,17 @@ __device__ __forceinline__ float exponents(uint32_t (&r)[64], float scale, float
 template <int HD, int KIND, bool PRESWZ>
 __device__ __forceinline__ void softmax_rest(uint32_t (&r)[64], float mx, float base, float scale, int nvalid,
                                              uint32_t o_addr, bool first, SmemBar p_empty_bar, uint32_t p_empty_parity,
-                                             float& m_ref, float& l, uint32_t p_row, int row) {
+                                             float& m_ref, float& l, uint32_t p_row, int row, bool live) {
     // The PV of this slot's previous step is the last reader of the P buffer and the last writer of O_s.  It was issued
     // at the end of the previous tile, so waiting for it HERE (before the exponentials) can stall every softmax warp
     // of the slot; only a raise of the reference maximum needs it this early (it rescales O_s).  The common path
     // takes the exponentials first, packed into the registers the scores occupied, and waits right before the stores.
     bool waited = false;
     float delta = 0.f;
-    if (first || __any_sync(0xffffffffu, mx > kLazyThreshold)) {
+    // Only LIVE rows vote: the rows of a tile past the sequence's last query row hold whatever follows in the q tensor
+    // (rows of other sequences), and a raise they triggered would change the rounding of the live rows' probabilities —
+    // results would depend on what a sequence is batched with.  (A dead row may overflow; nobody reads it.)
+    if (first || __any_sync(0xffffffffu, live && mx > kLazyThreshold)) {
         // first tile: the exact row maximum becomes the reference (may be negative).  later: raise by max(mx, 0).
         delta = first ? mx : fmaxf(mx, 0.f);
         const float corr = first ? 0.f : ex2_approx(-delta);
@@ -262,23 +265,23 @@ __device__ __forceinline__ void softmax_rest(uint32_t (&r)[64], float mx, float 
 template <int HD, bool ALIBI>
 __device__ __forceinline__ void softmax_tile(uint32_t (&r)[64], uint32_t o_addr, bool first, SmemBar p_empty_bar,
                                              uint32_t p_empty_parity, float scale, float slope, float qpos, int key0,
-                                             int Sk, float& m_ref, float& l, uint32_t p_row, int row, int lane) {
+                                             int Sk, float& m_ref, float& l, uint32_t p_row, int row, int lane, bool live) {
     const float base = first ? 0.f : m_ref;                  // exponents are first taken against `base`
     const float d0 = qpos - (float)key0;                     // query position minus the block's first key
     const int nvalid = Sk - key0;
     if (nvalid < kKB) {
         const float mx = exponents<3>(r, scale, ALIBI ? slope : 0.f, d0, base, nvalid);
-        softmax_rest<HD, 3, !ALIBI>(r, mx, base, scale, nvalid, o_addr, first, p_empty_bar, p_empty_parity, m_ref, l, p_row, row);
+        softmax_rest<HD, 3, !ALIBI>(r, mx, base, scale, nvalid, o_addr, first, p_empty_bar, p_empty_parity, m_ref, l, p_row, row, live);
     } else if constexpr (ALIBI) {
         float mx;
         if (__all_sync(0xffffffffu, d0 >= 63.f) || __all_sync(0xffffffffu, d0 <= 0.f))
             mx = exponents<1>(r, scale, slope, d0, base, nvalid);
         else
             mx = exponents<2>(r, scale, slope, d0, base, nvalid);
-        softmax_rest<HD, 1, !ALIBI>(r, mx, base, scale, nvalid, o_addr, first, p_empty_bar, p_empty_parity, m_ref, l, p_row, row);
+        softmax_rest<HD, 1, !ALIBI>(r, mx, base, scale, nvalid, o_addr, first, p_empty_bar, p_empty_parity, m_ref, l, p_row, row, live);
     } else {
         const float mx = exponents<0>(r, scale, 0.f, d0, base, nvalid);
-        softmax_rest<HD, 0, !ALIBI>(r, mx, base, scale, nvalid, o_addr, first, p_empty_bar, p_empty_parity, m_ref, l, p_row, row);
+        softmax_rest<HD, 0, !ALIBI>(r, mx, base, scale, nvalid, o_addr, first, p_empty_bar, p_empty_parity, m_ref, l, p_row, row, live);
     }
 }
 
@@ -619,7 +622,7 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 __syncwarp();
                 if (lane == 0) mbar_arrive(my_s_empty);
                 softmax_tile<HD, ALIBI>(r, o_addr, j == 0, my_p_empty, (m & 1) ^ 1, p.scale_log2, slope, qpos, j * kKB,
-                                        me.w, m_ref, l_run, my_p, row, lane);
+                                        me.w, m_ref, l_run, my_p, row, lane, row < me.y);
                 fence_proxy_async_smem();                     // generic-proxy P writes -> visible to the UMMA (async proxy)
                 tc_fence_before();                            // orders a possible tcgen05.st rescale before the PV
                 __syncwarp();
