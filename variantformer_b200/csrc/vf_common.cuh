@@ -275,6 +275,17 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
 
 // L2 prefetch of a 2-D tile (no shared-memory destination, no barrier): the tile is resident in L2 when ordinary
 // loads ask for it later.
+// TMA store of one box from shared memory (bulk async group): smem -> global, rows / columns past the tensor's extent
+// are clipped by the hardware.  The writer must make its generic-proxy shared-memory writes visible to the async proxy
+// first (fence_proxy_async_smem) and may overwrite the buffer only after tma_store_wait_read<N>().
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
                  ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1)

@@ -74,6 +74,7 @@ struct GemmParams {
     float ln_inv_d, ln_eps;  //                 1 / normalised width, eps
     float* stats_out;        // fp32 outputs: partial (sum, sum of squares) of every output row -> [M, 2*n_tiles, 2], or nullptr
     int tile_chunked;        // tile schedule: 1 = each unit walks a contiguous run of tiles (n fastest), 0 = round-robin
+    int tma_store;           // bf16 epilogues: slabs leave through cp.async.bulk.tensor stores (tmO) instead of per-lane stores
     int prefetch_resid;      // producer warp bulk-prefetches the residual tile into L2 (VF_GEMM_RESID_PREFETCH=1; off by
                              // default: measured 5-10 % slower than the epilogue's own one-slab-ahead register prefetch)
 };
@@ -145,10 +146,28 @@ struct RowStats {
 template <int EPI>
 __device__ __forceinline__ void epilogue_store_slab(const GemmParams& p, uint32_t stage, int row0, int col0, int n_out,
                                                     const float (&v)[32], int lane, const float4 (&rr4)[8],
-                                                    RowStats& rs) {
+                                                    RowStats& rs, const CUtensorMap* tmO = nullptr, int half_buf = 0) {
     // `stage` = shared-space address of the warp's 4 KB tile.  All reads of the transposed tile are issued as one batch
     // (no branch in between), then the global stores follow.
     if constexpr (epi_is_bf16<EPI>()) {
+        if (p.tma_store) {
+            // The slab leaves through ONE bulk tensor store: the staging layout ([32 rows][4 chunks of 16 B], chunk index
+            // XOR (row >> 1) & 3) is exactly SWIZZLE_64B, so the TMA unit reads it as it lies; rows / columns past M / N
+            // are clipped by the hardware.  The warp's 4 KB tile holds two bf16 slabs: while one is being read out by the
+            // TMA unit the next is written (at most one store group outstanding when a half is rewritten).
+            stage += half_buf * 2048;
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                sts128(stage + (lane * 4 + (j ^ ((lane >> 1) & 3))) * 16, pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]),
+                       pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]), pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]),
+                       pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(tmO, stage, col0, row0); tma_store_commit(); }
+            return;
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j)                                     // [32 rows][4 chunks of 16 B]
             sts128(stage + (lane * 4 + (j ^ ((lane >> 1) & 3))) * 16, pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]),
@@ -222,7 +241,8 @@ __device__ __forceinline__ void epilogue_store_slab(const GemmParams& p, uint32_
 template <int EPI, int CTAS>
 __global__ void __cluster_dims__(CTAS, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmR, const GemmParams p_in) {
+                    const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
+                    const GemmParams p_in) {
     // Local copy: the fields live in registers.  Read through the parameter itself they are re-fetched from the
     // constant bank (LDCU, a scoreboard wait each) after every asm statement with a memory clobber — in the epilogue
     // that is several times per slab.
@@ -271,6 +291,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if constexpr (EPI == VF_EPI_BIAS_RESID_F32) tma_prefetch_desc(&tmR);
+        if constexpr (epi_is_bf16<EPI>()) tma_prefetch_desc(&tmO);
         for (int s = 0; s < kStg; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         // the leader's tmem_empty collects the epilogue warps of BOTH CTAs of a pair
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kEpiWarps * CTAS); }
@@ -471,7 +492,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         f2_unpack(f2_mul(u23, f2_pack(y2, y3)), v[j + 2], v[j + 3]);
                     }
                     float4 none[8];
-                    epilogue_store_slab<EPI>(p, stage_out, row0, out0 + c * 32, n_out, v, lane, none, rs);
+                    epilogue_store_slab<EPI>(p, stage_out, row0, out0 + c * 32, n_out, v, lane, none, rs, &tmO, i & 1);
                 }
             } else if constexpr (EPI == VF_EPI_BIAS_RESID_F32) {
                 // The fp32 residual is the long-latency input of this epilogue (one DRAM round trip per slab) and it
@@ -552,7 +573,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
                     }
-                    epilogue_store_slab<EPI>(p, stage_out, row0, col0, n_out, v, lane, none, rs);
+                    epilogue_store_slab<EPI>(p, stage_out, row0, col0, n_out, v, lane, none, rs, &tmO, i & 1);
                 }
             }
             // all TMEM reads of this accumulator are complete (wait::ld above) -> hand it back to the MMA warp
@@ -569,6 +590,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     }
 
+    if constexpr (epi_is_bf16<EPI>()) tma_store_wait_read<0>();   // (no-op for threads that issued no bulk store)
     tc_fence_before();
     __syncthreads();
     if constexpr (CTAS == 2) cluster_sync_all();             // the leader's MMAs read the peer's shared memory until the end
@@ -683,6 +705,22 @@ static int make_tmap_kmajor(CUtensorMap* tm, const void* base, int rows, int col
     return 0;
 }
 
+// bf16 output [rows, cols] with row stride ld -> map with box {32 columns, 32 rows}, 64-byte swizzle: the layout of an
+// epilogue warp's staging slab.
+static int make_tmap_out_bf16(CUtensorMap* tm, void* base, int rows, int cols, int ld) {
+    PFN_encodeTiled enc = get_encode_fn();
+    VF_REQUIRE(enc, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VF_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (output) failed with CUresult %d (rows=%d cols=%d ld=%d)", (int)r,
+               rows, cols, ld);
+    return 0;
+}
+
 // fp32 residual [rows, cols] -> plain (unswizzled) map with box {64, 128}, used for L2 prefetch only.
 static int make_tmap_resid(CUtensorMap* tm, const float* base, int rows, int cols, int ld) {
     PFN_encodeTiled enc = get_encode_fn();
@@ -712,11 +750,12 @@ static int g_tile_chunked = -1;
 // faster than the single-CTA kernel at K = 1024 / 1536 (Wqkv 101k x 4608 x 1536: 1.03 -> 0.90 ms = 1590 TFLOP/s, cuBLAS
 // 0.91), not at K = 512 where the epilogue, not the operand traffic, is the limit.
 static int g_pair_min_rows = 1024, g_pair_min_k = 1024;
+static int g_tma_store = 1;
 static bool g_inited = false;
 
 template <int EPI>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const GemmParams& p,
-                     cudaStream_t s) {
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& to,
+                     const GemmParams& p, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
         VF_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -725,7 +764,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     }
     const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    gemm_tcgen05_kernel<EPI, 1><<<grid, kGemmThreads, kGemmSmem, s>>>(ta, tb, tr, p);
+    gemm_tcgen05_kernel<EPI, 1><<<grid, kGemmThreads, kGemmSmem, s>>>(ta, tb, tr, to, p);
     VF_LAUNCH_OK("gemm_tcgen05_kernel launch");
     return 0;
 }
@@ -733,8 +772,8 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
 // CTA-pair variant: grid = 2 x (number of pairs that can be co-scheduled, asked from the driver once)
 static int g_max_pairs = 0;
 template <int EPI>
-static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const GemmParams& p,
-                          cudaStream_t s) {
+static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& to,
+                          const GemmParams& p, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
         VF_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -755,7 +794,7 @@ static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CU
     }
     const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN - 1) / BN);
     const int pairs = tiles < g_max_pairs ? tiles : g_max_pairs;
-    gemm_tcgen05_kernel<EPI, 2><<<2 * pairs, kGemmThreads, kGemmSmem, s>>>(ta, tb, tr, p);
+    gemm_tcgen05_kernel<EPI, 2><<<2 * pairs, kGemmThreads, kGemmSmem, s>>>(ta, tb, tr, to, p);
     VF_LAUNCH_OK("gemm_tcgen05_kernel (CTA pair) launch");
     return 0;
 }
@@ -787,6 +826,8 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
         g_resid_prefetch = e2 && e2[0] == '1';
         const char* e5 = getenv("VF_GEMM_TILE_ORDER");
         if (e5) g_tile_chunked = e5[0] == 'c' ? 1 : e5[0] == 's' ? 0 : -1;
+        const char* e7 = getenv("VF_GEMM_TMA_STORE");
+        if (e7) g_tma_store = atoi(e7);
         const char* e3 = getenv("VF_GEMM_PAIR_MIN_ROWS");
         if (e3) g_pair_min_rows = atoi(e3);
         const char* e4 = getenv("VF_GEMM_PAIR_MIN_K");
@@ -838,21 +879,29 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
     } else {
         tr = ta;                                                       // never dereferenced
     }
+    // bf16 epilogues store through TMA (VF_GEMM_TMA_STORE=0: per-lane stores, for A/B runs); needs a 16-byte aligned
+    // output whose row stride keeps 16-byte alignment
+    CUtensorMap to = ta;
+    p.tma_store = 0;
+    if (out_bf16 && g_tma_store && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo % 8) == 0) {
+        if (make_tmap_out_bf16(&to, out, M, n_out, ldo)) return -1;
+        p.tma_store = 1;
+    }
     if (pair) {
         switch (epi) {
-            case VF_EPI_BIAS_BF16: return launch_tc_pair<VF_EPI_BIAS_BF16>(ta, tb, tr, p, stream);
-            case VF_EPI_BIAS_GEGLU_BF16: return launch_tc_pair<VF_EPI_BIAS_GEGLU_BF16>(ta, tb, tr, p, stream);
-            case VF_EPI_BIAS_RESID_F32: return launch_tc_pair<VF_EPI_BIAS_RESID_F32>(ta, tb, tr, p, stream);
-            case VF_EPI_BIAS_GELU_BF16: return launch_tc_pair<VF_EPI_BIAS_GELU_BF16>(ta, tb, tr, p, stream);
-            default: return launch_tc_pair<VF_EPI_BIAS_F32>(ta, tb, tr, p, stream);
+            case VF_EPI_BIAS_BF16: return launch_tc_pair<VF_EPI_BIAS_BF16>(ta, tb, tr, to, p, stream);
+            case VF_EPI_BIAS_GEGLU_BF16: return launch_tc_pair<VF_EPI_BIAS_GEGLU_BF16>(ta, tb, tr, to, p, stream);
+            case VF_EPI_BIAS_RESID_F32: return launch_tc_pair<VF_EPI_BIAS_RESID_F32>(ta, tb, tr, to, p, stream);
+            case VF_EPI_BIAS_GELU_BF16: return launch_tc_pair<VF_EPI_BIAS_GELU_BF16>(ta, tb, tr, to, p, stream);
+            default: return launch_tc_pair<VF_EPI_BIAS_F32>(ta, tb, tr, to, p, stream);
         }
     }
     switch (epi) {
-        case VF_EPI_BIAS_BF16: return launch_tc<VF_EPI_BIAS_BF16>(ta, tb, tr, p, stream);
-        case VF_EPI_BIAS_GEGLU_BF16: return launch_tc<VF_EPI_BIAS_GEGLU_BF16>(ta, tb, tr, p, stream);
-        case VF_EPI_BIAS_RESID_F32: return launch_tc<VF_EPI_BIAS_RESID_F32>(ta, tb, tr, p, stream);
-        case VF_EPI_BIAS_GELU_BF16: return launch_tc<VF_EPI_BIAS_GELU_BF16>(ta, tb, tr, p, stream);
-        default: return launch_tc<VF_EPI_BIAS_F32>(ta, tb, tr, p, stream);
+        case VF_EPI_BIAS_BF16: return launch_tc<VF_EPI_BIAS_BF16>(ta, tb, tr, to, p, stream);
+        case VF_EPI_BIAS_GEGLU_BF16: return launch_tc<VF_EPI_BIAS_GEGLU_BF16>(ta, tb, tr, to, p, stream);
+        case VF_EPI_BIAS_RESID_F32: return launch_tc<VF_EPI_BIAS_RESID_F32>(ta, tb, tr, to, p, stream);
+        case VF_EPI_BIAS_GELU_BF16: return launch_tc<VF_EPI_BIAS_GELU_BF16>(ta, tb, tr, to, p, stream);
+        default: return launch_tc<VF_EPI_BIAS_F32>(ta, tb, tr, to, p, stream);
     }
 }
 
