@@ -71,6 +71,19 @@ struct Params {
 #else
 #define VF_IDLE_WAIT mbar_wait
 #endif
+// Which lane of a softmax warp arrives on the warp's behalf: `elect.sync` needs no register and no S2R (the compiler does
+// not keep `lane` alive across the tile loop at 104 registers: it re-read SR_TID at every arrive).
+#ifndef VF_ATTN_ELECT
+#define VF_ATTN_ELECT 1
+#endif
+#if VF_ATTN_ELECT
+#define VF_ATTN_LEADER elect_one()
+#else
+#define VF_ATTN_LEADER (lane == 0)
+#endif
+#ifndef VF_ATTN_OPAQUE_SADDR
+#define VF_ATTN_OPAQUE_SADDR 1
+#endif
 #ifndef VF_ATTN_REGS_LO
 #define VF_ATTN_REGS_LO 32        // producer / MMA issuer warpgroup; 128 * LO + 256 * HI <= 384 * 80
 #define VF_ATTN_REGS_HI 104       // softmax warpgroups
@@ -81,6 +94,29 @@ struct Params {
 #ifndef VF_ATTN_ABLATE
 #define VF_ATTN_ABLATE 0          // timing experiments only (results are wrong): 1 no MUFU, 2 no P stores, 3 no TMEM loads
 #endif
+// 2^x for a PAIR of exponents (x <= ~0) on the FMA / ALU pipes instead of the MUFU: round(x) by the magic-number add,
+// 2^r on r = x - round(x) in [-0.5, 0.5] by a degree-3 minimax polynomial (7.5e-5 relative: 1/25 of the bf16 rounding P
+// gets right after), the integer part added into the exponent field.  10 instructions per pair (2 FMNMX clamps, 2 FADD2,
+// 4 FFMA2, 2 LEA) against 2 MUFU.EX2: used for every VF_ATTN_POLY_EVERY-th pair, because the softmax warps of an SM
+// sub-partition queue on the MUFU pipe (16 results/clk/SM) while their issue slots are half idle (ncu).
+#ifndef VF_ATTN_POLY_EVERY
+#define VF_ATTN_POLY_EVERY 0
+#endif
+__device__ __forceinline__ void ex2_poly_pair(float x0, float x1, float& p0, float& p1) {
+    const uint64_t x = f2_pack(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+    const uint64_t t = f2_add(x, f2_bcast(12582912.f));                      // 1.5 * 2^23 + round(x)
+    const uint64_t jf = f2_add(t, f2_bcast(-12582912.f));                    // round(x)
+    const uint64_t r = f2_fma(jf, f2_bcast(-1.f), x);
+    uint64_t q = f2_fma(f2_bcast(0.0551716685295105f), r, f2_bcast(0.2426111251115799f));
+    q = f2_fma(q, r, f2_bcast(0.6932609677314758f));
+    q = f2_fma(q, r, f2_bcast(0.9999280571937561f));
+    uint32_t t0, t1, q0, q1;
+    f2_unpack(t, t0, t1);
+    f2_unpack(q, q0, q1);
+    p0 = __uint_as_float(q0 + (t0 << 23));
+    p1 = __uint_as_float(q1 + (t1 << 23));
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
 #if VF_ATTN_ABLATE == 1
     return x * 0.001f;
@@ -191,7 +227,7 @@ __device__ __forceinline__ float exponents(uint32_t (&r)[64], float scale, float
 template <int HD, int KIND, bool PRESWZ>
 __device__ __forceinline__ void softmax_rest(uint32_t (&r)[64], float mx, float base, float scale, int nvalid,
                                              uint32_t o_addr, bool first, SmemBar p_empty_bar, uint32_t p_empty_parity,
-                                             float& m_ref, float& l, uint32_t p_row, int row, bool live) {
+                                             float& m_ref, float& l, uint32_t p_row, int row, float gate) {
     // The PV of this slot's previous step is the last reader of the P buffer and the last writer of O_s.  It was issued
     // at the end of the previous tile, so waiting for it HERE (before the exponentials) can stall every softmax warp
     // of the slot; only a raise of the reference maximum needs it this early (it rescales O_s).  The common path
@@ -201,7 +237,9 @@ __device__ __forceinline__ void softmax_rest(uint32_t (&r)[64], float mx, float 
     // Only LIVE rows vote: the rows of a tile past the sequence's last query row hold whatever follows in the q tensor
     // (rows of other sequences), and a raise they triggered would change the rounding of the live rows' probabilities —
     // results would depend on what a sequence is batched with.  (A dead row may overflow; nobody reads it.)
-    if (first || __any_sync(0xffffffffu, live && mx > kLazyThreshold)) {
+    // (`gate` = kLazyThreshold for a live row, +inf for a dead one: one register the caller sets once per item; a bool
+    // was recomputed from SR_TID at every tile.)
+    if (first || __any_sync(0xffffffffu, mx > gate)) {
         // first tile: the exact row maximum becomes the reference (may be negative).  later: raise by max(mx, 0).
         delta = first ? mx : fmaxf(mx, 0.f);
         const float corr = first ? 0.f : ex2_approx(-delta);
@@ -235,7 +273,13 @@ __device__ __forceinline__ void softmax_rest(uint32_t (&r)[64], float mx, float 
         float x0, x1;
         if constexpr (KIND == 0) f2_unpack(f2_fma(f2_pack(r[2 * i], r[2 * i + 1]), scale2, c2), x0, x1);
         else { x0 = __uint_as_float(r[2 * i]); x1 = __uint_as_float(r[2 * i + 1]); }
-        const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+        float p0, p1;
+        if (VF_ATTN_POLY_EVERY > 0 && (i % (VF_ATTN_POLY_EVERY > 0 ? VF_ATTN_POLY_EVERY : 1)) == (VF_ATTN_POLY_EVERY - 1)) {
+            ex2_poly_pair(x0, x1, p0, p1);
+        } else {
+            p0 = ex2_approx(x0);
+            p1 = ex2_approx(x1);
+        }
         if (i & 1) acc1 = f2_add(acc1, f2_pack(p0, p1));
         else acc0 = f2_add(acc0, f2_pack(p0, p1));
         r[i] = pack_bf16x2(p0, p1);
@@ -265,23 +309,23 @@ __device__ __forceinline__ void softmax_rest(uint32_t (&r)[64], float mx, float 
 template <int HD, bool ALIBI>
 __device__ __forceinline__ void softmax_tile(uint32_t (&r)[64], uint32_t o_addr, bool first, SmemBar p_empty_bar,
                                              uint32_t p_empty_parity, float scale, float slope, float qpos, int key0,
-                                             int Sk, float& m_ref, float& l, uint32_t p_row, int row, int lane, bool live) {
+                                             int Sk, float& m_ref, float& l, uint32_t p_row, int row, int lane, float gate) {
     const float base = first ? 0.f : m_ref;                  // exponents are first taken against `base`
     const float d0 = qpos - (float)key0;                     // query position minus the block's first key
     const int nvalid = Sk - key0;
     if (nvalid < kKB) {
         const float mx = exponents<3>(r, scale, ALIBI ? slope : 0.f, d0, base, nvalid);
-        softmax_rest<HD, 3, !ALIBI>(r, mx, base, scale, nvalid, o_addr, first, p_empty_bar, p_empty_parity, m_ref, l, p_row, row, live);
+        softmax_rest<HD, 3, !ALIBI>(r, mx, base, scale, nvalid, o_addr, first, p_empty_bar, p_empty_parity, m_ref, l, p_row, row, gate);
     } else if constexpr (ALIBI) {
         float mx;
         if (__all_sync(0xffffffffu, d0 >= 63.f) || __all_sync(0xffffffffu, d0 <= 0.f))
             mx = exponents<1>(r, scale, slope, d0, base, nvalid);
         else
             mx = exponents<2>(r, scale, slope, d0, base, nvalid);
-        softmax_rest<HD, 1, !ALIBI>(r, mx, base, scale, nvalid, o_addr, first, p_empty_bar, p_empty_parity, m_ref, l, p_row, row, live);
+        softmax_rest<HD, 1, !ALIBI>(r, mx, base, scale, nvalid, o_addr, first, p_empty_bar, p_empty_parity, m_ref, l, p_row, row, gate);
     } else {
         const float mx = exponents<0>(r, scale, 0.f, d0, base, nvalid);
-        softmax_rest<HD, 0, !ALIBI>(r, mx, base, scale, nvalid, o_addr, first, p_empty_bar, p_empty_parity, m_ref, l, p_row, row, live);
+        softmax_rest<HD, 0, !ALIBI>(r, mx, base, scale, nvalid, o_addr, first, p_empty_bar, p_empty_parity, m_ref, l, p_row, row, gate);
     }
 }
 
@@ -583,7 +627,13 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int quad = warp & 3;                            // TMEM lane quadrant of this warp
         const int row = quad * 32 + lane;                     // row inside the 128-row query tile
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
-        const uint32_t s_addr = t_lane + s * kKB, o_addr = t_lane + 128 + s * 64;
+        uint32_t s_addr = t_lane + s * kKB;
+        const uint32_t o_addr = t_lane + 128 + s * 64;
+#if VF_ATTN_OPAQUE_SADDR
+        // opaque: otherwise the address is REBUILT from SR_TID and the (spilled) TMEM base at every tile — S2R + LDL + 8
+        // integer instructions whose scoreboard waits were 6 % of the softmax warps' samples
+        asm volatile("mov.b32 %0, %0;" : "+r"(s_addr));
+#endif
         // this row of the P tile (shared-space address, 128-byte aligned) with the row's SWIZZLE_128B term folded in:
         // chunk q8 of the row lives at my_p ^ (q8 * 16)
         // (not in the ALiBi kernels: measured 3 % slower there, 0.6 % faster without the bias)
@@ -604,6 +654,8 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const float slope = ALIBI ? p.slopes[head] * 1.4426950408889634f : 0.f;
             const float qpos = (float)(qpos0 + row);
             float m_ref = 0.f, l_run = 0.f;
+            float gate = row < me.y ? kLazyThreshold : INFINITY;      // only live rows vote on a raise (softmax_rest)
+            asm volatile("mov.b32 %0, %0;" : "+f"(gate));
             for (int j = 0; j < my_nk; ++j) {
                 const uint32_t m = n_tiles++;
                 mbar_wait(my_s_full, m & 1);
@@ -620,13 +672,13 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #endif
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(my_s_empty);
+                if (VF_ATTN_LEADER) mbar_arrive(my_s_empty);
                 softmax_tile<HD, ALIBI>(r, o_addr, j == 0, my_p_empty, (m & 1) ^ 1, p.scale_log2, slope, qpos, j * kKB,
-                                        me.w, m_ref, l_run, my_p, row, lane, row < me.y);
+                                        me.w, m_ref, l_run, my_p, row, lane, gate);
                 fence_proxy_async_smem();                     // generic-proxy P writes -> visible to the UMMA (async proxy)
                 tc_fence_before();                            // orders a possible tcgen05.st rescale before the PV
                 __syncwarp();
-                if (lane == 0) mbar_arrive(my_p_full);
+                if (VF_ATTN_LEADER) mbar_arrive(my_p_full);
             }
             // ---- epilogue: O_s / l -> bf16 -> global ----
             mbar_wait(my_o_full, n_mine & 1);
@@ -639,7 +691,7 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(my_o_empty);          // O_s may be overwritten by the next item's first P V
+            if (VF_ATTN_LEADER) mbar_arrive(my_o_empty);          // O_s may be overwritten by the next item's first P V
             if (row < me.y) {
                 const float inv = 1.0f / l_run;
                 __nv_bfloat16* dst = p.o + (size_t)(me.x + row) * p.ldo + head * HD;
