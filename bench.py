@@ -284,6 +284,7 @@ class Bench:
         self.sd = random_init.make_state_dict(self.cfg, self.hp, seed=0, device=self.dev)
         self.engine = Engine(self.sd, self.cfg, self.hp, device=self.dev)
         self.peaks = load_peaks()
+        self.last_clocks = None
 
     def barrier(self):
         if self.world > 1:
@@ -308,7 +309,9 @@ class Bench:
         res = fn()
         e1.record()
         self.barrier()
-        return self.max_over_ranks(e0.elapsed_time(e1)), res, self.ops.launch_count() - n0, sampler.stop()
+        ms = self.max_over_ranks(e0.elapsed_time(e1))
+        self.last_clocks = sampler.stop()
+        return ms, res, self.ops.launch_count() - n0, self.last_clocks
 
     def time_wall(self, fn):
         self.barrier()
@@ -358,7 +361,24 @@ class Bench:
                 out["roofline"]["algorithmic_bytes_per_launch"] or 1.0, 1.0)
         others = []
         if "attention" in summ:
-            others.append(tensor_roofline("attention", "attention_mc_kernel (every attention of the path)"))
+            att = tensor_roofline("attention", "attention_mc_kernel (every attention of the path)")
+            # second bound of a softmax kernel: one ex2 per score on the MUFU pipe (16 results / clk / SM, measured:
+            # tools/ubench/ex2_rate.cu); a score costs 4 * head_dim tensor FLOPs, so at head dim 48 the MUFU ceiling is
+            # about half of the tensor peak.  Stated at the SM clock sampled during the timed region.
+            import re
+            exps = 0.0
+            for k, v in prof.summarize_detail().items():
+                m = re.search(r"attention .*hd=(\d+)", k)
+                if m:
+                    exps += v["flops"] / (4.0 * int(m.group(1)))
+            mhz = (self.last_clocks or {}).get("sm_mhz") or 0.0
+            if exps > 0 and mhz > 0 and summ["attention"]["ms"] > 0:
+                sms = torch.cuda.get_device_properties(self.local).multi_processor_count
+                t_min_ms = exps / (16.0 * sms * mhz * 1e6) * 1e3
+                ceil_tf = summ["attention"]["flops"] / (t_min_ms / 1e3) / 1e12
+                att["mufu_ceiling"] = {"tflops": ceil_tf, "frac_of_ceiling": att["achieved"] / ceil_tf, "sm_mhz": mhz,
+                                       "note": "one ex2 per score at 16/clk/SM; FLOPs per score = 4 x head_dim"}
+            others.append(att)
         s1 = [k for k in ("stage1_encode", "stage1_bpe", "stage1_bpe_cluster") if k in summ]
         if s1:
             ms = sum(summ[k]["ms"] for k in s1); by = sum(summ[k]["bytes"] for k in s1); n = sum(summ[k]["n"] for k in s1)
