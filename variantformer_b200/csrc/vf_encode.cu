@@ -597,11 +597,12 @@ int bpe_tokenize(const uint8_t* seq, int64_t pitch, const int32_t* len, int n_wi
                 (int)(pitch < (int64_t)max_len ? pitch : (int64_t)max_len)};
     if (max_len > kBpeSmemSyms) {
         // cluster path: CL CTAs per window, segment of the symbol array per CTA in shared memory.  16-CTA clusters (non
-        // portable size) put a slab's 8 gene windows on 128 SMs instead of 64; VF_BPE_CLUSTER=8 selects the portable size.
+        // portable size, VF_BPE_CLUSTER=16) put a slab's 8 gene windows on 128 SMs instead of 64 but the cluster barrier
+        // grows faster than the sweep shrinks: 3.1 ms against 2.6-2.8 ms per slab with the portable size (the default).
         static int cl = 0;
         if (cl == 0) {
             const char* e = getenv("VF_BPE_CLUSTER");
-            cl = (e && atoi(e) == 8) ? 8 : 16;
+            cl = (e && atoi(e) == 16) ? 16 : 8;
         }
         auto launch = [&](auto kern, int CL) -> int {
             const int seg_cap = (max_len + CL - 1) / CL + 32;
