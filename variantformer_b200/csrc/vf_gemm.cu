@@ -748,8 +748,11 @@ static int g_resid_prefetch = 0;
 static int g_tile_chunked = -1;
 // CTA-pair kernel for M >= g_pair_min_rows (VF_GEMM_PAIR_MIN_ROWS; 0 = never) and K >= g_pair_min_k: measured 6-12 %
 // faster than the single-CTA kernel at K = 1024 / 1536 (Wqkv 101k x 4608 x 1536: 1.03 -> 0.90 ms = 1590 TFLOP/s, cuBLAS
-// 0.91), not at K = 512 where the epilogue, not the operand traffic, is the limit.
-static int g_pair_min_rows = 1024, g_pair_min_k = 1024;
+// 0.91).  Round 1 kept K = 512 on the single-CTA kernel (its epilogue was the limit then); with the leaner epilogues of
+// round 2 (shared-memory column vectors, packed GeGLU, TMA stores) the operand traffic is the limit there too: 48 KB of
+// operands per 512-cycle k-step and SM against 32 KB for a pair — LN-folded Wqkv 1.11 M x 1536 x 512 1.61 -> 1.49 ms,
+// GeGLU1 x 2048 2.11-2.24 -> 1.95 ms (cuBLAS 1.44-1.64 / 2.02-2.31).
+static int g_pair_min_rows = 1024, g_pair_min_k = 512;
 static int g_tma_store = 1;
 static bool g_inited = false;
 
