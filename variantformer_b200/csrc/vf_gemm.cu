@@ -43,6 +43,10 @@
 #define VF_IDLE_WAIT mbar_wait
 #endif
 
+#ifndef VF_GEMM_INTERIOR_FAST
+#define VF_GEMM_INTERIOR_FAST 1
+#endif
+
 namespace vf {
 
 constexpr int BM = 128, BN = 256, BK = 64, kStages = 4;
@@ -94,6 +98,30 @@ constexpr bool epi_is_bf16() {
 // Issued as one batch well before they are needed so the (L2, see the producer's bulk prefetch) latency overlaps the
 // TMEM load and the staging writes (loads cannot be hoisted by the compiler itself: `out` may alias `resid`).
 __device__ __forceinline__ void load_resid_slab(const GemmParams& p, int row0, int col0, int lane, float4 (&rr4)[8]) {
+#if VF_GEMM_INTERIOR_FAST
+    // interior slab (warp-uniform test): one base pointer, constant row stride, no per-row predicates — the bounds
+    // checks, 64-bit address products and the branches around them were ~45 % of the residual epilogue's instructions
+    if (row0 + 32 <= p.M && col0 + 32 <= p.N) {
+        const int r = row0 + (lane >> 3), c = col0 + (lane & 7) * 4;
+        if (p.resid16) {
+            const __nv_bfloat16* src = p.resid16 + (size_t)r * p.ldr + c;
+            const size_t st = 4 * (size_t)p.ldr;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const uint2 h = *reinterpret_cast<const uint2*>(src + it * st);
+                rr4[it] = make_float4(__uint_as_float(h.x), __uint_as_float(h.y), 0.f, 0.f);
+            }
+            return;
+        }
+        if (p.resid) {
+            const float* src = p.resid + (size_t)r * p.ldr + c;
+            const size_t st = 4 * (size_t)p.ldr;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) rr4[it] = *reinterpret_cast<const float4*>(src + it * st);
+            return;
+        }
+    }
+#endif
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         const int grow = row0 + it * 4 + (lane >> 3), gcol = col0 + (lane & 7) * 4;
@@ -205,6 +233,36 @@ __device__ __forceinline__ void epilogue_store_slab(const GemmParams& p, uint32_
         __syncwarp();
         float* o = reinterpret_cast<float*>(p.out);
         const int gcol = col0 + (lane & 7) * 4;
+#if VF_GEMM_INTERIOR_FAST
+        if (row0 + 32 <= p.M && col0 + 32 <= n_out) {                   // interior slab (warp-uniform): see load_resid_slab
+            const int r = row0 + (lane >> 3);
+            float* op = o ? o + (size_t)r * p.ldo + gcol : nullptr;
+            __nv_bfloat16* mp = p.out2 ? p.out2 + (size_t)r * p.ldo2 + gcol : nullptr;
+            const size_t so = 4 * (size_t)p.ldo, sm = 4 * (size_t)p.ldo2;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                float4 f = make_float4(__uint_as_float(q[it].x), __uint_as_float(q[it].y), __uint_as_float(q[it].z),
+                                       __uint_as_float(q[it].w));
+                if constexpr (EPI == VF_EPI_BIAS_RESID_F32) {
+                    float4 rv = rr4[it];
+                    if (p.resid16) {
+                        const uint32_t hx = __float_as_uint(rv.x), hy = __float_as_uint(rv.y);
+                        rv = make_float4(__uint_as_float(hx << 16), __uint_as_float(hx & 0xffff0000u),
+                                         __uint_as_float(hy << 16), __uint_as_float(hy & 0xffff0000u));
+                    }
+                    f.x += rv.x; f.y += rv.y; f.z += rv.z; f.w += rv.w;
+                }
+                if (op) *reinterpret_cast<float4*>(op + it * so) = f;
+                if (mp) {
+                    uint2 h; h.x = pack_bf16x2(f.x, f.y); h.y = pack_bf16x2(f.z, f.w);
+                    *reinterpret_cast<uint2*>(mp + it * sm) = h;
+                }
+                rs.s1[it] += (f.x + f.y) + (f.z + f.w);
+                rs.s2[it] += fmaf(f.x, f.x, f.y * f.y) + fmaf(f.z, f.z, f.w * f.w);
+            }
+            return;
+        }
+#endif
         if (gcol + 4 <= n_out) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
