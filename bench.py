@@ -201,14 +201,20 @@ def run_reference(args):
     chroms, var, sets = make_workload(1234, 1, 1, args.cre, args.tissues, chrom_len=8_000_000)
     gene = sets[0][0]
     t_all = time.perf_counter()
-    for _ in range(args.warmup):
-        cpu_sample(sd, cfg, hp, chroms, var, gene, args.cre, 1)
+    warm = []                                                # warm-up samples at T = 2: a second tissue count for the line
+    for _ in range(args.warmup):                             # below when the timed steps cover only one (K = 1)
+        r = cpu_sample(sd, cfg, hp, chroms, var, gene, args.cre, 2)
+        warm.append((r["T"], r["t_model"]))
     pts, s1, t_timed = [], [], time.perf_counter()
     for i in range(args.steps):
         r = cpu_sample(sd, cfg, hp, chroms, var, gene, args.cre, CPU_SAMPLE_TISSUES[i % len(CPU_SAMPLE_TISSUES)])
         pts.append((r["T"], r["t_model"])); s1.append(r["t_stage1"])
     t_timed = time.perf_counter() - t_timed
-    v, base, marginal = fit_rate(pts, float(np.mean(s1)), args.tissues)
+    fit_pts = list(pts)
+    if len({p[0] for p in fit_pts}) < 2:                     # one tissue count cannot separate base from marginal cost
+        fit_pts += warm[-1:] if warm else [(lambda r: (r["T"], r["t_model"]))(
+            cpu_sample(sd, cfg, hp, chroms, var, gene, args.cre, 2))]
+    v, base, marginal = fit_rate(fit_pts, float(np.mean(s1)), args.tissues)
     cb = {"value": v, "unit": "predictions/s", "cores": os.cpu_count(), "kind": "port",
           "sample": (f"oracle port (C stage 1 + torch fp32 reference schedule): {args.steps} samples of 1 gene C={args.cre} "
                      f"G=200 at T in {CPU_SAMPLE_TISSUES} in rotation; least-squares line base={base:.1f}s "
