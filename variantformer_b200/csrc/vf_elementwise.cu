@@ -284,6 +284,70 @@ int embed_tokens(const int* ids, const int* pos, const float* emb, const float* 
     return 0;
 }
 
+// embed_tokens + center_rows in one pass (the coarse seq2reg entry point): a warp builds its token's row in registers,
+// takes the row mean, and writes the centred fp32 row, its bf16 mirror, the pivot and the first row statistics — the
+// uncentred rows (2.3 GB per benchmark slab) are never written and re-read.  Same arithmetic, same summation order as the
+// two kernels: bit-identical results.  NV = float4 per lane (d <= 128 * NV).
+template <int NV>
+__global__ void __launch_bounds__(256)
+embed_center_kernel(const int* __restrict__ ids, const int* __restrict__ pos, const float* __restrict__ emb,
+                    const float* __restrict__ pe, int n_tok, int d, float* __restrict__ x, float* __restrict__ pivot,
+                    float* __restrict__ stats, __nv_bfloat16* __restrict__ out) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_tok) return;
+    const int lane = threadIdx.x & 31;
+    const float* er = emb + (size_t)ids[row] * d;
+    const float* pr = pe ? pe + (size_t)pos[row] * d : nullptr;
+    float4 v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int c = lane * 4 + 128 * k;
+        if (c < d) {
+            float4 e = __ldg(reinterpret_cast<const float4*>(er + c));
+            if (pr) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(pr + c));
+                e.x += q.x; e.y += q.y; e.z += q.z; e.w += q.w;
+            }
+            v[k] = e;
+            s += (e.x + e.y) + (e.z + e.w);
+        }
+    }
+    const float mean = warp_sum(s) / (float)d;
+    s = 0.f;
+    float q2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int c = lane * 4 + 128 * k;
+        if (c < d) {
+            float4 e = v[k];
+            e.x -= mean; e.y -= mean; e.z -= mean; e.w -= mean;
+            *reinterpret_cast<float4*>(x + (size_t)row * d + c) = e;
+            s += (e.x + e.y) + (e.z + e.w);
+            q2 += fmaf(e.x, e.x, e.y * e.y) + fmaf(e.z, e.z, e.w * e.w);
+            uint2 pk; pk.x = pack_bf16x2(e.x, e.y); pk.y = pack_bf16x2(e.z, e.w);
+            *reinterpret_cast<uint2*>(out + (size_t)row * d + c) = pk;
+        }
+    }
+    s = warp_sum(s); q2 = warp_sum(q2);
+    if (lane == 0) { pivot[row] = mean; stats[2 * (size_t)row] = s; stats[2 * (size_t)row + 1] = q2; }
+}
+
+int embed_center(const int* ids, const int* pos, const float* emb, const float* pe, int n_tok, int d, float* x,
+                 float* pivot, float* stats, void* out_bf16, cudaStream_t s) {
+    if (n_tok == 0) return 0;
+    if (d % 4 != 0 || d > 1024 || !out_bf16) {               // shapes the register form does not cover: the two kernels
+        if (int rc = embed_tokens(ids, pos, emb, pe, n_tok, d, x, s)) return rc;
+        return center_rows(x, d, n_tok, d, pivot, stats, out_bf16, d, s);
+    }
+    const int grid = (n_tok + 7) / 8;
+    if (d <= 512) embed_center_kernel<4><<<grid, 256, 0, s>>>(ids, pos, emb, pe, n_tok, d, x, pivot, stats, (__nv_bfloat16*)out_bf16);
+    else embed_center_kernel<8><<<grid, 256, 0, s>>>(ids, pos, emb, pe, n_tok, d, x, pivot, stats, (__nv_bfloat16*)out_bf16);
+    VF_LAUNCH_OK("embed_center_kernel launch");
+    return 0;
+}
+
+
 // ---------------------------------------------------------------------------------
 // Masked mean over each window's valid tokens (seq2reg/model.py:263-267).
 // One CTA per window; 0/0 -> NaN for an empty window, as upstream.

@@ -79,8 +79,7 @@ static int seq2reg_forward(const vf_seq2reg_weights_t& w, const int32_t* tokens,
     const int d = w.d, H = w.heads, hd = d / H, P = stats_parts(d), n = (int)n_tok, F = w.ffn_hidden;
     int rc;
     if ((rc = compact_tokens(tokens, pad_mask, cu, n_win, L, b.ids, b.pos, s))) return rc;
-    if ((rc = embed_tokens(b.ids, b.pos, w.emb, w.pe, n, d, b.x, s))) return rc;
-    if ((rc = center_rows(b.x, d, n, d, b.piv, b.xs0, b.xb, d, s))) return rc;
+    if ((rc = embed_center(b.ids, b.pos, w.emb, w.pe, n, d, b.x, b.piv, b.xs0, b.xb, s))) return rc;
     for (int l = 0; l < w.n_layers; ++l) {
         const vf_seq2reg_layer_t& Lr = w.layers[l];
         if ((rc = linear(Lr.qkv, b.xb, d, n, 3 * d, d, VF_EPI_BIAS_BF16, nullptr, 0, 0, b.qkv, 3 * d, nullptr, 0,

@@ -25,6 +25,8 @@ int compact_tokens(const int* tokens, const uint8_t* pad_mask, const int* cu, in
 int embed_tokens(const int* ids, const int* pos, const float* emb, const float* pe, int n_tok, int d, float* out,
                  cudaStream_t s);
 int center_rows(float* x, int ldx, int M, int d, float* pivot, float* stats, void* out_bf16, int ldo, cudaStream_t s);
+int embed_center(const int* ids, const int* pos, const float* emb, const float* pe, int n_tok, int d, float* x,
+                 float* pivot, float* stats, void* out_bf16, cudaStream_t s);
 int uncenter_rows(const float* x, int ldx, const float* pivot, const int* idx, int M, int d, float* out_f32,
                   void* out_bf16, int ldo, cudaStream_t s);
 int masked_meanpool(const float* x, int ldx, const int* cu, int n_win, int d, const float* pivot, void* out_bf16,
