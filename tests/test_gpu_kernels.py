@@ -137,7 +137,7 @@ def test_gemm_stats_out_and_layernorm_fold(M, N, K):
     assert torch.allclose(got3.float(), want3, atol=5e-2, rtol=3e-2), _describe_mismatch(got3.float(), want3, 5e-2)
 
 
-@pytest.mark.parametrize("M,N,K", [(515, 512, 512), (3000, 1536, 1024)])
+@pytest.mark.parametrize("M,N,K", [(515, 512, 512), (3000, 1536, 1024), (1301, 768, 512), (2049, 512, 1536), (1100, 1280, 512)])
 def test_gemm_bf16_residual_and_mirror_only(M, N, K):
     """Intra-layer temporaries: x1' = x1 + Linear(a) with x1 held in bf16, in place, only mirror + statistics written."""
     g = torch.Generator(device="cpu").manual_seed(M + N)

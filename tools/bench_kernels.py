@@ -60,15 +60,19 @@ def main():
             st = torch.empty(M, ops.stats_parts(N), 2, device=DEV)
             o2 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
             ms_full = timeit(lambda: ops.gemm(a, w, epi, bias=bias, resid=resid, out=out, out2=o2, stats_out=st))
+            # the out_proj configuration: bf16 residual (the stream's mirror), in place, mirror + statistics only
+            ms_r16 = timeit(lambda: ops.gemm(a, w, epi, bias=bias, resid=o2, out2=o2, stats_out=st, mirror_only=True))
             del o2
         else:
             st = torch.rand(M, 12, 2, device=DEV) / 12 + 1.0 / 12
             st[:, :, 1] += K / 12
             ms_full = timeit(lambda: ops.gemm(a, w, epi, bias=bias, out=out, ln=(st, bias, K, 1e-5)))
+        if epi != EPI_BIAS_RESID_F32:
+            ms_r16 = None
         ms_t = timeit(lambda: torch.matmul(a, w.t()))
         tf = 2.0 * M * N * K / ms / 1e9
         res.append(dict(kernel="gemm", name=name, M=M, N=N, K=K, epi=epi, ms=ms, tflops=tf, ms_engine_cfg=ms_full,
-                        tflops_engine_cfg=2.0 * M * N * K / ms_full / 1e9, cublas_ms=ms_t,
+                        tflops_engine_cfg=2.0 * M * N * K / ms_full / 1e9, ms_resid16_mirror_only=ms_r16, cublas_ms=ms_t,
                         cublas_tflops=2.0 * M * N * K / ms_t / 1e9))
         print(json.dumps(res[-1])); sys.stdout.flush()
         del a, w, out, resid

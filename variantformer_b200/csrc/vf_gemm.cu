@@ -61,6 +61,13 @@ constexpr uint32_t kColVecBytes = 2 * BN * 4;         // bias and LayerNorm colu
 // (no alignment slack: the dynamic shared memory of a kernel without static shared memory starts 1 KB aligned; the
 // kernel traps otherwise)
 constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + kEpiWarps * kStageOutBytes + 256 /*barriers*/ + kColVecBytes;
+// "RT" residual epilogue (CTA-pair kernel, bf16 residual in, bf16 mirror + row statistics out: the out_proj shapes): the
+// residual slabs come in by TMA into a per-warp ring (3 x 2 KB, SWIZZLE_64B) and the mirror slabs leave by TMA from a
+// 2 KB tile, so a warp owns 8 KB instead of 4; one operand stage (32 KB) pays for it.
+constexpr int kStagesPairRT = 5;
+constexpr uint32_t kStageOutBytesRT = 8192, kBarBytesRT = 512;
+constexpr size_t kGemmSmemRT = (size_t)kStagesPairRT * (kABytes + kBBytes / 2) + kEpiWarps * kStageOutBytesRT + kBarBytesRT + kColVecBytes;
+static_assert(kGemmSmemRT <= 227 * 1024, "shared memory budget (RT)");
 
 struct GemmParams {
     int M, N, K;
@@ -296,7 +303,7 @@ __device__ __forceinline__ void epilogue_store_slab(const GemmParams& p, uint32_
 // tile: each CTA stages its own 128 A rows and HALF of the W rows (32 KB per stage instead of 48: a third less
 // L2 -> SM operand traffic and room for more stages), the pair leader issues M=256 MMAs that read both CTAs' shared
 // memory and write each CTA's 128 accumulator rows into its own TMEM; every CTA runs its own epilogue.
-template <int EPI, int CTAS>
+template <int EPI, int CTAS, bool RT = false>
 __global__ void __cluster_dims__(CTAS, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
@@ -312,18 +319,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if (smem_u32(smem_raw) & 1023u) __trap();                // SWIZZLE_128B tiles need 1 KB alignment
-    constexpr int kStg = CTAS == 2 ? kStagesPair : kStages;
+    static_assert(!RT || (CTAS == 2 && EPI == VF_EPI_BIAS_RESID_F32), "RT is a variant of the pair kernel's residual epilogue");
+    constexpr int kStg = CTAS == 2 ? (RT ? kStagesPairRT : kStagesPair) : kStages;
     constexpr uint32_t kBBytesC = kBBytes / CTAS, kStageBytesC = kABytes + kBBytesC;
+    constexpr uint32_t kOutW = RT ? kStageOutBytesRT : kStageOutBytes;
     uint8_t* smem_a = smem;                                  // kStg x 16 KB
     uint8_t* smem_b = smem + kStg * kABytes;                 // kStg x 32 KB (16 KB per CTA of a pair)
-    uint8_t* smem_out = smem + kStg * kStageBytesC;          // kEpiWarps x 4 KB staging tiles
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + kEpiWarps * kStageOutBytes);
+    uint8_t* smem_out = smem + kStg * kStageBytesC;          // kEpiWarps x 4 KB staging tiles (RT: 8 KB)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + kEpiWarps * kOutW);
     uint64_t* full = bars;                 // [kStg]
     uint64_t* empty = bars + kStg;         // [kStg]
     uint64_t* tmem_full = bars + 2 * kStg;          // [2]
     uint64_t* tmem_empty = bars + 2 * kStg + 2;     // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStg + 4);
-    const uint32_t colvec = smem_u32(bars) + 256;            // [256] bias | [256] LayerNorm column sums (shared-space address)
+    uint64_t* rbars = bars + 2 * kStg + 6;                   // RT: [kEpiWarps][3] "residual slab landed"
+    const uint32_t colvec = smem_u32(bars) + (RT ? kBarBytesRT : 256u);   // [256] bias | [256] LayerNorm column sums (shared-space address)
 
     const int warp = threadIdx.x >> 5;
     // work unit = CTA (CTAS 1) or CTA pair (CTAS 2); `rank` = this CTA's half of the pair's 256 rows / 256 W rows
@@ -349,10 +359,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if constexpr (EPI == VF_EPI_BIAS_RESID_F32) tma_prefetch_desc(&tmR);
+        if constexpr (RT) tma_prefetch_desc(&tmO);
         if constexpr (epi_is_bf16<EPI>()) tma_prefetch_desc(&tmO);
         for (int s = 0; s < kStg; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         // the leader's tmem_empty collects the epilogue warps of BOTH CTAs of a pair
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kEpiWarps * CTAS); }
+        if constexpr (RT) for (int i = 0; i < kEpiWarps * 3; ++i) mbar_init(&rbars[i], 1);
         fence_barrier_init();
     }
     if constexpr (CTAS == 2) cluster_sync_all();             // both CTAs' barriers exist before anyone signals the peer's
@@ -442,14 +454,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int quad = warp & 3;
         const int half = (warp - kFirstEpiWarp) >> 2;
         const int lane = threadIdx.x & 31;
-        const uint32_t stage_out = smem_u32(smem_out + (warp - kFirstEpiWarp) * kStageOutBytes);
+        const uint32_t stage_out = smem_u32(smem_out + (warp - kFirstEpiWarp) * kOutW);
         constexpr int kSlabs = (EPI == VF_EPI_BIAS_GEGLU_BF16) ? 2 : 4;      // per warp per tile
         const int n_out = (EPI == VF_EPI_BIAS_GEGLU_BF16) ? p.N / 2 : p.N;
         const bool ln = epi_is_bf16<EPI>() && p.ln_stats != nullptr;
         const bool want_stats = !epi_is_bf16<EPI>() && p.stats_out != nullptr;
         RowStats rs;
         float4 rr4[4][8];                                     // residual of slab i of a tile (RESID epilogue only)
-        if constexpr (EPI == VF_EPI_BIAS_RESID_F32) {
+        // RT: slab stream of this warp: slab G = (tile G / 4 of the unit's schedule, column slab half + 2 * (G % 4)); ring
+        // slot G % 3; lane 0 keeps the loads of the next two slabs in flight.
+        const SmemBar rbar = smem_bar(rbars + (warp - kFirstEpiWarp) * 3);
+        uint32_t rt_g = 0;                                    // slabs consumed so far
+        auto rt_issue = [&](uint32_t G) {                     // (lane 0 only)
+            const int ti = (int)(G >> 2);
+            if (ti >= t_count) return;
+            const int tt = t_first + ti * t_step;
+            const int r0 = (tt / n_tiles) * BM * CTAS + rank * BM + quad * 32, c0 = (tt % n_tiles) * BN + (half + 2 * (int)(G & 3)) * 32;
+            const uint32_t k = G % 3;
+            mbar_arrive_expect_tx(rbar[k], 2048);
+            tma_load_2d(stage_out + k * 2048, &tmR, rbar[k], c0, r0);
+        };
+        if constexpr (RT) {
+            if (lane == 0) { rt_issue(0); rt_issue(1); }
+        }
+        if constexpr (EPI == VF_EPI_BIAS_RESID_F32 && !RT) {
             if (t_count > 0) {                                // prime the slab stream: slabs 0 and 1 of the first tile
                 const int m0f = (t_first / n_tiles) * BM * CTAS + rank * BM, n0f = (t_first % n_tiles) * BN;
                 load_resid_slab(p, m0f + quad * 32, n0f + half * 32, lane, rr4[0]);
@@ -552,6 +580,64 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     float4 none[8];
                     epilogue_store_slab<EPI>(p, stage_out, row0, out0 + c * 32, n_out, v, lane, none, rs, &tmO, i & 1);
                 }
+            } else if constexpr (RT) {
+                // acc + bias + residual in the accumulator's own layout (lane = row): the residual row comes out of the
+                // TMA-filled SWIZZLE_64B tile with four conflict-free 16-byte reads, the row statistics need no shuffles,
+                // the bf16 mirror leaves through one bulk tensor store per slab.  No transposed read-back, no per-row
+                // address arithmetic, no prefetch registers.
+                float st1 = 0.f, st2 = 0.f;
+                uint32_t r[32];
+#pragma unroll
+                for (int i = 0; i < kSlabs; ++i) {
+                    const int c = half + 2 * i;
+                    const int col0 = n0 + c * 32;
+                    const uint32_t k = rt_g % 3;
+                    if (lane == 0) rt_issue(rt_g + 2);        // slot (rt_g + 2) % 3 was read out one slab ago
+                    tmem_ld_32x32(t_row + c * 32, r);
+                    float4 bb[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) bb[j] = lds_f4(colvec + (c * 32 + 4 * j) * 4);
+                    mbar_wait(rbar[k], (rt_g / 3) & 1);
+                    uint4 rq[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        rq[j] = lds128(stage_out + k * 2048 + (lane * 4 + (j ^ ((lane >> 1) & 3))) * 16);
+                    tmem_ld_wait();
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t w[4] = {rq[j].x, rq[j].y, rq[j].z, rq[j].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int q = j * 8 + e * 2;
+                            const float4 b = bb[q >> 2];
+                            const float b0 = (q & 2) ? b.z : b.x, b1 = (q & 2) ? b.w : b.y;
+                            v[q] = (__uint_as_float(r[q]) + b0) + __uint_as_float(w[e] << 16);
+                            v[q + 1] = (__uint_as_float(r[q + 1]) + b1) + __uint_as_float(w[e] & 0xffff0000u);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        st1 += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
+                        st2 += fmaf(v[j], v[j], v[j + 1] * v[j + 1]) + fmaf(v[j + 2], v[j + 2], v[j + 3] * v[j + 3]);
+                    }
+                    // mirror slab -> the warp's out tile (SWIZZLE_64B as it lies) -> one bulk store
+                    const uint32_t ot = stage_out + 6144;
+                    if (lane == 0) tma_store_wait_read<0>();  // the previous slab's store has read the tile
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        sts128(ot + (lane * 4 + (j ^ ((lane >> 1) & 3))) * 16, pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]),
+                               pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]), pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]),
+                               pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) { tma_store_2d(&tmO, ot, col0, row0); tma_store_commit(); }
+                    ++rt_g;
+                }
+                if (want_stats && row0 + lane < p.M)
+                    *reinterpret_cast<float2*>(p.stats_out + 2 * ((size_t)(row0 + lane) * (2 * n_tiles) + (t % n_tiles) * 2 + half)) =
+                        make_float2(st1, st2);
             } else if constexpr (EPI == VF_EPI_BIAS_RESID_F32) {
                 // The fp32 residual is the long-latency input of this epilogue (one DRAM round trip per slab) and it
                 // does not depend on the MMA: the slab stream of this warp (4 per tile, tile after tile) keeps the
@@ -643,12 +729,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 else mbar_arrive(&tmem_empty[acc]);
             }
             if constexpr (!epi_is_bf16<EPI>()) {
-                if (want_stats) rs.flush(p.stats_out, row0, p.M, (t % n_tiles) * 2 + half, 2 * n_tiles, lane);
+                if (!RT && want_stats) rs.flush(p.stats_out, row0, p.M, (t % n_tiles) * 2 + half, 2 * n_tiles, lane);
             }
         }
     }
 
-    if constexpr (epi_is_bf16<EPI>()) tma_store_wait_read<0>();   // (no-op for threads that issued no bulk store)
+    if constexpr (epi_is_bf16<EPI>() || RT) tma_store_wait_read<0>();   // (no-op for threads that issued no bulk store)
     tc_fence_before();
     __syncthreads();
     if constexpr (CTAS == 2) cluster_sync_all();             // the leader's MMAs read the peer's shared memory until the end
@@ -812,6 +898,7 @@ static int g_tile_chunked = -1;
 // GeGLU1 x 2048 2.11-2.24 -> 1.95 ms (cuBLAS 1.44-1.64 / 2.02-2.31).
 static int g_pair_min_rows = 1024, g_pair_min_k = 512;
 static int g_tma_store = 1;
+static int g_rt = 1;                                    // TMA-staged out_proj epilogue (VF_GEMM_RT=0: register-prefetch path)
 static bool g_inited = false;
 
 template <int EPI>
@@ -832,30 +919,31 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
 
 // CTA-pair variant: grid = 2 x (number of pairs that can be co-scheduled, asked from the driver once)
 static int g_max_pairs = 0;
-template <int EPI>
+template <int EPI, bool RT = false>
 static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& to,
                           const GemmParams& p, cudaStream_t s) {
+    constexpr size_t kSmem = RT ? kGemmSmemRT : kGemmSmem;
     static bool attr_set = false;
     if (!attr_set) {
-        VF_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)kGemmSmem));
+        VF_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, 2, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)kSmem));
         attr_set = true;
     }
     if (g_max_pairs == 0) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(g_num_sms & ~1); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = kGemmSmem;
+        cfg.gridDim = dim3(g_num_sms & ~1); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = kSmem;
         cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 2;
         at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
         cfg.attrs = &at; cfg.numAttrs = 1;
         int n = 0;
-        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<EPI, 2>, &cfg);
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<EPI, 2, RT>, &cfg);
         g_max_pairs = (e == cudaSuccess && n > 0) ? n : g_num_sms / 2;
         if (g_max_pairs > g_num_sms / 2) g_max_pairs = g_num_sms / 2;
         (void)cudaGetLastError();
     }
     const int tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * ((p.N + BN - 1) / BN);
     const int pairs = tiles < g_max_pairs ? tiles : g_max_pairs;
-    gemm_tcgen05_kernel<EPI, 2><<<2 * pairs, kGemmThreads, kGemmSmem, s>>>(ta, tb, tr, to, p);
+    gemm_tcgen05_kernel<EPI, 2, RT><<<2 * pairs, kGemmThreads, kSmem, s>>>(ta, tb, tr, to, p);
     VF_LAUNCH_OK("gemm_tcgen05_kernel (CTA pair) launch");
     return 0;
 }
@@ -889,6 +977,8 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
         if (e5) g_tile_chunked = e5[0] == 'c' ? 1 : e5[0] == 's' ? 0 : -1;
         const char* e7 = getenv("VF_GEMM_TMA_STORE");
         if (e7) g_tma_store = atoi(e7);
+        const char* e8 = getenv("VF_GEMM_RT");
+        if (e8) g_rt = atoi(e8);
         const char* e3 = getenv("VF_GEMM_PAIR_MIN_ROWS");
         if (e3) g_pair_min_rows = atoi(e3);
         const char* e4 = getenv("VF_GEMM_PAIR_MIN_K");
@@ -947,6 +1037,14 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
     if (out_bf16 && g_tma_store && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo % 8) == 0) {
         if (make_tmap_out_bf16(&to, out, M, n_out, ldo)) return -1;
         p.tma_store = 1;
+    }
+    if (pair && g_rt && epi == VF_EPI_BIAS_RESID_F32 && resid_bf16 && !out && out2 && N % BN == 0 &&
+        (reinterpret_cast<uintptr_t>(resid) & 15) == 0 && (ldr % 8) == 0 && (reinterpret_cast<uintptr_t>(out2) & 15) == 0 &&
+        (ldo2 % 8) == 0) {
+        // out_proj shape: bf16 residual in, bf16 mirror + row statistics out -> TMA-staged epilogue (see kGemmSmemRT)
+        if (make_tmap_out_bf16(&tr, const_cast<void*>(resid), M, N, ldr)) return -1;
+        if (make_tmap_out_bf16(&to, out2, M, N, ldo2)) return -1;
+        return launch_tc_pair<VF_EPI_BIAS_RESID_F32, true>(ta, tb, tr, to, p, stream);
     }
     if (pair) {
         switch (epi) {
