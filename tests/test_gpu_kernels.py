@@ -155,6 +155,34 @@ def test_gemm_bf16_residual_and_mirror_only(M, N, K):
     assert torch.allclose(tot[:, 0], want.sum(1), atol=5e-2, rtol=1e-3) and torch.allclose(tot[:, 1], (want * want).sum(1), rtol=2e-3)
 
 
+@pytest.mark.parametrize("form", ["ffn2", "out_proj"])
+def test_gemm_residual_rows_do_not_depend_on_how_many_rows_are_batched(form):
+    """Which kernel a residual GEMM runs through depends on M (single CTA below 1024 rows, CTA pairs with the TMA-staged
+    epilogues above): values, mirror and row statistics of a row must be bit-identical either way, or results would depend
+    on how genes are batched (and the multi-GPU gather check could not be bit-exact)."""
+    g = torch.Generator(device="cpu").manual_seed(77)
+    M, N, K = 2304, 768, 512
+    a = (torch.randn(M, K, generator=g) * 0.5).to(DEV).bfloat16()
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV).bfloat16()
+    bias = torch.randn(N, generator=g).to(DEV)
+    x0 = (torch.randn(M, N, generator=g) * 3).to(DEV)
+
+    def run(rows):
+        st = torch.empty(rows, ops.stats_parts(N), 2, device=DEV)
+        if form == "ffn2":
+            x = x0[:rows].clone(); xb = torch.empty(rows, N, device=DEV, dtype=torch.bfloat16)
+            ops.gemm(a[:rows].contiguous(), w, EPI_BIAS_RESID_F32, bias=bias, resid=x, out=x, out2=xb, stats_out=st)
+            return x, xb, st
+        xb = x0[:rows].bfloat16().contiguous()
+        ops.gemm(a[:rows].contiguous(), w, EPI_BIAS_RESID_F32, bias=bias, resid=xb, out2=xb, stats_out=st, mirror_only=True)
+        return xb, xb, st
+    big = run(M)                                          # CTA pairs (TMA-staged epilogue)
+    small = run(640)                                      # single-CTA kernel (register-prefetch epilogue)
+    torch.cuda.synchronize()
+    for b, s_ in zip(big, small):
+        assert torch.equal(b[:640], s_)
+
+
 def test_rowstats_mirror():
     x = torch.randn(1001, 1536, device=DEV) * 2 + 0.5
     xb = torch.empty(1001, 1536, dtype=torch.bfloat16, device=DEV)

@@ -69,6 +69,30 @@ def main():
         torch.cuda.synchronize()
         print(f"M={M} N={N} K={K} out_proj (bf16 residual, mirror only): {n} launches, {int(bad.item())} differ; rel err vs fp32 {err:.1e}")
 
+    # the FFN2 configuration: fp32 residual stream updated IN PLACE + bf16 mirror + row statistics (the in-place TMA-staged
+    # epilogue when the CTA-pair kernel runs); the stream is restored before every launch
+    for (M, N, K) in [(40000, 512, 1024), (20000, 1536, 1024), (5000, 1536, 1024)]:
+        g = torch.Generator(device=DEV).manual_seed(M + N + 2)
+        a = torch.randn(M, K, device=DEV, generator=g).bfloat16(); w = torch.randn(N, K, device=DEV, generator=g).bfloat16()
+        bias = torch.randn(N, device=DEV, generator=g)
+        x0 = torch.randn(M, N, device=DEV, generator=g); x = x0.clone()
+        o2 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16); st = torch.empty(M, ops.stats_parts(N), 2, device=DEV)
+        ops.gemm(a, w, EPI_BIAS_RESID_F32, bias=bias, resid=x, out=x, out2=o2, stats_out=st)
+        ref, ref1, ref2 = x.clone(), o2.clone(), st.clone()
+        want = a.float() @ w.float().t() + bias + x0
+        err = float((ref - want).abs().max() / want.abs().max())
+        bad = torch.zeros((), dtype=torch.int64, device=DEV)
+        for i in range(n):
+            if i % 5 == 0:
+                with torch.cuda.stream(side):
+                    (junk @ junk).sum()
+            x.copy_(x0); o2.zero_(); st.zero_()
+            ops.gemm(a, w, EPI_BIAS_RESID_F32, bias=bias, resid=x, out=x, out2=o2, stats_out=st)
+            bad += ((x.view(torch.int32) != ref.view(torch.int32)).any().to(torch.int64) +
+                    (o2.view(torch.int16) != ref1.view(torch.int16)).any().to(torch.int64) + (st != ref2).any().to(torch.int64))
+        torch.cuda.synchronize()
+        print(f"M={M} N={N} K={K} FFN2 (fp32 stream in place + mirror + statistics): {n} launches, {int(bad.item())} differ; rel err vs fp32 {err:.1e}")
+
 
 if __name__ == "__main__":
     main()

@@ -64,10 +64,11 @@ constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + kEpiWarps * kStageO
 // "RT" residual epilogue (CTA-pair kernel, bf16 residual in, bf16 mirror + row statistics out: the out_proj shapes): the
 // residual slabs come in by TMA into a per-warp ring (3 x 2 KB, SWIZZLE_64B) and the mirror slabs leave by TMA from a
 // 2 KB tile, so a warp owns 8 KB instead of 4; one operand stage (32 KB) pays for it.
-constexpr int kStagesPairRT = 5;
-constexpr uint32_t kStageOutBytesRT = 8192, kBarBytesRT = 512;
+constexpr int kStagesPairRT = 5, kStagesPairRT2 = 4;      // (RT 2, the FFN2 form: 12 KB per warp, see the epilogue)
+constexpr uint32_t kStageOutBytesRT = 8192, kStageOutBytesRT2 = 12288, kBarBytesRT = 512;
 constexpr size_t kGemmSmemRT = (size_t)kStagesPairRT * (kABytes + kBBytes / 2) + kEpiWarps * kStageOutBytesRT + kBarBytesRT + kColVecBytes;
 static_assert(kGemmSmemRT <= 227 * 1024, "shared memory budget (RT)");
+static_assert((size_t)kStagesPairRT2 * (kABytes + kBBytes / 2) + kEpiWarps * kStageOutBytesRT2 + kBarBytesRT + kColVecBytes <= kGemmSmemRT, "RT 2 fits the RT budget");
 
 struct GemmParams {
     int M, N, K;
@@ -303,7 +304,7 @@ __device__ __forceinline__ void epilogue_store_slab(const GemmParams& p, uint32_
 // tile: each CTA stages its own 128 A rows and HALF of the W rows (32 KB per stage instead of 48: a third less
 // L2 -> SM operand traffic and room for more stages), the pair leader issues M=256 MMAs that read both CTAs' shared
 // memory and write each CTA's 128 accumulator rows into its own TMEM; every CTA runs its own epilogue.
-template <int EPI, int CTAS, bool RT = false>
+template <int EPI, int CTAS, int RT = 0>
 __global__ void __cluster_dims__(CTAS, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
@@ -319,10 +320,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if (smem_u32(smem_raw) & 1023u) __trap();                // SWIZZLE_128B tiles need 1 KB alignment
-    static_assert(!RT || (CTAS == 2 && EPI == VF_EPI_BIAS_RESID_F32), "RT is a variant of the pair kernel's residual epilogue");
-    constexpr int kStg = CTAS == 2 ? (RT ? kStagesPairRT : kStagesPair) : kStages;
+    static_assert(RT == 0 || (CTAS == 2 && EPI == VF_EPI_BIAS_RESID_F32), "RT is a variant of the pair kernel's residual epilogue");
+    constexpr int kStg = CTAS == 2 ? (RT == 2 ? kStagesPairRT2 : RT == 1 ? kStagesPairRT : kStagesPair) : kStages;
     constexpr uint32_t kBBytesC = kBBytes / CTAS, kStageBytesC = kABytes + kBBytesC;
-    constexpr uint32_t kOutW = RT ? kStageOutBytesRT : kStageOutBytes;
+    constexpr uint32_t kOutW = RT == 2 ? kStageOutBytesRT2 : RT == 1 ? kStageOutBytesRT : kStageOutBytes;
     uint8_t* smem_a = smem;                                  // kStg x 16 KB
     uint8_t* smem_b = smem + kStg * kABytes;                 // kStg x 32 KB (16 KB per CTA of a pair)
     uint8_t* smem_out = smem + kStg * kStageBytesC;          // kEpiWarps x 4 KB staging tiles (RT: 8 KB)
@@ -359,12 +360,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if constexpr (EPI == VF_EPI_BIAS_RESID_F32) tma_prefetch_desc(&tmR);
-        if constexpr (RT) tma_prefetch_desc(&tmO);
+        if constexpr (RT != 0) tma_prefetch_desc(&tmO);
         if constexpr (epi_is_bf16<EPI>()) tma_prefetch_desc(&tmO);
         for (int s = 0; s < kStg; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         // the leader's tmem_empty collects the epilogue warps of BOTH CTAs of a pair
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kEpiWarps * CTAS); }
-        if constexpr (RT) for (int i = 0; i < kEpiWarps * 3; ++i) mbar_init(&rbars[i], 1);
+        if constexpr (RT != 0) for (int i = 0; i < kEpiWarps * 3; ++i) mbar_init(&rbars[i], 1);
         fence_barrier_init();
     }
     if constexpr (CTAS == 2) cluster_sync_all();             // both CTAs' barriers exist before anyone signals the peer's
@@ -470,14 +471,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (ti >= t_count) return;
             const int tt = t_first + ti * t_step;
             const int r0 = (tt / n_tiles) * BM * CTAS + rank * BM + quad * 32, c0 = (tt % n_tiles) * BN + (half + 2 * (int)(G & 3)) * 32;
-            const uint32_t k = G % 3;
-            mbar_arrive_expect_tx(rbar[k], 2048);
-            tma_load_2d(stage_out + k * 2048, &tmR, rbar[k], c0, r0);
+            if constexpr (RT == 2) {                          // fp32 slabs: two 4 KB slots
+                const uint32_t k = G & 1;
+                mbar_arrive_expect_tx(rbar[k], 4096);
+                tma_load_2d(stage_out + k * 4096, &tmR, rbar[k], c0, r0);
+            } else {                                          // bf16 slabs: three 2 KB slots
+                const uint32_t k = G % 3;
+                mbar_arrive_expect_tx(rbar[k], 2048);
+                tma_load_2d(stage_out + k * 2048, &tmR, rbar[k], c0, r0);
+            }
         };
-        if constexpr (RT) {
+        if constexpr (RT == 1) {
             if (lane == 0) { rt_issue(0); rt_issue(1); }
         }
-        if constexpr (EPI == VF_EPI_BIAS_RESID_F32 && !RT) {
+        if constexpr (RT == 2) {
+            if (lane == 0) rt_issue(0);
+        }
+        if constexpr (EPI == VF_EPI_BIAS_RESID_F32 && RT == 0) {
             if (t_count > 0) {                                // prime the slab stream: slabs 0 and 1 of the first tile
                 const int m0f = (t_first / n_tiles) * BM * CTAS + rank * BM, n0f = (t_first % n_tiles) * BN;
                 load_resid_slab(p, m0f + quad * 32, n0f + half * 32, lane, rr4[0]);
@@ -580,12 +590,79 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     float4 none[8];
                     epilogue_store_slab<EPI>(p, stage_out, row0, out0 + c * 32, n_out, v, lane, none, rs, &tmO, i & 1);
                 }
-            } else if constexpr (RT) {
+            } else if constexpr (RT == 2) {
+                // FFN2 form, IN PLACE (out == resid: the fp32 stream): a slab's residual arrives by TMA in a SWIZZLE_128B
+                // tile, the sum is formed in the accumulator's layout (lane = row) and written back into the same tile,
+                // which then leaves by a bulk tensor store through the same tensor map; the mirror leaves from a 2 KB
+                // SWIZZLE_64B tile.  Two fp32 slots and two mirror tiles per warp: while slab G is computed, slot G ^ 1
+                // (stored at the end of slab G - 1) is refilled with slab G + 1 — a lead of one slab (2-4 us, several DRAM
+                // round trips).
+                // Row statistics in EXACTLY the association of the register-prefetch epilogue (RowStats: one partial per
+                // group of four columns, slabs added in order, then ((S0+S4)+(S2+S6)) + ((S1+S5)+(S3+S7))): which kernel a
+                // GEMM runs through depends on M, and results must not depend on how rows are batched.
+                float st1[8], st2[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { st1[j] = 0.f; st2[j] = 0.f; }
+                uint32_t r[32];
+#pragma unroll
+                for (int i = 0; i < kSlabs; ++i) {
+                    const int c = half + 2 * i;
+                    const int col0 = n0 + c * 32;
+                    const uint32_t k = rt_g & 1;
+                    const uint32_t slot = stage_out + k * 4096, mt = stage_out + 8192 + k * 2048;
+                    if (lane == 0) { tma_store_wait_read<0>(); rt_issue(rt_g + 1); }   // slot k ^ 1 has been read out
+                    tmem_ld_32x32(t_row + c * 32, r);
+                    float4 bb[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) bb[j] = lds_f4(colvec + (c * 32 + 4 * j) * 4);
+                    mbar_wait(rbar[k], (rt_g >> 1) & 1);
+                    float4 rq[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) rq[j] = lds_f4(slot + (lane * 8 + (j ^ (lane & 7))) * 16);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 f;
+                        f.x = (__uint_as_float(r[4 * j + 0]) + bb[j].x) + rq[j].x;
+                        f.y = (__uint_as_float(r[4 * j + 1]) + bb[j].y) + rq[j].y;
+                        f.z = (__uint_as_float(r[4 * j + 2]) + bb[j].z) + rq[j].z;
+                        f.w = (__uint_as_float(r[4 * j + 3]) + bb[j].w) + rq[j].w;
+                        st1[j] += (f.x + f.y) + (f.z + f.w);
+                        st2[j] += fmaf(f.x, f.x, f.y * f.y) + fmaf(f.z, f.z, f.w * f.w);
+                        rq[j] = f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        sts128(slot + (lane * 8 + (j ^ (lane & 7))) * 16, __float_as_uint(rq[j].x), __float_as_uint(rq[j].y),
+                               __float_as_uint(rq[j].z), __float_as_uint(rq[j].w));
+                    if (p.out2) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            sts128(mt + (lane * 4 + (j ^ ((lane >> 1) & 3))) * 16, pack_bf16x2(rq[2 * j].x, rq[2 * j].y),
+                                   pack_bf16x2(rq[2 * j].z, rq[2 * j].w), pack_bf16x2(rq[2 * j + 1].x, rq[2 * j + 1].y),
+                                   pack_bf16x2(rq[2 * j + 1].z, rq[2 * j + 1].w));
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmR, slot, col0, row0);
+                        if (p.out2) tma_store_2d(&tmO, mt, col0, row0);
+                        tma_store_commit();
+                    }
+                    ++rt_g;
+                }
+                if (want_stats && row0 + lane < p.M)
+                    *reinterpret_cast<float2*>(p.stats_out + 2 * ((size_t)(row0 + lane) * (2 * n_tiles) + (t % n_tiles) * 2 + half)) =
+                        make_float2(((st1[0] + st1[4]) + (st1[2] + st1[6])) + ((st1[1] + st1[5]) + (st1[3] + st1[7])),
+                                    ((st2[0] + st2[4]) + (st2[2] + st2[6])) + ((st2[1] + st2[5]) + (st2[3] + st2[7])));
+            } else if constexpr (RT == 1) {
                 // acc + bias + residual in the accumulator's own layout (lane = row): the residual row comes out of the
                 // TMA-filled SWIZZLE_64B tile with four conflict-free 16-byte reads, the row statistics need no shuffles,
                 // the bf16 mirror leaves through one bulk tensor store per slab.  No transposed read-back, no per-row
                 // address arithmetic, no prefetch registers.
-                float st1 = 0.f, st2 = 0.f;
+                float st1[8], st2[8];                         // (same association as RowStats, see the FFN2 form above)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { st1[j] = 0.f; st2[j] = 0.f; }
                 uint32_t r[32];
 #pragma unroll
                 for (int i = 0; i < kSlabs; ++i) {
@@ -618,8 +695,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        st1 += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
-                        st2 += fmaf(v[j], v[j], v[j + 1] * v[j + 1]) + fmaf(v[j + 2], v[j + 2], v[j + 3] * v[j + 3]);
+                        st1[j >> 2] += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
+                        st2[j >> 2] += fmaf(v[j], v[j], v[j + 1] * v[j + 1]) + fmaf(v[j + 2], v[j + 2], v[j + 3] * v[j + 3]);
                     }
                     // mirror slab -> the warp's out tile (SWIZZLE_64B as it lies) -> one bulk store
                     const uint32_t ot = stage_out + 6144;
@@ -637,7 +714,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 if (want_stats && row0 + lane < p.M)
                     *reinterpret_cast<float2*>(p.stats_out + 2 * ((size_t)(row0 + lane) * (2 * n_tiles) + (t % n_tiles) * 2 + half)) =
-                        make_float2(st1, st2);
+                        make_float2(((st1[0] + st1[4]) + (st1[2] + st1[6])) + ((st1[1] + st1[5]) + (st1[3] + st1[7])),
+                                    ((st2[0] + st2[4]) + (st2[2] + st2[6])) + ((st2[1] + st2[5]) + (st2[3] + st2[7])));
             } else if constexpr (EPI == VF_EPI_BIAS_RESID_F32) {
                 // The fp32 residual is the long-latency input of this epilogue (one DRAM round trip per slab) and it
                 // does not depend on the MMA: the slab stream of this warp (4 per tile, tile after tile) keeps the
@@ -729,12 +807,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 else mbar_arrive(&tmem_empty[acc]);
             }
             if constexpr (!epi_is_bf16<EPI>()) {
-                if (!RT && want_stats) rs.flush(p.stats_out, row0, p.M, (t % n_tiles) * 2 + half, 2 * n_tiles, lane);
+                if (RT == 0 && want_stats) rs.flush(p.stats_out, row0, p.M, (t % n_tiles) * 2 + half, 2 * n_tiles, lane);
             }
         }
     }
 
-    if constexpr (epi_is_bf16<EPI>() || RT) tma_store_wait_read<0>();   // (no-op for threads that issued no bulk store)
+    if constexpr (epi_is_bf16<EPI>() || RT != 0) tma_store_wait_read<0>();   // (no-op for threads that issued no bulk store)
     tc_fence_before();
     __syncthreads();
     if constexpr (CTAS == 2) cluster_sync_all();             // the leader's MMAs read the peer's shared memory until the end
@@ -851,6 +929,21 @@ static int make_tmap_kmajor(CUtensorMap* tm, const void* base, int rows, int col
 
 // bf16 output [rows, cols] with row stride ld -> map with box {32 columns, 32 rows}, 64-byte swizzle: the layout of an
 // epilogue warp's staging slab.
+// fp32 [rows, cols] tile map, box 32 x 32 (128-byte rows), SWIZZLE_128B: the in-place slabs of the RT == 2 epilogue
+static int make_tmap_slab_f32(CUtensorMap* tm, void* base, int rows, int cols, int ld) {
+    PFN_encodeTiled enc = get_encode_fn();
+    VF_REQUIRE(enc, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VF_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp32 slab) failed with CUresult %d (rows=%d cols=%d ld=%d)", (int)r,
+               rows, cols, ld);
+    return 0;
+}
+
 static int make_tmap_out_bf16(CUtensorMap* tm, void* base, int rows, int cols, int ld) {
     PFN_encodeTiled enc = get_encode_fn();
     VF_REQUIRE(enc, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
@@ -898,7 +991,7 @@ static int g_tile_chunked = -1;
 // GeGLU1 x 2048 2.11-2.24 -> 1.95 ms (cuBLAS 1.44-1.64 / 2.02-2.31).
 static int g_pair_min_rows = 1024, g_pair_min_k = 512;
 static int g_tma_store = 1;
-static int g_rt = 1;                                    // TMA-staged out_proj epilogue (VF_GEMM_RT=0: register-prefetch path)
+static int g_rt = 3;                                    // TMA-staged residual epilogues: bit 0 out_proj form, bit 1 in-place FFN2 form (VF_GEMM_RT)
 static bool g_inited = false;
 
 template <int EPI>
@@ -919,7 +1012,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
 
 // CTA-pair variant: grid = 2 x (number of pairs that can be co-scheduled, asked from the driver once)
 static int g_max_pairs = 0;
-template <int EPI, bool RT = false>
+template <int EPI, int RT = 0>
 static int launch_tc_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& to,
                           const GemmParams& p, cudaStream_t s) {
     constexpr size_t kSmem = RT ? kGemmSmemRT : kGemmSmem;
@@ -1038,13 +1131,21 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
         if (make_tmap_out_bf16(&to, out, M, n_out, ldo)) return -1;
         p.tma_store = 1;
     }
-    if (pair && g_rt && epi == VF_EPI_BIAS_RESID_F32 && resid_bf16 && !out && out2 && N % BN == 0 &&
+    if (pair && (g_rt & 1) && epi == VF_EPI_BIAS_RESID_F32 && resid_bf16 && !out && out2 && N % BN == 0 &&
         (reinterpret_cast<uintptr_t>(resid) & 15) == 0 && (ldr % 8) == 0 && (reinterpret_cast<uintptr_t>(out2) & 15) == 0 &&
         (ldo2 % 8) == 0) {
         // out_proj shape: bf16 residual in, bf16 mirror + row statistics out -> TMA-staged epilogue (see kGemmSmemRT)
         if (make_tmap_out_bf16(&tr, const_cast<void*>(resid), M, N, ldr)) return -1;
         if (make_tmap_out_bf16(&to, out2, M, N, ldo2)) return -1;
-        return launch_tc_pair<VF_EPI_BIAS_RESID_F32, true>(ta, tb, tr, to, p, stream);
+        return launch_tc_pair<VF_EPI_BIAS_RESID_F32, 1>(ta, tb, tr, to, p, stream);
+    }
+    if (pair && (g_rt & 2) && epi == VF_EPI_BIAS_RESID_F32 && resid && !resid_bf16 && out == resid && ldo == ldr && N % BN == 0 &&
+        (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo % 4) == 0 &&
+        (!out2 || ((reinterpret_cast<uintptr_t>(out2) & 15) == 0 && (ldo2 % 8) == 0))) {
+        // FFN2 form, in place on the fp32 stream (+ mirror, statistics)
+        if (make_tmap_slab_f32(&tr, out, M, N, ldo)) return -1;
+        if (out2 && make_tmap_out_bf16(&to, out2, M, N, ldo2)) return -1;
+        return launch_tc_pair<VF_EPI_BIAS_RESID_F32, 2>(ta, tb, tr, to, p, stream);
     }
     if (pair) {
         switch (epi) {
